@@ -1,0 +1,94 @@
+// Shared helpers for libcse_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/cse.h"
+
+namespace cse {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define CSE_CUDA(call)                                                          \
+  do {                                                                          \
+    cudaError_t _e = (call);                                                    \
+    if (_e != cudaSuccess) return ::cse::cuda_fail(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define CSE_REQUIRE(cond, ...)                    \
+  do {                                            \
+    if (!(cond)) {                                \
+      ::cse::set_error(__VA_ARGS__);              \
+      return CSE_ERR_INVALID;                     \
+    }                                             \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t dtype_size(int dt) { return dt == CSE_F32 ? 4 : (dt == CSE_BF16 ? 2 : 1); }
+
+// ---- dtype load/store helpers ------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// Geometry of one conv / pool launch (per clip dims; batch n is separate).
+struct WinGeom {
+  int Di, Hi, Wi, Ci, in_ld;
+  int Do, Ho, Wo, Co, out_ld;
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+};
+
+// Epilogue description shared by both conv engines.
+struct Epilogue {
+  const float* scale0;   // [Co] or null (=1)
+  const float* shift0;   // [Co] or null (=0)
+  const float* scale1;   // [Co] or null
+  const float* shift1;   // [Co] or null
+  const void* res;       // residual (same dtype as out), or null
+  int res_ld;
+  void* out0;
+  void* out1;            // null = none
+  int out1_ld;
+  int relu0, relu1;
+};
+
+// ---- launchers implemented in the .cu files ------------------------------------
+int launch_conv_direct(int in_dt, int w_dt, int out_dt, const void* in, const void* w, int n,
+                       const WinGeom& g, const Epilogue& ep, cudaStream_t st);
+int launch_pool(int dt, bool is_max, bool pad_is_zero, const void* in, void* out, int n,
+                const WinGeom& g, cudaStream_t st);
+int launch_affine(int dt, const void* in, int in_ld, void* out, int out_ld, long long pixels, int C,
+                  const float* scale, const float* shift, int relu, cudaStream_t st);
+int launch_add(int dt, const void* a, int a_ld, const void* b, int b_ld, void* out, int out_ld,
+               long long pixels, int C, cudaStream_t st);
+int launch_softmax(const float* in, float* out, int rows, int C, cudaStream_t st);
+int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int t0, int h0, int w0,
+                      int To, int Ho, int Wo, const float* mean3, const float* scale3, void* out,
+                      int out_dt, int out_ld, cudaStream_t st);
+
+// tcgen05 engine
+struct ConvTcDesc {            // built once at plan finalize
+  CUtensorMap tmap_a, tmap_b;
+  WinGeom g;
+  int kc, bn, n_tiles_n;       // K chunk (channels), N tile, number of N tiles
+  int kchunks;                 // chunks per tap = ceil(Ci/kc)
+  int brick[4];                // n,d,h,w
+  int tiles_d, tiles_h, tiles_w;
+  int stages;
+  size_t smem_bytes;
+  int max_batch;
+};
+int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, int max_batch, const WinGeom& g,
+                  int kc, int bn, const int brick[4]);
+int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);
+
+}  // namespace cse

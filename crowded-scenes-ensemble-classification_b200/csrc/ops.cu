@@ -1,0 +1,481 @@
+// HBM-bound kernels (preprocess, pooling, affine, add, softmax) and the CUDA-core
+// implicit-GEMM Conv3D ("direct" engine: any shape, fp32 accumulate; it is the FP32
+// parity path and the fallback for shapes the tcgen05 engine does not take).
+//
+// Semantics follow Keras 2.2.4 / TF 1.15 channels_last as used by the reference:
+//   Conv3D            train.py:653-658, 1230-1258, 1294-1298   cross-correlation, zero padding
+//   MaxPooling3D      train.py:1029-1187, 1233-1261, 1487      padded taps ignored
+//   AveragePooling3D  train.py:1215-1217, 1504-1507            'valid' mean
+//   BatchNormalization train.py:665, 1280                      x*inv + (beta-mean*inv)
+#include "common.cuh"
+
+namespace cse {
+
+// ============================================================================
+// direct conv
+// ============================================================================
+constexpr int DBM = 64, DBN = 64, DBK = 16;
+
+template <typename TI, typename TW, typename TO>
+__global__ void __launch_bounds__(256)
+conv_direct_kernel(const TI* __restrict__ in, const TW* __restrict__ w, long long M, int K,
+                   WinGeom g, Epilogue ep) {
+  __shared__ float As[DBK][DBM + 4];
+  __shared__ __align__(16) float Bs[DBK][DBN + 4];
+  __shared__ int r_n[DBM], r_d[DBM], r_h[DBM], r_w[DBM];
+
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * DBM;
+  const int n0 = blockIdx.y * DBN;
+
+  if (tid < DBM) {
+    long long m = m0 + tid;
+    if (m < M) {
+      int ow = (int)(m % g.Wo); long long t = m / g.Wo;
+      int oh = (int)(t % g.Ho); t /= g.Ho;
+      int od = (int)(t % g.Do); int nn = (int)(t / g.Do);
+      r_n[tid] = nn; r_d[tid] = od * g.sd - g.pd; r_h[tid] = oh * g.sh - g.ph; r_w[tid] = ow * g.sw - g.pw;
+    } else {
+      r_n[tid] = -1; r_d[tid] = 0; r_h[tid] = 0; r_w[tid] = 0;
+    }
+  }
+  __syncthreads();
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int tx = tid % 16, ty = tid / 16;
+  const int a_kk = tid % 16, a_r0 = tid / 16;
+  const int b_kk = tid / 16, b_c = (tid % 16) * 4;
+  const int khw = g.kh * g.kw;
+
+  for (int k0 = 0; k0 < K; k0 += DBK) {
+    // ---- A tile (gather) ----
+    {
+      int k = k0 + a_kk;
+      bool kval = k < K;
+      int tap = kval ? k / g.Ci : 0;
+      int c = kval ? k - tap * g.Ci : 0;
+      int fd = tap / khw; int rem = tap - fd * khw; int fh = rem / g.kw; int fw = rem - fh * g.kw;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int r = a_r0 + 16 * j;
+        float v = 0.f;
+        int nn = r_n[r];
+        if (kval && nn >= 0) {
+          int id = r_d[r] + fd, ih = r_h[r] + fh, iw = r_w[r] + fw;
+          if ((unsigned)id < (unsigned)g.Di && (unsigned)ih < (unsigned)g.Hi && (unsigned)iw < (unsigned)g.Wi) {
+            long long pix = (((long long)nn * g.Di + id) * g.Hi + ih) * g.Wi + iw;
+            v = to_f32(in[pix * g.in_ld + c]);
+          }
+        }
+        As[a_kk][r] = v;
+      }
+    }
+    // ---- B tile ----
+    {
+      int k = k0 + b_kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int col = n0 + b_c + j;
+        float v = 0.f;
+        if (k < K && col < g.Co) v = to_f32(w[(long long)k * g.Co + col]);
+        Bs[b_kk][b_c + j] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < DBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  TO* out0 = reinterpret_cast<TO*>(ep.out0);
+  TO* out1 = reinterpret_cast<TO*>(ep.out1);
+  const TO* res = reinterpret_cast<const TO*>(ep.res);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = n0 + tx * 4 + j;
+      if (col >= g.Co) continue;
+      float y = acc[i][j];
+      if (ep.scale0) y *= ep.scale0[col];
+      if (ep.shift0) y += ep.shift0[col];
+      if (res) y += to_f32(res[m * ep.res_ld + col]);
+      float y0 = ep.relu0 ? fmaxf(y, 0.f) : y;
+      out0[m * g.out_ld + col] = from_f32<TO>(y0);
+      if (out1) {
+        float z = y;
+        if (ep.scale1) z *= ep.scale1[col];
+        if (ep.shift1) z += ep.shift1[col];
+        if (ep.relu1) z = fmaxf(z, 0.f);
+        out1[m * ep.out1_ld + col] = from_f32<TO>(z);
+      }
+    }
+  }
+}
+
+template <typename TI, typename TW, typename TO>
+static int conv_direct_t(const void* in, const void* w, int n, const WinGeom& g, const Epilogue& ep,
+                         cudaStream_t st) {
+  long long M = (long long)n * g.Do * g.Ho * g.Wo;
+  int K = g.kd * g.kh * g.kw * g.Ci;
+  if (M == 0) return CSE_OK;
+  dim3 grid((unsigned)((M + DBM - 1) / DBM), (unsigned)ceil_div(g.Co, DBN));
+  conv_direct_kernel<TI, TW, TO><<<grid, 256, 0, st>>>(
+      reinterpret_cast<const TI*>(in), reinterpret_cast<const TW*>(w), M, K, g, ep);
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}
+
+int launch_conv_direct(int in_dt, int w_dt, int out_dt, const void* in, const void* w, int n,
+                       const WinGeom& g, const Epilogue& ep, cudaStream_t st) {
+  using bf = __nv_bfloat16;
+  if (in_dt == CSE_F32 && w_dt == CSE_F32 && out_dt == CSE_F32)
+    return conv_direct_t<float, float, float>(in, w, n, g, ep, st);
+  if (in_dt == CSE_BF16 && w_dt == CSE_BF16 && out_dt == CSE_BF16)
+    return conv_direct_t<bf, bf, bf>(in, w, n, g, ep, st);
+  if (in_dt == CSE_BF16 && w_dt == CSE_BF16 && out_dt == CSE_F32)
+    return conv_direct_t<bf, bf, float>(in, w, n, g, ep, st);
+  if (in_dt == CSE_BF16 && w_dt == CSE_F32 && out_dt == CSE_F32)
+    return conv_direct_t<bf, float, float>(in, w, n, g, ep, st);
+  set_error("conv direct: unsupported dtype combination in=%d w=%d out=%d", in_dt, w_dt, out_dt);
+  return CSE_ERR_INVALID;
+}
+
+// ============================================================================
+// pooling: one thread per (output pixel, V-channel vector)
+// ============================================================================
+template <typename T, int V> struct Vec;
+template <> struct Vec<float, 4> { using type = float4; };
+template <> struct Vec<float, 1> { using type = float; };
+template <> struct Vec<__nv_bfloat16, 8> { using type = uint4; };
+template <> struct Vec<__nv_bfloat16, 1> { using type = __nv_bfloat16; };
+
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T* p, float (&v)[V]) {
+  typename Vec<T, V>::type raw = *reinterpret_cast<const typename Vec<T, V>::type*>(p);
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = to_f32(e[i]);
+}
+template <typename T, int V>
+__device__ __forceinline__ void store_vec(T* p, const float (&v)[V]) {
+  typename Vec<T, V>::type raw;
+  T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < V; ++i) e[i] = from_f32<T>(v[i]);
+  *reinterpret_cast<typename Vec<T, V>::type*>(p) = raw;
+}
+
+template <typename T, int V, bool IS_MAX>
+__global__ void __launch_bounds__(256)
+pool_kernel(const T* __restrict__ in, T* __restrict__ out, long long total, WinGeom g, int pad_is_zero) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = g.Co / V;
+  int c = (int)(idx % cv) * V; long long t = idx / cv;
+  int ow = (int)(t % g.Wo); t /= g.Wo;
+  int oh = (int)(t % g.Ho); t /= g.Ho;
+  int od = (int)(t % g.Do); long long nn = t / g.Do;
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = IS_MAX ? -INFINITY : 0.f;
+  bool saw_pad = false;
+  for (int fd = 0; fd < g.kd; ++fd) {
+    int id = od * g.sd - g.pd + fd;
+    for (int fh = 0; fh < g.kh; ++fh) {
+      int ih = oh * g.sh - g.ph + fh;
+      for (int fw = 0; fw < g.kw; ++fw) {
+        int iw = ow * g.sw - g.pw + fw;
+        if ((unsigned)id < (unsigned)g.Di && (unsigned)ih < (unsigned)g.Hi && (unsigned)iw < (unsigned)g.Wi) {
+          long long pix = ((nn * g.Di + id) * g.Hi + ih) * g.Wi + iw;
+          float v[V];
+          load_vec<T, V>(in + pix * g.in_ld + c, v);
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] = IS_MAX ? fmaxf(acc[i], v[i]) : acc[i] + v[i];
+        } else {
+          saw_pad = true;
+        }
+      }
+    }
+  }
+  if (IS_MAX) {
+    if (saw_pad && pad_is_zero) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    }
+  } else {
+    const float inv = 1.f / (float)(g.kd * g.kh * g.kw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] *= inv;
+  }
+  long long opix = ((nn * g.Do + od) * g.Ho + oh) * g.Wo + ow;
+  store_vec<T, V>(out + opix * g.out_ld + c, acc);
+}
+
+template <typename T, int V>
+static int pool_t(bool is_max, bool pad_is_zero, const void* in, void* out, int n, const WinGeom& g,
+                  cudaStream_t st) {
+  long long total = (long long)n * g.Do * g.Ho * g.Wo * (g.Co / V);
+  if (total == 0) return CSE_OK;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (is_max)
+    pool_kernel<T, V, true><<<blocks, 256, 0, st>>>((const T*)in, (T*)out, total, g, pad_is_zero ? 1 : 0);
+  else
+    pool_kernel<T, V, false><<<blocks, 256, 0, st>>>((const T*)in, (T*)out, total, g, 0);
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}
+
+static bool vec_ok(int C, int in_ld, int out_ld, int V, const void* a, const void* b, size_t es) {
+  return C % V == 0 && in_ld % V == 0 && out_ld % V == 0 &&
+         ((uintptr_t)a % (V * es)) == 0 && ((uintptr_t)b % (V * es)) == 0;
+}
+
+int launch_pool(int dt, bool is_max, bool pad_is_zero, const void* in, void* out, int n,
+                const WinGeom& g, cudaStream_t st) {
+  CSE_REQUIRE(g.Ci == g.Co, "pool: channel mismatch %d vs %d", g.Ci, g.Co);
+  if (dt == CSE_F32) {
+    if (vec_ok(g.Co, g.in_ld, g.out_ld, 4, in, out, 4)) return pool_t<float, 4>(is_max, pad_is_zero, in, out, n, g, st);
+    return pool_t<float, 1>(is_max, pad_is_zero, in, out, n, g, st);
+  }
+  if (dt == CSE_BF16) {
+    if (vec_ok(g.Co, g.in_ld, g.out_ld, 8, in, out, 2))
+      return pool_t<__nv_bfloat16, 8>(is_max, pad_is_zero, in, out, n, g, st);
+    return pool_t<__nv_bfloat16, 1>(is_max, pad_is_zero, in, out, n, g, st);
+  }
+  set_error("pool: unsupported dtype %d", dt);
+  return CSE_ERR_INVALID;
+}
+
+// ============================================================================
+// affine (stand-alone BN +/- ReLU) and add
+// ============================================================================
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+affine_kernel(const T* __restrict__ in, int in_ld, T* __restrict__ out, int out_ld, long long total, int C,
+              const float* __restrict__ scale, const float* __restrict__ shift, int relu) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = C / V;
+  int c = (int)(idx % cv) * V; long long pix = idx / cv;
+  float v[V];
+  load_vec<T, V>(in + pix * in_ld + c, v);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float y = v[i];
+    if (scale) y *= scale[c + i];
+    if (shift) y += shift[c + i];
+    v[i] = relu ? fmaxf(y, 0.f) : y;
+  }
+  store_vec<T, V>(out + pix * out_ld + c, v);
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+add_kernel(const T* __restrict__ a, int a_ld, const T* __restrict__ b, int b_ld, T* __restrict__ out,
+           int out_ld, long long total, int C) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = C / V;
+  int c = (int)(idx % cv) * V; long long pix = idx / cv;
+  float x[V], y[V];
+  load_vec<T, V>(a + pix * a_ld + c, x);
+  load_vec<T, V>(b + pix * b_ld + c, y);
+#pragma unroll
+  for (int i = 0; i < V; ++i) x[i] += y[i];
+  store_vec<T, V>(out + pix * out_ld + c, x);
+}
+
+int launch_affine(int dt, const void* in, int in_ld, void* out, int out_ld, long long pixels, int C,
+                  const float* scale, const float* shift, int relu, cudaStream_t st) {
+  if (pixels == 0) return CSE_OK;
+  if (dt == CSE_F32) {
+    if (vec_ok(C, in_ld, out_ld, 4, in, out, 4)) {
+      long long total = pixels * (C / 4);
+      affine_kernel<float, 4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          (const float*)in, in_ld, (float*)out, out_ld, total, C, scale, shift, relu);
+    } else {
+      long long total = pixels * C;
+      affine_kernel<float, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          (const float*)in, in_ld, (float*)out, out_ld, total, C, scale, shift, relu);
+    }
+  } else if (dt == CSE_BF16) {
+    using bf = __nv_bfloat16;
+    if (vec_ok(C, in_ld, out_ld, 8, in, out, 2)) {
+      long long total = pixels * (C / 8);
+      affine_kernel<bf, 8><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          (const bf*)in, in_ld, (bf*)out, out_ld, total, C, scale, shift, relu);
+    } else {
+      long long total = pixels * C;
+      affine_kernel<bf, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          (const bf*)in, in_ld, (bf*)out, out_ld, total, C, scale, shift, relu);
+    }
+  } else {
+    set_error("affine: unsupported dtype %d", dt);
+    return CSE_ERR_INVALID;
+  }
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}
+
+int launch_add(int dt, const void* a, int a_ld, const void* b, int b_ld, void* out, int out_ld,
+               long long pixels, int C, cudaStream_t st) {
+  if (pixels == 0) return CSE_OK;
+  if (dt == CSE_F32) {
+    bool v = vec_ok(C, a_ld, out_ld, 4, a, out, 4) && b_ld % 4 == 0 && ((uintptr_t)b % 16) == 0;
+    if (v) {
+      long long total = pixels * (C / 4);
+      add_kernel<float, 4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          (const float*)a, a_ld, (const float*)b, b_ld, (float*)out, out_ld, total, C);
+    } else {
+      long long total = pixels * C;
+      add_kernel<float, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          (const float*)a, a_ld, (const float*)b, b_ld, (float*)out, out_ld, total, C);
+    }
+  } else if (dt == CSE_BF16) {
+    using bf = __nv_bfloat16;
+    bool v = vec_ok(C, a_ld, out_ld, 8, a, out, 2) && b_ld % 8 == 0 && ((uintptr_t)b % 16) == 0;
+    if (v) {
+      long long total = pixels * (C / 8);
+      add_kernel<bf, 8><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          (const bf*)a, a_ld, (const bf*)b, b_ld, (bf*)out, out_ld, total, C);
+    } else {
+      long long total = pixels * C;
+      add_kernel<bf, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          (const bf*)a, a_ld, (const bf*)b, b_ld, (bf*)out, out_ld, total, C);
+    }
+  } else {
+    set_error("add: unsupported dtype %d", dt);
+    return CSE_ERR_INVALID;
+  }
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}
+
+// ============================================================================
+// softmax: one warp per row, fp32, stable form (Keras softmax over the last axis)
+// ============================================================================
+__global__ void __launch_bounds__(128)
+softmax_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int C) {
+  int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float* x = in + (long long)row * C;
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, x[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) sum += expf(x[c] - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int c = lane; c < C; c += 32) out[(long long)row * C + c] = expf(x[c] - mx) / sum;
+}
+
+int launch_softmax(const float* in, float* out, int rows, int C, cudaStream_t st) {
+  if (rows == 0) return CSE_OK;
+  softmax_kernel<<<ceil_div(rows, 4), 128, 0, st>>>(in, out, rows, C);
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}
+
+// ============================================================================
+// clip pre-processing: uint8 NDHWC -> float (bf16 / fp32), optional crop + mean/scale,
+// output channel count padded with zeros up to out_ld.
+// Reference: frames are stored raw into an np.float32 batch (train.py:466-478):
+// crop = none, mean = 0, scale = 1.
+// ============================================================================
+struct PreArgs {
+  int T, H, W, C, t0, h0, w0, To, Ho, Wo, out_ld;
+  float mean[4], scale[4];
+};
+
+template <typename TO, int CO>
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const uint8_t* __restrict__ src, TO* __restrict__ out, long long total, PreArgs a) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int w = (int)(idx % a.Wo); long long t = idx / a.Wo;
+  int h = (int)(t % a.Ho); t /= a.Ho;
+  int d = (int)(t % a.To); long long nn = t / a.To;
+  long long spix = ((nn * a.T + (d + a.t0)) * a.H + (h + a.h0)) * a.W + (w + a.w0);
+  const uint8_t* s = src + spix * a.C;
+  __align__(16) TO v[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    float f = 0.f;
+    if (c < a.C) f = ((float)s[c] - a.mean[c]) * a.scale[c];
+    v[c] = from_f32<TO>(f);
+  }
+  TO* o = out + idx * a.out_ld;
+  if (CO * sizeof(TO) == 16) {
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(v);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CO; ++c) o[c] = v[c];
+  }
+}
+
+int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int t0, int h0, int w0,
+                      int To, int Ho, int Wo, const float* mean, const float* scale, void* out,
+                      int out_dt, int out_ld, cudaStream_t st) {
+  CSE_REQUIRE(C >= 1 && C <= 4, "preprocess: C=%d not in 1..4", C);
+  CSE_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + To <= T && h0 + Ho <= H && w0 + Wo <= W,
+              "preprocess: crop (%d,%d,%d)+(%d,%d,%d) outside clip (%d,%d,%d)", t0, h0, w0, To, Ho, Wo, T, H, W);
+  CSE_REQUIRE(out_ld >= C && out_ld <= 8, "preprocess: out_ld=%d must be in [C,8]", out_ld);
+  PreArgs a;
+  a.T = T; a.H = H; a.W = W; a.C = C; a.t0 = t0; a.h0 = h0; a.w0 = w0;
+  a.To = To; a.Ho = Ho; a.Wo = Wo; a.out_ld = out_ld;
+  for (int c = 0; c < 4; ++c) {
+    a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
+    a.scale[c] = (scale && c < C) ? scale[c] : 1.f;
+  }
+  long long total = (long long)n * To * Ho * Wo;
+  if (total == 0) return CSE_OK;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  using bf = __nv_bfloat16;
+#define PRE_CASE(TT, CO) preprocess_kernel<TT, CO><<<blocks, 256, 0, st>>>(src, (TT*)out, total, a)
+  if (out_dt == CSE_BF16) {
+    switch (out_ld) {
+      case 8: PRE_CASE(bf, 8); break;
+      case 4: PRE_CASE(bf, 4); break;
+      case 3: PRE_CASE(bf, 3); break;
+      case 2: PRE_CASE(bf, 2); break;
+      default: set_error("preprocess: bf16 out_ld=%d unsupported (2,3,4,8)", out_ld); return CSE_ERR_INVALID;
+    }
+  } else if (out_dt == CSE_F32) {
+    switch (out_ld) {
+      case 4: PRE_CASE(float, 4); break;
+      case 3: PRE_CASE(float, 3); break;
+      case 2: PRE_CASE(float, 2); break;
+      case 8: PRE_CASE(float, 8); break;
+      default: set_error("preprocess: f32 out_ld=%d unsupported (2,3,4,8)", out_ld); return CSE_ERR_INVALID;
+    }
+  } else {
+    set_error("preprocess: unsupported output dtype %d", out_dt);
+    return CSE_ERR_INVALID;
+  }
+#undef PRE_CASE
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}
+
+}  // namespace cse

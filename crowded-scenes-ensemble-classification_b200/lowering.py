@@ -1,0 +1,597 @@
+"""Graph -> device plan: fusion, engine selection, weight packing, buffer planning.
+
+The layer graph (graph.py, one node per Keras layer of the reference model) is lowered into
+the flat list of fused ``cse_op`` records that libcse_b200 executes:
+
+* Conv3D (+bias) [+BatchNormalization] [+ReLU]  -> one CONV3D op with a scale/shift/ReLU epilogue
+  (conv3d_bn train.py:646-668; Conv3D(activation='relu') train.py:1230-1258; _conv_bn_relu3D :1283)
+* add([shortcut, residual]) (train.py:1346)     -> folded into the residual conv's epilogue; the
+  following BN-ReLU of the next pre-activation block (_bn_relu train.py:1278) becomes the op's
+  second output, so each R3D block is two or three kernels
+* concatenate (Inception Mixed blocks, train.py:1048-1193) -> no kernel: every branch writes its
+  channel slice of the concat buffer
+* ZeroPadding3D + MaxPooling3D (train.py:1259-1261) -> one pool with 0-valued padding
+* Flatten -> view;  Dense -> CONV3D on [n,1,1,1,K];  softmax -> SOFTMAX op on fp32 logits
+* TwoStream feature concat + Dense (train.py:1006-1007) -> two chained Dense ops
+  (f_rgb @ W[:F] + b, then + f_flow @ W[F:]) so no concat copy exists
+
+Weight folding is done in float32 exactly like TF's non-fused BN: inv = gamma*rsqrt(var+eps);
+y = x*inv + (beta - mean*inv)  (SURVEY App. A.0).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import runtime as rt
+from .graph import Graph, Node, BN_EPS
+from .weights import check_weights
+
+ALIGN = 1024
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+@dataclass
+class Buf:
+    name: str
+    nbytes: int
+    first: int = 1 << 30
+    last: int = -1
+    offset: int = -1
+    pinned_to_end: bool = False
+
+
+@dataclass
+class TRef:
+    """A [n,D,H,W,C] view: channel slice [coff, coff+C) of a buffer whose pixels have ld channels."""
+    buf: Buf
+    coff: int
+    C: int
+    ld: int
+    dims: Tuple[int, int, int]
+    dtype: int
+
+    @property
+    def esize(self) -> int:
+        return 4 if self.dtype == rt.F32 else 2
+
+    def byte_off(self) -> int:
+        return self.buf.offset + self.coff * self.esize
+
+
+@dataclass
+class DevOp:
+    kind: int
+    name: str
+    in0: Optional[TRef] = None
+    in1: Optional[TRef] = None
+    out0: Optional[TRef] = None
+    out1: Optional[TRef] = None
+    engine: int = 0
+    w_dtype: int = 0
+    k: Tuple[int, int, int] = (1, 1, 1)
+    s: Tuple[int, int, int] = (1, 1, 1)
+    pad: Tuple[int, int, int] = (0, 0, 0)
+    relu0: int = 0
+    relu1: int = 0
+    pad_is_zero: int = 0
+    ext_input: int = 0
+    crop: Tuple[int, int, int] = (0, 0, 0)
+    src_dims: Tuple[int, int, int, int] = (0, 0, 0, 0)
+    pre_mean: Tuple[float, ...] = (0.0, 0.0, 0.0, 0.0)
+    pre_scale: Tuple[float, ...] = (1.0, 1.0, 1.0, 1.0)
+    kc: int = 0
+    bn: int = 0
+    brick: Tuple[int, int, int, int] = (0, 0, 0, 0)
+    w_blob: int = -1
+    scale0: int = -1
+    shift0: int = -1
+    scale1: int = -1
+    shift1: int = -1
+    flops: float = 0.0            # algorithmic 2*MACs per clip (un-padded reference shape)
+    layers: Tuple[str, ...] = ()  # Keras layers folded into this op
+    softmax_C: int = 0
+
+
+@dataclass
+class Plan:
+    ops: List[DevOp]
+    buffers: List[Buf]
+    workspace_bytes: int
+    weight_arena: np.ndarray          # uint8
+    blob_offsets: List[int]
+    logits: TRef
+    probs: TRef
+    max_batch: int
+    nb_classes: int
+    precision: str
+    n_inputs: int
+    tensors: Dict[str, object] = field(default_factory=dict)   # Keras layer name -> TRef
+
+    def to_structs(self) -> List[rt.CseOp]:
+        out = []
+        for op in self.ops:
+            s = rt.CseOp()
+            s.kind, s.engine, s.w_dtype = op.kind, op.engine, op.w_dtype
+            i0, o0 = op.in0, op.out0
+            if op.kind == rt.OP_SOFTMAX:
+                s.in_dims[:] = (1, 1, 1, op.softmax_C)
+                s.out_dims[:] = (1, 1, 1, op.softmax_C)
+                s.in_dtype = s.out_dtype = rt.F32
+                s.in0_off, s.out0_off = i0.byte_off(), o0.byte_off()
+                s.in1_off = s.out1_off = s.w_off = -1
+                s.scale0_off = s.shift0_off = s.scale1_off = s.shift1_off = -1
+                out.append(s)
+                continue
+            if i0 is not None:
+                s.in_dims[:] = tuple(i0.dims) + (i0.C,)
+                s.in_ld, s.in_dtype, s.in0_off = i0.ld, i0.dtype, i0.byte_off()
+            else:
+                s.in0_off = -1
+            s.out_dims[:] = tuple(o0.dims) + (o0.C,)
+            s.out_ld, s.out_dtype, s.out0_off = o0.ld, o0.dtype, o0.byte_off()
+            if op.in1 is not None:
+                s.in1_ld, s.in1_off = op.in1.ld, op.in1.byte_off()
+            else:
+                s.in1_off = -1
+            if op.out1 is not None:
+                s.out1_ld, s.out1_off = op.out1.ld, op.out1.byte_off()
+            else:
+                s.out1_off = -1
+            s.k[:], s.s[:], s.pad[:] = op.k, op.s, op.pad
+            s.relu0, s.relu1, s.pad_is_zero, s.ext_input = op.relu0, op.relu1, op.pad_is_zero, op.ext_input
+            s.crop[:] = op.crop
+            s.src_dims[:] = op.src_dims
+            s.pre_mean[:] = tuple(op.pre_mean)
+            s.pre_scale[:] = tuple(op.pre_scale)
+            s.kc, s.bn = op.kc, op.bn
+            s.brick[:] = op.brick
+            bo = self.blob_offsets
+            s.w_off = bo[op.w_blob] if op.w_blob >= 0 else -1
+            s.scale0_off = bo[op.scale0] if op.scale0 >= 0 else -1
+            s.shift0_off = bo[op.shift0] if op.shift0 >= 0 else -1
+            s.scale1_off = bo[op.scale1] if op.scale1 >= 0 else -1
+            s.shift1_off = bo[op.shift1] if op.shift1 >= 0 else -1
+            out.append(s)
+        return out
+
+    def describe(self) -> str:
+        lines = []
+        for i, op in enumerate(self.ops):
+            eng = {0: "", 1: "direct", 2: "tcgen05"}[op.engine]
+            lines.append("%3d %-10s %-8s %-40s out=%s%s" % (
+                i, rt.OP_NAMES[op.kind], eng, op.name,
+                (tuple(op.out0.dims) + (op.out0.C,)) if op.out0 else "",
+                " kc=%d bn=%d brick=%s" % (op.kc, op.bn, op.brick) if op.engine == 2 else ""))
+        return "\n".join(lines)
+
+
+# --------------------------------------------------------------------------- #
+def to_bf16_bits(a: np.ndarray) -> np.ndarray:
+    """float32 -> bfloat16 (round to nearest even), returned as uint16 bit patterns."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16)
+    return t.view(torch.int16).numpy().view(np.uint16)
+
+
+def fold_bn(bias, bn_weights, has_gamma, co):
+    """(conv bias, BN tensors) -> float32 (scale, shift) with y = acc*scale + shift."""
+    one = np.float32(1.0)
+    if bn_weights is None:
+        return None, (None if bias is None else bias.astype(np.float32))
+    if has_gamma:
+        gamma, beta, mean, var = bn_weights
+    else:
+        beta, mean, var = bn_weights
+        gamma = None
+    inv = (one / np.sqrt(var.astype(np.float32) + np.float32(BN_EPS))).astype(np.float32)
+    if gamma is not None:
+        inv = (inv * gamma.astype(np.float32)).astype(np.float32)
+    shift = (beta.astype(np.float32) - mean.astype(np.float32) * inv).astype(np.float32)
+    if bias is not None:
+        shift = (bias.astype(np.float32) * inv + shift).astype(np.float32)
+    return inv, shift
+
+
+def choose_kc(ci: int) -> int:
+    best, best_pad = 64, None
+    for kc in (64, 32, 16):
+        pad = _round_up(ci, kc)
+        if best_pad is None or pad < best_pad:
+            best, best_pad = kc, pad
+    return best
+
+
+def choose_bn(co: int) -> Tuple[int, int]:
+    n_tiles = -(-co // 256)
+    bn = _round_up(-(-co // n_tiles), 16)
+    return bn, n_tiles
+
+
+def choose_brick(nb: int, do: int, ho: int, wo: int) -> Tuple[int, int, int, int]:
+    """Output-pixel brick (n,d,h,w), product <= 128, minimising the number of M tiles."""
+    best, best_key = None, None
+    for bw in range(1, min(wo, 128) + 1):
+        tw = -(-wo // bw)
+        for bh in range(1, min(ho, 128 // bw) + 1):
+            th = -(-ho // bh)
+            for bd in range(1, min(do, 128 // (bw * bh)) + 1):
+                td = -(-do // bd)
+                bn_ = max(1, min(nb, 128 // (bw * bh * bd)))
+                tn = -(-nb // bn_)
+                tiles = tn * td * th * tw
+                rows = bn_ * bd * bh * bw
+                key = (tiles, bn_, -bw, -bh)
+                if best_key is None or key < best_key:
+                    best, best_key = (bn_, bd, bh, bw), key
+    return best
+
+
+def pack_tc_weights(kernel: np.ndarray, kc: int, bn: int, n_tiles: int) -> np.ndarray:
+    """Keras [kd,kh,kw,Ci,Co] -> [Co_pad][taps*kchunks*kc] bf16 bits (K-major rows)."""
+    kd, kh, kw, ci, co = kernel.shape
+    taps = kd * kh * kw
+    cip = _round_up(ci, kc)
+    w = np.zeros((taps, cip, n_tiles * bn), np.float32)
+    w[:, :ci, :co] = kernel.reshape(taps, ci, co)
+    w = np.ascontiguousarray(w.reshape(taps * cip, n_tiles * bn).T)
+    return to_bf16_bits(w)
+
+
+class Lowerer:
+    def __init__(self, g: Graph, weights: Dict[str, List[np.ndarray]], precision: str = "bf16",
+                 max_batch: int = 8, tc: bool = True, tc_strided: bool = False,
+                 crop=None, mean=None, scale=None, keep_all: bool = False):
+        self.keep_all = keep_all
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        check_weights(g, weights)
+        self.g, self.w = g, weights
+        self.precision = precision
+        self.act = rt.BF16 if precision == "bf16" else rt.F32
+        self.nb = max_batch
+        self.use_tc = tc and precision == "bf16"
+        self.tc_strided = tc_strided
+        self.crop, self.mean, self.scale = crop, mean, scale
+        self.ops: List[DevOp] = []
+        self.bufs: List[Buf] = []
+        self.blobs: List[np.ndarray] = []
+        self.val: Dict[str, object] = {}
+        self.consumers: Dict[str, List[str]] = {n: [] for n in g.nodes}
+        for n in g.nodes.values():
+            for i in n.inputs:
+                self.consumers[i].append(n.name)
+        self.done = set()
+        self.place: Dict[str, Tuple[str, int]] = {}
+        self.concat_ref: Dict[str, TRef] = {}
+        for n in g.nodes.values():
+            if n.op == "concat" and len(n.out_shape) == 4:
+                off = 0
+                for i in n.inputs:
+                    if len(self.consumers[i]) == 1:
+                        self.place[i] = (n.name, off)
+                    off += g.shape(i)[-1]
+
+    # ---- allocation ------------------------------------------------------- #
+    def esize(self, dt):
+        return 4 if dt == rt.F32 else 2
+
+    def new_buf(self, name, dims, ld, dt) -> Buf:
+        nbytes = self.nb * dims[0] * dims[1] * dims[2] * ld * self.esize(dt)
+        b = Buf(name, _round_up(max(nbytes, 16), ALIGN))
+        self.bufs.append(b)
+        return b
+
+    def out_ref(self, final_name: str, dims, C, dt) -> TRef:
+        """Output view for the chain ending in `final_name`: a concat slice if one was planned."""
+        if final_name in self.place and dt == self.act:
+            cname, coff = self.place[final_name]
+            if cname not in self.concat_ref:
+                ctot = self.g.shape(cname)[-1]
+                b = self.new_buf(cname, dims, ctot, dt)
+                self.concat_ref[cname] = TRef(b, 0, ctot, ctot, tuple(dims), dt)
+            base = self.concat_ref[cname]
+            return TRef(base.buf, coff, C, base.ld, tuple(dims), dt)
+        b = self.new_buf(final_name, dims, C, dt)
+        return TRef(b, 0, C, C, tuple(dims), dt)
+
+    def blob(self, arr: np.ndarray) -> int:
+        self.blobs.append(np.ascontiguousarray(arr))
+        return len(self.blobs) - 1
+
+    def fblob(self, arr) -> int:
+        return -1 if arr is None else self.blob(np.asarray(arr, np.float32))
+
+    def emit(self, op: DevOp):
+        self.ops.append(op)
+
+    def sole_consumer(self, name: str, kind: str) -> Optional[Node]:
+        c = self.consumers[name]
+        if len(c) == 1 and self.g.nodes[c[0]].op == kind:
+            return self.g.nodes[c[0]]
+        return None
+
+    # ---- node handlers ------------------------------------------------------ #
+    def lower(self) -> Plan:
+        g = self.g
+        for node in g.nodes.values():
+            if node.name in self.done:
+                continue
+            getattr(self, "_" + node.op)(node)
+        logits, probs = self.val.get("__logits__"), self.val.get("__probs__")
+        # liveness
+        for idx, op in enumerate(self.ops):
+            for r in (op.in0, op.in1, op.out0, op.out1):
+                if r is not None:
+                    r.buf.first = min(r.buf.first, idx)
+                    r.buf.last = max(r.buf.last, idx)
+        for r in (logits, probs):
+            if r is not None:
+                r.buf.last = len(self.ops) + 1
+        if self.keep_all:           # tests: every intermediate stays readable after the run
+            for b in self.bufs:
+                if b.last >= 0:
+                    b.last = len(self.ops) + 1
+        ws = self._assign_offsets()
+        # weight arena
+        offs, cur = [], 0
+        for b in self.blobs:
+            cur = _round_up(cur, 256)
+            offs.append(cur)
+            cur += b.nbytes
+        arena = np.zeros(_round_up(max(cur, 256), 256), np.uint8)
+        for b, o in zip(self.blobs, offs):
+            arena[o:o + b.nbytes] = b.view(np.uint8).reshape(-1)
+        tensors = {k: v for k, v in self.val.items() if isinstance(v, TRef) and not k.startswith("__")}
+        return Plan(self.ops, self.bufs, ws, arena, offs, logits, probs, self.nb,
+                    (g.shape(g.output)[-1] if g.output else 1), self.precision, len(g.inputs), tensors)
+
+    def _assign_offsets(self) -> int:
+        live = [b for b in self.bufs if b.last >= 0]
+        live.sort(key=lambda b: (b.first, -b.nbytes))
+        placed: List[Buf] = []
+        top = 0
+        for b in live:
+            busy = sorted(((p.offset, p.offset + p.nbytes) for p in placed
+                           if not (p.last < b.first or p.first > b.last)))
+            off = 0
+            for lo, hi in busy:
+                if off + b.nbytes <= lo:
+                    break
+                off = max(off, hi)
+            b.offset = off
+            placed.append(b)
+            top = max(top, off + b.nbytes)
+        return _round_up(top, ALIGN)
+
+    def _input(self, node: Node):
+        t, h, w, c = node.out_shape
+        idx = self.g.inputs.index(node.name)
+        crop = self.crop
+        if crop is not None:
+            t0, h0, w0, to, ho, wo = crop
+            raise NotImplementedError("crop changes the graph's input shape; build the graph for the cropped shape")
+        ld = c if self.act == rt.F32 else 8
+        b = self.new_buf(node.name, (t, h, w), ld, self.act)
+        out = TRef(b, 0, c, ld, (t, h, w), self.act)
+        mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
+        scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
+        self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
+                        src_dims=(t, h, w, c), pre_mean=mean, pre_scale=scale, layers=(node.name,)))
+        self.val[node.name] = out
+
+    def _conv_like(self, name, x: TRef, kernel, bias, k, s, pads, out_dims, chain_bn, relu, final_name,
+                   layers, out_dtype=None, residual: Optional[TRef] = None, flops=0.0,
+                   second: Optional[Tuple[np.ndarray, np.ndarray, int, str]] = None):
+        """Emit one CONV3D op.  chain_bn = (bn_weights, has_gamma) or None."""
+        co = kernel.shape[-1]
+        out_dtype = self.act if out_dtype is None else out_dtype
+        scale, shift = fold_bn(bias, chain_bn[0] if chain_bn else None, chain_bn[1] if chain_bn else False, co)
+        out0 = self.out_ref(final_name, out_dims, co, out_dtype)
+        op = DevOp(rt.OP_CONV3D, name, x, residual, out0, k=tuple(k), s=tuple(s), pad=tuple(pads),
+                   relu0=int(relu), layers=tuple(layers), flops=flops)
+        op.scale0, op.shift0 = self.fblob(scale), self.fblob(shift)
+        ci = x.C
+        tc_ok = (self.use_tc and x.dtype == rt.BF16 and out_dtype == rt.BF16 and ci % 8 == 0 and x.ld % 8 == 0
+                 and x.coff % 8 == 0 and co % 8 == 0 and co >= 16 and out0.ld % 8 == 0 and out0.coff % 8 == 0
+                 and (self.tc_strided or tuple(s) == (1, 1, 1))
+                 and (residual is None or (residual.ld % 8 == 0 and residual.coff % 8 == 0)))
+        if tc_ok:
+            kc = choose_kc(ci)
+            bn, n_tiles = choose_bn(co)
+            op.engine, op.w_dtype, op.kc, op.bn = rt.ENGINE_TCGEN05, rt.BF16, kc, bn
+            op.brick = choose_brick(self.nb, *out_dims)
+            op.w_blob = self.blob(pack_tc_weights(kernel, kc, bn, n_tiles))
+        else:
+            op.engine = rt.ENGINE_DIRECT
+            kflat = kernel.reshape(-1, co)
+            if x.dtype == rt.BF16:
+                op.w_dtype = rt.BF16
+                op.w_blob = self.blob(to_bf16_bits(kflat))
+            else:
+                op.w_dtype = rt.F32
+                op.w_blob = self.blob(kflat.astype(np.float32))
+        if second is not None:
+            sc1, sh1, relu1, second_name = second
+            op.out1 = self.out_ref(second_name, out_dims, co, out_dtype)
+            op.scale1, op.shift1, op.relu1 = self.fblob(sc1), self.fblob(sh1), int(relu1)
+        self.emit(op)
+        return op
+
+    def _conv3d(self, node: Node):
+        g = self.g
+        x = self.val[node.inputs[0]]
+        ws = self.w[node.name]
+        kernel = ws[0]
+        bias = ws[1] if node.attrs["use_bias"] else None
+        layers = [node.name]
+        final = node.name
+        relu = node.attrs["activation"] == "relu"
+        chain_bn = None
+        nxt = self.sole_consumer(final, "bn")
+        if nxt is not None and not relu:
+            chain_bn = (self.w[nxt.name], nxt.attrs["scale"])
+            layers.append(nxt.name)
+            final = nxt.name
+        nxt = self.sole_consumer(final, "relu")
+        if nxt is not None and not relu:
+            relu = True
+            layers.append(nxt.name)
+            final = nxt.name
+        out_dims = node.out_shape[:3]
+        flops = g.conv_dense_flops()[node.name]
+        # residual fusion: conv (no bn/relu tail) whose only consumer is add([shortcut, this])
+        add = self.sole_consumer(final, "add") if (chain_bn is None and not relu) else None
+        if add is not None and len(add.inputs) == 2 and add.inputs[1] == final and add.inputs[0] not in self.val:
+            # projection shortcut (_shortcut3d, train.py:1338): created after the residual convs
+            # in the graph but only depends on the block input -> lower it first
+            sc_node = g.nodes[add.inputs[0]]
+            if sc_node.op == "conv3d" and sc_node.inputs[0] in self.val:
+                self._conv3d(sc_node)
+        if add is not None and len(add.inputs) == 2 and add.inputs[1] == final and add.inputs[0] in self.val:
+            self._fused_residual(node, add, x, kernel, bias, out_dims, flops)
+            return
+        self._conv_like(node.name, x, kernel, bias, node.attrs["k"], node.attrs["s"], node.attrs["pads_before"],
+                        out_dims, chain_bn, relu, final, layers, flops=flops)
+        ref = self.ops[-1].out0
+        for l in layers:
+            self.val[l] = ref
+            self.done.add(l)
+
+    def _fused_residual(self, node, add, x, kernel, bias, out_dims, flops):
+        """residual conv + add (+ the next block's BN-ReLU as a second output)."""
+        sc = self.val[add.inputs[0]]
+        layers = [node.name, add.name]
+        second = None
+        cons = self.consumers[add.name]
+        bn_nodes = [self.g.nodes[c] for c in cons if self.g.nodes[c].op == "bn"]
+        second_layers = []
+        if len(bn_nodes) == 1:
+            bn = bn_nodes[0]
+            r = self.sole_consumer(bn.name, "relu")
+            sc1, sh1 = fold_bn(None, self.w[bn.name], bn.attrs["scale"], kernel.shape[-1])
+            second_name = r.name if r is not None else bn.name
+            second = (sc1, sh1, r is not None, second_name)
+            second_layers = [bn.name] + ([r.name] if r is not None else [])
+        op = self._conv_like(node.name, x, kernel, bias, node.attrs["k"], node.attrs["s"],
+                             node.attrs["pads_before"], out_dims, None, False, add.name,
+                             layers + second_layers, residual=sc, flops=flops, second=second)
+        for l in layers:
+            self.val[l] = op.out0
+            self.done.add(l)
+        for l in second_layers:
+            self.val[l] = op.out1
+            self.done.add(l)
+
+    def _bn(self, node: Node):
+        x = self.val[node.inputs[0]]
+        scale, shift = fold_bn(None, self.w[node.name], node.attrs["scale"], x.C)
+        layers, final, relu = [node.name], node.name, False
+        nxt = self.sole_consumer(final, "relu")
+        if nxt is not None:
+            relu, final = True, nxt.name
+            layers.append(final)
+        out = self.out_ref(final, x.dims, x.C, x.dtype)
+        op = DevOp(rt.OP_AFFINE, node.name, x, None, out, relu0=int(relu), layers=tuple(layers))
+        op.scale0, op.shift0 = self.fblob(scale), self.fblob(shift)
+        self.emit(op)
+        for l in layers:
+            self.val[l] = out
+            self.done.add(l)
+
+    def _relu(self, node: Node):
+        x = self.val[node.inputs[0]]
+        out = self.out_ref(node.name, x.dims, x.C, x.dtype)
+        self.emit(DevOp(rt.OP_AFFINE, node.name, x, None, out, relu0=1, layers=(node.name,)))
+        self.val[node.name] = out
+
+    def _dropout(self, node: Node):
+        self.val[node.name] = self.val[node.inputs[0]]     # identity at inference
+
+    def _add(self, node: Node):
+        a, b = (self.val[i] for i in node.inputs)
+        out = self.out_ref(node.name, a.dims, a.C, a.dtype)
+        self.emit(DevOp(rt.OP_ADD, node.name, a, b, out, layers=(node.name,)))
+        self.val[node.name] = out
+
+    def _concat(self, node: Node):
+        if len(node.out_shape) == 1:
+            self.val[node.name] = [self.val[i] for i in node.inputs]     # consumed by _dense
+            return
+        if node.name not in self.concat_ref or any(i not in self.place for i in node.inputs):
+            raise NotImplementedError("concat %s: an input was not written in place" % node.name)
+        self.val[node.name] = self.concat_ref[node.name]
+
+    def _pool(self, node: Node, kind: int, x: TRef, pads, pad_is_zero, out_dims, layers):
+        out = self.out_ref(node.name, out_dims, x.C, x.dtype)
+        self.emit(DevOp(kind, node.name, x, None, out, k=node.attrs["k"], s=node.attrs["s"], pad=tuple(pads),
+                        pad_is_zero=int(pad_is_zero), layers=tuple(layers)))
+        for l in layers:
+            self.val[l] = out
+            self.done.add(l)
+
+    def _maxpool(self, node: Node):
+        self._pool(node, rt.OP_MAXPOOL3D, self.val[node.inputs[0]], node.attrs["pads_before"], False,
+                   node.out_shape[:3], [node.name])
+
+    def _avgpool(self, node: Node):
+        self._pool(node, rt.OP_AVGPOOL3D, self.val[node.inputs[0]], (0, 0, 0), False, node.out_shape[:3],
+                   [node.name])
+
+    def _zeropad(self, node: Node):
+        nxt = self.sole_consumer(node.name, "maxpool")
+        if nxt is None or nxt.attrs["padding"] != "valid":
+            raise NotImplementedError("ZeroPadding3D is only supported in front of a 'valid' MaxPooling3D")
+        pads = node.attrs["pads"]
+        self._pool(nxt, rt.OP_MAXPOOL3D, self.val[node.inputs[0]], tuple(p[0] for p in pads), True,
+                   nxt.out_shape[:3], [node.name, nxt.name])
+
+    def _flatten(self, node: Node):
+        x = self.val[node.inputs[0]]
+        if x.ld != x.C or x.coff != 0:
+            raise NotImplementedError("flatten of a channel slice")
+        n = x.dims[0] * x.dims[1] * x.dims[2] * x.C
+        self.val[node.name] = TRef(x.buf, 0, n, n, (1, 1, 1), x.dtype)
+
+    def _dense(self, node: Node):
+        g = self.g
+        kernel, bias = self.w[node.name]
+        act = node.attrs["activation"]
+        is_final = node.name == g.output
+        units = node.attrs["units"]
+        xin = self.val[node.inputs[0]]
+        parts = xin if isinstance(xin, list) else [xin]
+        out_dtype = rt.F32 if is_final else self.act
+        flops_total = g.conv_dense_flops()[node.name]
+        row = 0
+        prev = None
+        for pi, x in enumerate(parts):
+            kpart = kernel[row:row + x.C].reshape(1, 1, 1, x.C, units)
+            row += x.C
+            last = pi == len(parts) - 1
+            name = node.name if len(parts) == 1 else "%s#%d" % (node.name, pi)
+            final_name = node.name if last else name
+            self._conv_like(name, x, kpart, bias if pi == 0 else None, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1),
+                            None, act == "relu" and last, final_name, [node.name], out_dtype=out_dtype,
+                            residual=prev, flops=flops_total * x.C / kernel.shape[0])
+            prev = self.ops[-1].out0
+        assert row == kernel.shape[0]
+        self.val[node.name] = prev
+        if is_final:
+            if act != "softmax":
+                raise NotImplementedError("final activation %r" % act)
+            pb = self.new_buf(node.name + ":probs", (1, 1, 1), units, rt.F32)
+            probs = TRef(pb, 0, units, units, (1, 1, 1), rt.F32)
+            self.emit(DevOp(rt.OP_SOFTMAX, node.name + ":softmax", prev, None, probs, softmax_C=units,
+                            layers=(node.name,)))
+            self.val["__logits__"], self.val["__probs__"] = prev, probs
+
+
+def lower(g: Graph, weights, precision="bf16", max_batch=8, **kw) -> Plan:
+    return Lowerer(g, weights, precision, max_batch, **kw).lower()

