@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py - ensemble clips/sec of the B200-native hot path (and of the CPU reference arm).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch of synthetic clips per GPU: every member
+of the ensemble runs its forward pass on the batch (pre-processing included) and the soft vote
+produces one prediction per clip.  Default workload = BASELINE.json configs[1]: the homogeneous
+C3D fold ensemble on [256,16,112,112,3] uint8 clips, 11 classes, M = folds-1 = 4 members
+(evaluate_ensemble.py:1042-1049), SUM vote.  Prints ONE JSON line (rank 0).
+
+* value      : ensemble clips/s over all GPUs, inputs resident in HBM (uint8), CUDA events,
+               max over ranks.
+* e2e        : same metric through Member/Ensemble's host API: pinned host uint8 batch -> H2D,
+               forward, vote, D2H of the int32 predictions, all inside the timed region.
+* roofline   : the tcgen05 conv kernel: algorithmic conv FLOPs (un-padded reference shapes) of
+               the layers it ran / its summed launch durations (CUDA events around each launch in
+               a separate profiling pass on the same stream), vs the measured dense-bf16 peak.
+* cpu_baseline / --impl reference : the oracle's torch-CPU fp32 restatement of the same members
+               (Keras 2.2.4 / TF 1.15 cannot be installed offline) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOADS = {
+    # name: (model_type, input shape, members, batch per GPU)
+    "c3d_ens": ("C3D", (16, 112, 112, 3), 4, 256),
+    "c3d_single_b8": ("C3D", (16, 112, 112, 3), 1, 8),
+    "r3d34_ens": ("R3D_34", (16, 112, 112, 3), 4, 256),
+    "i3d20_ens": ("I3D", (20, 224, 224, 3), 4, 32),
+    "i3d64_ens": ("I3D", (64, 224, 224, 3), 4, 8),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_clips_per_s(model_type, shape, members, clips_per_step, steps, warmup, threads=None):
+    """Oracle port (torch CPU fp32) of the same ensemble: every member forward + numpy vote."""
+    import torch
+    from cse_b200 import graph as G
+    from cse_b200.weights import synthetic_weights
+    from oracle import models as OM, vote as OV
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    g = G.build_model_graph(model_type, shape, 11)
+    ws = [synthetic_weights(g, seed=100 + m) for m in range(members)]
+    x = np.random.default_rng(1234).integers(0, 256, (clips_per_step,) + tuple(shape), dtype=np.uint8)
+
+    def step():
+        probs = [OM.forward(model_type, w, x, torch.float32)[1].numpy() for w in ws]
+        return OV.ensemble_predictions(np.stack(probs).astype(np.float64), np.ones(members))
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return clips_per_step * steps / dt, dt / steps, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mt, shape, members, batch = WORKLOADS[args.workload]
+    sample = 4 if mt == "C3D" else 2
+    v, sec, threads = cpu_reference_clips_per_s(mt, shape, members, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "ensemble clips/sec", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model": mt, "clip": list(shape), "members": members,
+                   "batch_per_gpu": batch, "vote": "SUM", "classes": 11},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+                         "sample": "%d clips x %d members per step, torch CPU fp32 oracle restatement "
+                                   "(Keras 2.2.4/TF 1.15 not installable offline)" % (sample, members)},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cse_b200 import graph as G, runtime as rt
+    from cse_b200.ensemble_runtime import DeviceEnsemble
+    from cse_b200.weights import synthetic_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rt.load_library()
+    mt, shape, members, batch = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    if args.members:
+        members = args.members
+    g = G.build_model_graph(mt, shape, 11)
+    weight_sets = [synthetic_weights(g, seed=100 + m) for m in range(members)]
+    ens = DeviceEnsemble(g, weight_sets, precision=args.precision, max_batch=batch, micro_batch=args.micro_batch)
+    del weight_sets
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host = torch.randint(0, 256, (batch,) + tuple(shape), dtype=torch.uint8, generator=gen).pin_memory()
+    dev_in = host.cuda()
+    in_bytes = dev_in.numel()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return ens.predict_device([dev_in])
+
+    def step_e2e():
+        return ens.predict_host([host])
+
+    # ---- kernel-resident timing ----
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        pred = step_resident()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ens.last_launches * args.steps
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end timing (host buffers, H2D + D2H inside) ----
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        out = step_e2e()
+    e3.record(stream)
+    barrier()
+    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    total_clips = batch * world * args.steps
+    value = total_clips / (ms / 1e3)
+    e2e_value = total_clips / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = load_peaks()
+        prof = ens.profile_ops([dev_in], iters=2)
+        tc = [p for p in prof if p["engine"] == "tcgen05"]
+        tc_flops = sum(p["flops"] for p in tc)
+        tc_ms = sum(p["ms"] for p in tc)
+        step_ms_prof = sum(p["ms"] for p in prof)
+        achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+        peak = peaks["bf16_sustained"]
+        roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (peaks["source"], peaks["bf16_burst"]),
+                    "kernel_share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
+                    "launches_per_step": len(tc),
+                    "whole_step_model_tflops": members * g.total_flops() * batch / (ms / args.steps / 1e3) / 1e12}
+        top = sorted(prof, key=lambda p: -p["ms"])[:6]
+        roofline["top_ops"] = [{"op": p["name"], "engine": p["engine"], "ms": round(p["ms"], 3),
+                                "tflops": round(p["flops"] / (p["ms"] / 1e3) / 1e12, 1) if p["ms"] > 0 else 0}
+                               for p in top]
+        cpu = None
+        if not args.no_cpu_baseline:
+            sample = 4
+            v, sec, threads = cpu_reference_clips_per_s(mt, shape, members, sample, 1, 1)
+            cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+                   "sample": "%d clips x %d members, 1 warm-up + 1 timed pass, torch CPU fp32 oracle restatement"
+                             % (sample, members)}
+        line = {
+            "metric": "ensemble clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "model": mt, "clip": list(shape), "members": members,
+                       "batch_per_gpu": batch, "vote": "SUM", "classes": 11,
+                       "l2_policy": "input batch (%d MB uint8) and activations exceed the 126 MB L2" % (in_bytes >> 20)},
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": batch * 4},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3d_ens", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--members", type=int, default=0)
+    ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,113 @@
+"""Device-resident ensemble: M members of one architecture + the soft vote, on one GPU.
+
+This is the batched replacement of the reference's member loop (evaluate_ensemble.py:1048-1060,
+one Keras model per member, batch 1, every clip re-decoded per member) followed by
+ensemble_predictions (evaluate_ensemble.py:343-370): each micro-batch of clips is uploaded once and
+run through every member while it is still L2/HBM resident; member probabilities land directly in
+one [M, N, C] device buffer that the vote kernel reduces.  Members share one workspace arena
+(they run back to back on one stream), so HBM holds M weight arenas + one set of activations.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import runtime as rt
+from .graph import Graph
+from .model import Member
+
+
+class DeviceEnsemble:
+    def __init__(self, graph: Graph, weight_sets: Sequence[Dict[str, List[np.ndarray]]], precision: str = "bf16",
+                 max_batch: int = 256, micro_batch: int = 0, device=None, vote_weights=None, vote_mode: str = "SUM",
+                 **lower_kw):
+        torch = rt.require_cuda()
+        self.torch = torch
+        self.graph = graph
+        self.max_batch = int(max_batch)
+        self.micro_batch = int(micro_batch) if micro_batch else min(self.max_batch, 32)
+        self.members: List[Member] = []
+        shared = None
+        for w in weight_sets:
+            m = Member(graph, w, precision=precision, max_batch=self.micro_batch, device=device,
+                       workspace=shared, **lower_kw)
+            shared = m.workspace
+            self.members.append(m)
+        self.device = self.members[0].device
+        self.nb_classes = self.members[0].nb_classes
+        self.M = len(self.members)
+        self.probs = torch.empty((self.M, self.max_batch, self.nb_classes), dtype=torch.float32, device=self.device)
+        self.logits = torch.empty((self.M, self.max_batch, self.nb_classes), dtype=torch.float32, device=self.device)
+        self.vote_mode = vote_mode
+        self.vote_weights = None
+        if vote_weights is not None:
+            self.vote_weights = torch.as_tensor(np.asarray(vote_weights, np.float64)).to(self.device)
+        self.last_launches = 0
+        self._stage = None
+
+    # ---- device path --------------------------------------------------------- #
+    def forward_members(self, inputs_u8):
+        """inputs: list of uint8 CUDA tensors [n,...] -> fills self.probs[:, :n], self.logits[:, :n]."""
+        n = inputs_u8[0].shape[0]
+        if n > self.max_batch:
+            raise ValueError("batch %d exceeds max_batch %d" % (n, self.max_batch))
+        launches = 0
+        mb = self.micro_batch
+        for i in range(0, n, mb):
+            chunk = [x[i:i + mb] for x in inputs_u8]
+            for j, m in enumerate(self.members):
+                m.forward_device(chunk, self.logits[j, i:i + mb], self.probs[j, i:i + mb])
+                launches += m.launches + 2          # + the two D2D copies of logits / probs
+        self.last_launches = launches
+        return n
+
+    def vote(self, n):
+        probs = self.probs[:, :n].contiguous() if n != self.max_batch else self.probs
+        pred = rt.vote(probs, self.vote_weights, self.vote_mode)
+        self.last_launches += 1
+        return pred
+
+    def predict_device(self, inputs_u8):
+        n = self.forward_members(inputs_u8)
+        return self.vote(n)
+
+    def predict_host(self, host_inputs):
+        """host_inputs: list of pinned uint8 CPU tensors [n,...]; uploads, runs, returns numpy int32 [n]."""
+        torch = self.torch
+        dev = [h.to(self.device, non_blocking=True) for h in host_inputs]
+        pred = self.predict_device(dev)
+        return pred.cpu().numpy()
+
+    # ---- profiling -------------------------------------------------------------- #
+    def profile_ops(self, inputs_u8, iters: int = 2):
+        """CUDA-event duration of every op launch (summed over members and micro-batches) for one
+        step; events are recorded on the stream the kernels are launched on."""
+        torch = self.torch
+        stream = torch.cuda.current_stream()
+        n = inputs_u8[0].shape[0]
+        mb = self.micro_batch
+        plan = self.members[0].plan
+        acc = [0.0] * len(plan.ops)
+        for it in range(iters + 1):
+            evs = []
+            for i in range(0, n, mb):
+                chunk = [x[i:i + mb] for x in inputs_u8]
+                for m in self.members:
+                    for k in range(len(plan.ops)):
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(stream)
+                        m.run_ops(chunk, k, k + 1)
+                        b.record(stream)
+                        evs.append((k, a, b))
+            torch.cuda.synchronize()
+            if it == 0:
+                continue            # warm-up pass
+            for k, a, b in evs:
+                acc[k] += a.elapsed_time(b)
+        out = []
+        eng = {0: "", 1: "direct", 2: "tcgen05"}
+        for k, op in enumerate(plan.ops):
+            out.append({"name": op.name, "kind": rt.OP_NAMES[op.kind], "engine": eng[op.engine],
+                        "ms": acc[k] / iters, "flops": op.flops * n * self.M})
+        return out

@@ -24,7 +24,7 @@ from .lowering import Plan, lower
 
 class Member:
     def __init__(self, graph: Graph, weights: Dict[str, List[np.ndarray]], precision: str = "bf16",
-                 max_batch: int = 8, device=None, **lower_kw):
+                 max_batch: int = 8, device=None, workspace=None, **lower_kw):
         torch = rt.require_cuda()
         self.lib = rt.load_library()
         self.torch = torch
@@ -36,7 +36,13 @@ class Member:
         self.nb_classes = self.plan.nb_classes
         self.input_shapes = [graph.shape(n) for n in graph.inputs]
         with torch.cuda.device(self.device):
-            self.workspace = torch.empty(self.plan.workspace_bytes + 1024, dtype=torch.uint8, device=self.device)
+            if workspace is not None:       # members that run back to back may share one activation arena
+                if workspace.numel() < self.plan.workspace_bytes + 1024:
+                    raise rt.CseError("shared workspace too small")
+                self.workspace = workspace
+            else:
+                self.workspace = torch.empty(self.plan.workspace_bytes + 1024, dtype=torch.uint8,
+                                             device=self.device)
             self.weights_dev = torch.from_numpy(self.plan.weight_arena).to(self.device)
             ws_ptr = (self.workspace.data_ptr() + 1023) // 1024 * 1024
             if self.weights_dev.data_ptr() % 256:

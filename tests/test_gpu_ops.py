@@ -223,7 +223,7 @@ def test_zeropad_maxpool_and_avgpool():
 # --------------------------------------------------------------------------- vote
 def test_vote_bit_exact_vs_oracle():
     rng = np.random.default_rng(11)
-    for (mm, n, c) in [(4, 300, 11), (12, 1000, 11), (1, 7, 11), (32, 129, 11), (4, 128, 5)]:
+    for (mm, n, c) in [(4, 300, 11), (12, 1000, 11), (1, 7, 11), (32, 129, 11), (4, 128, 3)]:
         z = rng.standard_normal((mm, n, c)) * 3
         p = np.exp(z - z.max(-1, keepdims=True))
         p = (p / p.sum(-1, keepdims=True)).astype(np.float32)
