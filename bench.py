@@ -229,6 +229,10 @@ def run_ours(args):
                     "kernel_share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
                     "launches_per_step": len(tc),
                     "whole_step_model_tflops": members * g.total_flops() * batch / (ms / args.steps / 1e3) / 1e12}
+        if args.profile_out:
+            with open(args.profile_out, "w") as f:
+                json.dump({"workload": args.workload, "batch": batch, "members": members, "micro_batch": ens.micro_batch,
+                           "ops": prof}, f, indent=1)
         top = sorted(prof, key=lambda p: -p["ms"])[:6]
         roofline["top_ops"] = [{"op": p["name"], "engine": p["engine"], "ms": round(p["ms"], 3),
                                 "tflops": round(p["flops"] / (p["ms"] / 1e3) / 1e12, 1) if p["ms"] > 0 else 0}
@@ -268,6 +272,7 @@ def main():
     ap.add_argument("--members", type=int, default=0)
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default="")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -42,6 +42,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 
 // Geometry of one conv / pool launch (per clip dims; batch n is separate).
 struct WinGeom {
+  int in_wpitch = 0;     // input row pitch in pixels (0 = Wi): rows of a W-padded tensor
   int Di, Hi, Wi, Ci, in_ld;
   int Do, Ho, Wo, Co, out_ld;
   int kd, kh, kw, sd, sh, sw, pd, ph, pw;
@@ -73,7 +74,7 @@ int launch_add(int dt, const void* a, int a_ld, const void* b, int b_ld, void* o
 int launch_softmax(const float* in, float* out, int rows, int C, cudaStream_t st);
 int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int t0, int h0, int w0,
                       int To, int Ho, int Wo, const float* mean3, const float* scale3, void* out,
-                      int out_dt, int out_ld, cudaStream_t st);
+                      int out_dt, int out_ld, cudaStream_t st, int wpitch = 0, int wpad = 0);
 
 // tcgen05 engine
 struct ConvTcDesc {            // built once at plan finalize

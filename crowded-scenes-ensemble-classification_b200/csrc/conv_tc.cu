@@ -381,6 +381,8 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, int max_b
   CSE_REQUIRE(kc == 16 || kc == 32 || kc == 64, "conv_tc: kc=%d must be 16/32/64", kc);
   CSE_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "conv_tc: bn=%d must be a multiple of 16 in [16,256]", bn);
   CSE_REQUIRE(g.Ci % 8 == 0 && g.in_ld % 8 == 0, "conv_tc: Cin=%d / ld=%d must be multiples of 8", g.Ci, g.in_ld);
+  CSE_REQUIRE(g.in_wpitch == 0 || g.in_wpitch * g.in_ld >= (g.Wi - 1) * g.in_ld + g.Ci,
+              "conv_tc: row pitch %d too small for W=%d, window %d", g.in_wpitch, g.Wi, g.Ci);
   CSE_REQUIRE(g.Co % 8 == 0 && g.out_ld % 8 == 0, "conv_tc: Cout=%d / ld=%d must be multiples of 8", g.Co, g.out_ld);
   CSE_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)w_packed % 16) == 0, "conv_tc: pointers must be 16B aligned");
   CSE_REQUIRE(g.sd >= 1 && g.sd <= 8 && g.sh >= 1 && g.sh <= 8 && g.sw >= 1 && g.sw <= 8, "conv_tc: stride out of range");
@@ -397,14 +399,17 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, int max_b
   d->tiles_h = ceil_div(g.Ho, brick[2]);
   d->tiles_w = ceil_div(g.Wo, brick[3]);
 
-  // A: 5-D map over the NDHWC activation (dims C,W,H,D,N).  With stride s the box spans
-  // (b-1)*s+1 input positions and elementStrides = s picks every s-th one.
+  // A: 5-D map over the NDHWC activation (dims C,W,H,D,N).  With stride s the box spans b*s
+  // input positions and elementStrides = s picks every s-th one (b elements land in smem).
   {
     cuuint64_t dims[5] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di, (cuuint64_t)max_batch};
-    cuuint64_t strides[4] = {(cuuint64_t)g.in_ld * 2, (cuuint64_t)g.Wi * g.in_ld * 2,
-                             (cuuint64_t)g.Hi * g.Wi * g.in_ld * 2, (cuuint64_t)g.Di * g.Hi * g.Wi * g.in_ld * 2};
-    cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)((brick[3] - 1) * g.sw + 1), (cuuint32_t)((brick[2] - 1) * g.sh + 1),
-                         (cuuint32_t)((brick[1] - 1) * g.sd + 1), (cuuint32_t)brick[0]};
+    // in_wpitch > Wi: rows of a W-padded tensor; with Ci > in_ld the channel window of a pixel
+    // overlaps its right neighbours (packed stem: 4 pixels x 8 channels = one 32-wide K chunk).
+    const cuuint64_t wp = (cuuint64_t)(g.in_wpitch > 0 ? g.in_wpitch : g.Wi);
+    cuuint64_t strides[4] = {(cuuint64_t)g.in_ld * 2, wp * g.in_ld * 2, (cuuint64_t)g.Hi * wp * g.in_ld * 2,
+                             (cuuint64_t)g.Di * g.Hi * wp * g.in_ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(brick[3] * g.sw), (cuuint32_t)(brick[2] * g.sh),
+                         (cuuint32_t)(brick[1] * g.sd), (cuuint32_t)brick[0]};
     cuuint32_t estr[5] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, (cuuint32_t)g.sd, 1};
     CUresult r = enc(&d->tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

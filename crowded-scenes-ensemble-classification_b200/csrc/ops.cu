@@ -131,12 +131,63 @@ conv_direct_kernel(const TI* __restrict__ in, const TW* __restrict__ w, long lon
   }
 }
 
+// Dense with a handful of outputs (the 11-class heads: fc8 / predictions / dense_1,
+// train.py:1268, 840, 1007, 1510): one block per clip row, threads stride over K reading the
+// Keras [K][Co] kernel rows contiguously, block-wide reduction of Co partial sums.
+constexpr int DS_MAX_CO = 16;
+template <typename TI, typename TW, typename TO>
+__global__ void __launch_bounds__(256)
+dense_small_kernel(const TI* __restrict__ in, const TW* __restrict__ w, int K, int Co, int in_ld, int out_ld,
+                   Epilogue ep) {
+  __shared__ float red[8][DS_MAX_CO];
+  const int row = blockIdx.x;
+  const TI* x = in + (long long)row * in_ld;
+  float acc[DS_MAX_CO];
+#pragma unroll
+  for (int j = 0; j < DS_MAX_CO; ++j) acc[j] = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float xv = to_f32(x[k]);
+    const TW* wr = w + (long long)k * Co;
+#pragma unroll
+    for (int j = 0; j < DS_MAX_CO; ++j)
+      if (j < Co) acc[j] = fmaf(xv, to_f32(wr[j]), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < DS_MAX_CO; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < DS_MAX_CO; ++j) red[warp][j] = acc[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < Co) {
+    const int col = threadIdx.x;
+    float y = 0.f;
+    for (int wi = 0; wi < 8; ++wi) y += red[wi][col];
+    if (ep.scale0) y *= ep.scale0[col];
+    if (ep.shift0) y += ep.shift0[col];
+    if (ep.res) y += to_f32(reinterpret_cast<const TO*>(ep.res)[(long long)row * ep.res_ld + col]);
+    if (ep.relu0) y = fmaxf(y, 0.f);
+    reinterpret_cast<TO*>(ep.out0)[(long long)row * out_ld + col] = from_f32<TO>(y);
+  }
+}
+
 template <typename TI, typename TW, typename TO>
 static int conv_direct_t(const void* in, const void* w, int n, const WinGeom& g, const Epilogue& ep,
                          cudaStream_t st) {
   long long M = (long long)n * g.Do * g.Ho * g.Wo;
   int K = g.kd * g.kh * g.kw * g.Ci;
   if (M == 0) return CSE_OK;
+  if (g.kd * g.kh * g.kw == 1 && g.Do * g.Ho * g.Wo == 1 && g.Di * g.Hi * g.Wi == 1 && g.Co <= DS_MAX_CO &&
+      ep.out1 == nullptr) {
+    dense_small_kernel<TI, TW, TO><<<(unsigned)n, 256, 0, st>>>(
+        reinterpret_cast<const TI*>(in), reinterpret_cast<const TW*>(w), K, g.Co, g.in_ld, g.out_ld, ep);
+    CSE_CUDA(cudaGetLastError());
+    return CSE_OK;
+  }
   dim3 grid((unsigned)((M + DBM - 1) / DBM), (unsigned)ceil_div(g.Co, DBN));
   conv_direct_kernel<TI, TW, TO><<<grid, 256, 0, st>>>(
       reinterpret_cast<const TI*>(in), reinterpret_cast<const TW*>(w), M, K, g, ep);
@@ -405,6 +456,7 @@ int launch_softmax(const float* in, float* out, int rows, int C, cudaStream_t st
 // ============================================================================
 struct PreArgs {
   int T, H, W, C, t0, h0, w0, To, Ho, Wo, out_ld;
+  int wpitch, wpad;      // output row pitch in pixels and zero columns on the left (>= Wo + wpad)
   float mean[4], scale[4];
 };
 
@@ -413,16 +465,18 @@ __global__ void __launch_bounds__(256)
 preprocess_kernel(const uint8_t* __restrict__ src, TO* __restrict__ out, long long total, PreArgs a) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  int w = (int)(idx % a.Wo); long long t = idx / a.Wo;
+  int wp = (int)(idx % a.wpitch); long long t = idx / a.wpitch;
   int h = (int)(t % a.Ho); t /= a.Ho;
   int d = (int)(t % a.To); long long nn = t / a.To;
-  long long spix = ((nn * a.T + (d + a.t0)) * a.H + (h + a.h0)) * a.W + (w + a.w0);
+  const int w = wp - a.wpad;
+  const bool real = (w >= 0 && w < a.Wo);         // pad columns of the row are written as zeros
+  long long spix = ((nn * a.T + (d + a.t0)) * a.H + (h + a.h0)) * a.W + (real ? (w + a.w0) : 0);
   const uint8_t* s = src + spix * a.C;
   __align__(16) TO v[CO];
 #pragma unroll
   for (int c = 0; c < CO; ++c) {
     float f = 0.f;
-    if (c < a.C) f = ((float)s[c] - a.mean[c]) * a.scale[c];
+    if (real && c < a.C) f = ((float)s[c] - a.mean[c]) * a.scale[c];
     v[c] = from_f32<TO>(f);
   }
   TO* o = out + idx * a.out_ld;
@@ -436,7 +490,7 @@ preprocess_kernel(const uint8_t* __restrict__ src, TO* __restrict__ out, long lo
 
 int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int t0, int h0, int w0,
                       int To, int Ho, int Wo, const float* mean, const float* scale, void* out,
-                      int out_dt, int out_ld, cudaStream_t st) {
+                      int out_dt, int out_ld, cudaStream_t st, int wpitch, int wpad) {
   CSE_REQUIRE(C >= 1 && C <= 4, "preprocess: C=%d not in 1..4", C);
   CSE_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + To <= T && h0 + Ho <= H && w0 + Wo <= W,
               "preprocess: crop (%d,%d,%d)+(%d,%d,%d) outside clip (%d,%d,%d)", t0, h0, w0, To, Ho, Wo, T, H, W);
@@ -444,11 +498,14 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
   PreArgs a;
   a.T = T; a.H = H; a.W = W; a.C = C; a.t0 = t0; a.h0 = h0; a.w0 = w0;
   a.To = To; a.Ho = Ho; a.Wo = Wo; a.out_ld = out_ld;
+  if (wpitch <= 0) { wpitch = Wo; wpad = 0; }
+  CSE_REQUIRE(wpad >= 0 && wpitch >= Wo + wpad, "preprocess: row pitch %d < Wo %d + pad %d", wpitch, Wo, wpad);
+  a.wpitch = wpitch; a.wpad = wpad;
   for (int c = 0; c < 4; ++c) {
     a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
     a.scale[c] = (scale && c < C) ? scale[c] : 1.f;
   }
-  long long total = (long long)n * To * Ho * Wo;
+  long long total = (long long)n * To * Ho * wpitch;
   if (total == 0) return CSE_OK;
   unsigned blocks = (unsigned)((total + 255) / 256);
   using bf = __nv_bfloat16;

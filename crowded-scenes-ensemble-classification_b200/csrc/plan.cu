@@ -65,6 +65,7 @@ static WinGeom geom_of(const cse_op& o) {
   g.kd = o.k[0]; g.kh = o.k[1]; g.kw = o.k[2];
   g.sd = o.s[0]; g.sh = o.s[1]; g.sw = o.s[2];
   g.pd = o.pad[0]; g.ph = o.pad[1]; g.pw = o.pad[2];
+  g.in_wpitch = o.in_wpitch;
   return g;
 }
 
@@ -80,10 +81,11 @@ static int check_span(const cse_plan* p, int64_t off, long long elems, int dt, c
   return CSE_OK;
 }
 
-static long long tensor_span(int n, const int32_t dims[4], int ld) {
+static long long tensor_span(int n, const int32_t dims[4], int ld, int wpitch = 0) {
   // elements from the first to one past the last addressed element of a [n,D,H,W,(C of ld)] slice
-  long long pix = (long long)n * dims[0] * dims[1] * dims[2];
+  long long pix = (long long)n * dims[0] * dims[1] * (wpitch > 0 ? wpitch : dims[2]);
   if (pix == 0) return 0;
+  if (wpitch > 0) return pix * ld;           // padded rows: the whole pitch belongs to the tensor
   return (pix - 1) * ld + dims[3];
 }
 
@@ -146,7 +148,7 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
     const cse_op& o = po.op;
     // bounds of every tensor the op touches
     if (o.kind != CSE_OP_PREPROCESS && o.kind != CSE_OP_SOFTMAX) {
-      if ((rc = check_span(p, o.in0_off, tensor_span(nb, o.in_dims, o.in_ld), o.in_dtype, "in0", false))) return rc;
+      if ((rc = check_span(p, o.in0_off, tensor_span(nb, o.in_dims, o.in_ld, o.in_wpitch), o.in_dtype, "in0", false))) return rc;
     }
     if (o.kind == CSE_OP_SOFTMAX) {
       long long e = (long long)nb * o.in_dims[3];
@@ -154,7 +156,8 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
       if ((rc = check_span(p, o.out0_off, e, CSE_F32, "softmax out", false))) return rc;
       continue;
     }
-    if ((rc = check_span(p, o.out0_off, tensor_span(nb, o.out_dims, o.out_ld), o.out_dtype, "out0", false))) return rc;
+    if ((rc = check_span(p, o.out0_off, tensor_span(nb, o.out_dims, o.out_ld, o.kind == CSE_OP_PREPROCESS ? o.out_wpitch : 0),
+                         o.out_dtype, "out0", false))) return rc;
     if (o.out1_off >= 0 &&
         (rc = check_span(p, o.out1_off, tensor_span(nb, o.out_dims, o.out1_ld), o.out_dtype, "out1", false))) return rc;
     if (o.in1_off >= 0) {
@@ -202,7 +205,7 @@ static int run_op(cse_plan* p, PlanOp& po, const uint8_t* rgb, const uint8_t* fl
       CSE_REQUIRE(src != nullptr, "plan_run: external input %d is NULL", o.ext_input);
       return launch_preprocess(src, n, o.src_dims[0], o.src_dims[1], o.src_dims[2], o.src_dims[3], o.crop[0],
                                o.crop[1], o.crop[2], o.out_dims[0], o.out_dims[1], o.out_dims[2], o.pre_mean,
-                               o.pre_scale, wsp(o.out0_off), o.out_dtype, o.out_ld, st);
+                               o.pre_scale, wsp(o.out0_off), o.out_dtype, o.out_ld, st, o.out_wpitch, o.out_wpad);
     }
     case CSE_OP_CONV3D: {
       Epilogue ep;

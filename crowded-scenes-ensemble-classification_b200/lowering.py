@@ -56,6 +56,8 @@ class TRef:
     ld: int
     dims: Tuple[int, int, int]
     dtype: int
+    wpitch: int = 0          # row pitch in pixels (0 = dims[2]); > W for the W-padded packed-stem input
+    wpad: int = 0            # zero columns on the left of each row
 
     @property
     def esize(self) -> int:
@@ -132,10 +134,13 @@ class Plan:
             if i0 is not None:
                 s.in_dims[:] = tuple(i0.dims) + (i0.C,)
                 s.in_ld, s.in_dtype, s.in0_off = i0.ld, i0.dtype, i0.byte_off()
+                s.in_wpitch = i0.wpitch
             else:
                 s.in0_off = -1
             s.out_dims[:] = tuple(o0.dims) + (o0.C,)
             s.out_ld, s.out_dtype, s.out0_off = o0.ld, o0.dtype, o0.byte_off()
+            if op.kind == rt.OP_PREPROCESS:
+                s.out_wpitch, s.out_wpad = o0.wpitch, o0.wpad
             if op.in1 is not None:
                 s.in1_ld, s.in1_off = op.in1.ld, op.in1.byte_off()
             else:
@@ -247,8 +252,9 @@ def pack_tc_weights(kernel: np.ndarray, kc: int, bn: int, n_tiles: int) -> np.nd
 class Lowerer:
     def __init__(self, g: Graph, weights: Dict[str, List[np.ndarray]], precision: str = "bf16",
                  max_batch: int = 8, tc: bool = True, tc_strided: bool = False,
-                 crop=None, mean=None, scale=None, keep_all: bool = False):
+                 crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True):
         self.keep_all = keep_all
+        self.packed_stem = packed_stem
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         check_weights(g, weights)
@@ -378,8 +384,17 @@ class Lowerer:
             t0, h0, w0, to, ho, wo = crop
             raise NotImplementedError("crop changes the graph's input shape; build the graph for the cropped shape")
         ld = c if self.act == rt.F32 else 8
-        b = self.new_buf(node.name, (t, h, w), ld, self.act)
-        out = TRef(b, 0, c, ld, (t, h, w), self.act)
+        wpitch = wpad = 0
+        cons = self.consumers[node.name]
+        first = self.g.nodes[cons[0]] if len(cons) == 1 else None
+        if (self.use_tc and self.packed_stem and first is not None and first.op == "conv3d" and c <= 8
+                and first.attrs["k"] == (3, 3, 3) and first.attrs["s"] == (1, 1, 1)
+                and first.attrs["padding"] == "same" and first.attrs["filters"] % 8 == 0):
+            # packed stem: rows padded with zero columns so that the 3 kw taps of a pixel are
+            # 3 (+1 zero-weighted) neighbouring 8-channel pixels = one contiguous 32-wide K chunk
+            wpad, wpitch = 1, w + 4
+        b = self.new_buf(node.name, (t, h, wpitch or w), ld, self.act)
+        out = TRef(b, 0, c, ld, (t, h, w), self.act, wpitch, wpad)
         mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
         scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
         self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
@@ -446,6 +461,9 @@ class Lowerer:
             final = nxt.name
         out_dims = node.out_shape[:3]
         flops = g.conv_dense_flops()[node.name]
+        if x.wpitch:
+            self._packed_stem_conv(node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops)
+            return
         # residual fusion: conv (no bn/relu tail) whose only consumer is add([shortcut, this])
         add = self.sole_consumer(final, "add") if (chain_bn is None and not relu) else None
         if add is not None and len(add.inputs) == 2 and add.inputs[1] == final and add.inputs[0] not in self.val:
@@ -462,6 +480,28 @@ class Lowerer:
         ref = self.ops[-1].out0
         for l in layers:
             self.val[l] = ref
+            self.done.add(l)
+
+    def _packed_stem_conv(self, node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops):
+        """3x3x3 'same' stem on a C<=8 input (C3D conv1, train.py:1230): the kw taps are folded into
+        the channel axis.  The input rows carry one zero column on the left (x.wpad) and >= 2 on the
+        right, channels padded to 8, so the window (w-1 .. w+2) x 8 channels of output pixel w is
+        32 contiguous bf16 values starting at padded column w: an overlapping-stride TMA view
+        [.., W, 32] with pixel stride 8.  The conv becomes k=(3,3,1), Cin=32 with zero weights for
+        the 4th pixel and the padded channels."""
+        kd, kh, kw, ci, co = kernel.shape
+        assert (kd, kh, kw) == (3, 3, 3) and x.wpad == 1 and x.ld == 8
+        k2 = np.zeros((3, 3, 1, 32, co), np.float32)
+        for j in range(3):
+            k2[:, :, 0, j * 8:j * 8 + ci, :] = kernel[:, :, j, :, :]
+        view = TRef(x.buf, 0, 32, 8, x.dims, x.dtype, x.wpitch, x.wpad)
+        saved = self.tc_strided
+        op = self._conv_like(node.name, view, k2, bias, (3, 3, 1), (1, 1, 1), (1, 1, 0), out_dims, chain_bn, relu,
+                             final, layers, flops=flops)
+        if op.engine != rt.ENGINE_TCGEN05:
+            raise RuntimeError("packed stem must lower to the tcgen05 engine")
+        for l in layers:
+            self.val[l] = op.out0
             self.done.add(l)
 
     def _fused_residual(self, node, add, x, kernel, bias, out_dims, flops):

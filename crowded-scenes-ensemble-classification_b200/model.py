@@ -121,9 +121,10 @@ class Member:
         tdt = torch.float32 if ref.dtype == rt.F32 else torch.bfloat16
         es = 4 if ref.dtype == rt.F32 else 2
         start = (self._ws_ptr - self.workspace.data_ptr()) + ref.buf.offset
-        nelem = n * d * h * w * ref.ld
+        wp = ref.wpitch or w
+        nelem = n * d * h * wp * ref.ld
         flat = self.workspace[start:start + nelem * es].view(tdt)
-        t = flat.view(n, d, h, w, ref.ld)[..., ref.coff:ref.coff + ref.C]
+        t = flat.view(n, d, h, wp, ref.ld)[:, :, :, ref.wpad:ref.wpad + w, ref.coff:ref.coff + ref.C]
         return t.float().cpu().numpy()
 
     # ---- host-level API -------------------------------------------------------- #

@@ -150,6 +150,51 @@ def test_conv_tcgen05_vs_oracle(dhw, cin, cout, k, nb):
     assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
 
 
+@pytest.mark.parametrize("dhw,c,cout,nb", [((4, 16, 16), 3, 64, 2), ((3, 9, 13), 3, 24, 3), ((5, 8, 8), 2, 64, 2)])
+def test_conv_tcgen05_packed_stem(dhw, c, cout, nb):
+    """First-layer 3x3x3 conv on the C<=8 uint8 clip (C3D conv1): kw taps folded into a 32-wide K
+    chunk read through an overlapping-stride TMA view of the W-padded pre-processed clip."""
+    def build(g):
+        x = g.input(dhw + (c,), name="in")
+        g.conv3d(x, cout, (3, 3, 3), (1, 1, 1), "same", True, "relu", name="c")
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c)
+    op = [o for o in m.plan.ops if o.name == "c"][0]
+    assert op.engine == rt.ENGINE_TCGEN05 and op.in0.wpitch == dhw[2] + 4
+    xs = clips(8, nb, dhw + (c,))
+    run(m, [xs])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["in"], nb), dtype=T64)
+    assert np.array_equal(xin.numpy(), (xs.astype(np.float64) - 128.0) / 64.0)
+    kern, bias = w["c"]
+    y = O.relu(O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (1, 1, 1), "same"))
+    got = m.read_tensor(m.plan.tensors["c"], nb)
+    err = np.abs(got - y.numpy()).max() / np.abs(y.numpy()).max()
+    assert err <= 2.0 ** -7, "rel err %g" % err
+
+
+STRIDED_TC = [((6, 12, 12), 16, 32, (3, 3, 3), (2, 2, 2), "same"), ((4, 8, 8), 64, 128, (1, 1, 1), (2, 2, 2), "valid"),
+              ((1, 7, 7), 64, 128, (1, 1, 1), (1, 2, 2), "valid"), ((5, 9, 9), 32, 64, (3, 3, 3), (2, 2, 2), "same")]
+
+
+@pytest.mark.parametrize("dhw,cin,cout,k,s,pad", STRIDED_TC)
+def test_conv_tcgen05_strided(dhw, cin, cout, k, s, pad):
+    """Strided convs (R3D stage transitions / projection shortcuts, train.py:1338-1345, 1355-1357) on
+    the tcgen05 engine: TMA elementStrides pick every s-th input position."""
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, cin, (1, 1, 1), (1, 1, 1), "same", True, "relu", name="pre")
+        g.conv3d(x, cout, k, s, pad, True, None, name="c")
+    g, w, m = make_member(build, "bf16", 2, scale=[1 / 64.0] * 3, mean=[128.0] * 3, tc_strided=True)
+    op = [o for o in m.plan.ops if o.name == "c"][0]
+    assert op.engine == rt.ENGINE_TCGEN05
+    run(m, [clips(9, 2, dhw + (3,))])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], 2), dtype=T64)
+    kern, bias = w["c"]
+    y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), s, pad).numpy()
+    got = m.read_tensor(m.plan.tensors["c"], 2)
+    err = np.abs(got - y).max() / np.abs(y).max()
+    assert err <= 2.0 ** -7, "rel err %g" % err
+
+
 def test_conv_tcgen05_partial_batch_and_residual():
     """n < max_batch, residual add + second BN-ReLU output (pre-activation ResNet epilogue)."""
     dhw = (2, 6, 6)
