@@ -78,7 +78,10 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
 
 // tcgen05 engine
 struct ConvTcDesc {            // built once at plan finalize
-  CUtensorMap tmap_a, tmap_b;
+  CUtensorMap tmap_a, tmap_b, tmap_o0, tmap_o1;
+  int ec, nslots;              // epilogue chunk width (channels per TMA store) and staging slots
+  bool has_out1;
+  uint32_t stage_region;
   WinGeom g;
   int kc, bn, n_tiles_n;       // K chunk (channels), N tile, number of N tiles
   int kchunks;                 // chunks per tap = ceil(Ci/kc)
@@ -88,8 +91,8 @@ struct ConvTcDesc {            // built once at plan finalize
   size_t smem_bytes;
   int max_batch;
 };
-int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, int max_batch, const WinGeom& g,
-                  int kc, int bn, const int brick[4]);
+int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
+                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4]);
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);
 
 }  // namespace cse

@@ -65,34 +65,51 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+// Warp-uniform issue: all 32 lanes of the producer / MMA warp run the loops with warp-uniform
+// operands (so ptxas keeps them in uniform registers - no per-instruction R2UR waterfall), and the
+// asynchronous instruction itself is predicated on the lane chosen once by elect.sync.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint32_t pred, uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+               "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t pred, uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
                                             int c1, int c2, int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %8, 0;\n\t"
+      "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t}"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(pred)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+__device__ __forceinline__ void tma_load_2d(uint32_t pred, uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
                                             int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(pred)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void tc_commit(uint32_t pred, uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(pred)
+               : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_bf16(uint32_t pred, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(pred)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -141,26 +158,38 @@ struct ConvTcArgs {
   long long num_tiles;             // m_tiles * n_tiles_n
   int stages;
   uint32_t a_bytes, b_bytes;       // TMA bytes per stage
-  int out_ld;
+  uint32_t stage_region;           // bytes of the A/B pipeline region (1024-aligned)
+  int nslots;                      // staging slots for the TMA-store epilogue
   Epilogue ep;
 };
 
-// KC = channels per stage (16 -> SWIZZLE_32B, 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B)
-template <int KC>
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// KC = channels per pipeline stage (16 -> SWIZZLE_32B, 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B)
+// EC = output channels per epilogue chunk = TMA-store box width (16/32/64, same swizzle family)
+template <int KC, int EC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1,
                const ConvTcArgs a) {
   constexpr uint32_t ROW_BYTES = KC * 2;
   constexpr uint32_t SBO = 8 * ROW_BYTES;
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : (KC == 32 ? 4u : 6u);
   constexpr uint32_t A_STAGE = TC_BM * ROW_BYTES;
+  constexpr uint32_t STG_BYTES = TC_BM * EC * 2;       // one staged [128][EC] bf16 tile
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  // barriers: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty  (byte offsets 0/64/128/144)
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 4];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_par[4][256];                      // scale0, shift0, scale1, shift1 of the N tile
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -168,15 +197,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_stage_bytes = (uint32_t)a.bn * ROW_BYTES;
   const uint32_t stage_bytes = A_STAGE + ((b_stage_bytes + 1023u) & ~1023u);
+  const uint32_t stg_base = smem_base + a.stage_region;
 
+  const uint32_t bar_base = smem_u32(bars);
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(bar_base + 8u * s, 1);
+      mbar_init(bar_base + 64u + 8u * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[b]), 128);
+      mbar_init(bar_base + 128u + 8u * b, 1);
+      mbar_init(bar_base + 144u + 8u * b, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -190,90 +221,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
+  // The CTA owns the SM (1 CTA/SM) and allocates all 512 columns, so the allocation starts at
+  // TMEM address 0; treating it as a constant keeps every TMEM operand warp-uniform.
+  if (tmem_base_smem != 0u) {
+    if (threadIdx.x == 0) printf("cse conv_tc: unexpected TMEM base %u\n", tmem_base_smem);
+    __trap();
+  }
+  const uint32_t tmem_base = 0u;
 
   const int taps = a.kd * a.kh * a.kw;
   const int ksteps = taps * a.kchunks;
-  const int tiles_per_n = a.tiles_d * a.tiles_h * a.tiles_w;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        const int nt = (int)(tile % a.n_tiles_n);
-        long long mt = tile / a.n_tiles_n;
-        const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
-        const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
-        const int td = (int)(mt % a.tiles_d);
-        const int tn = (int)(mt / a.tiles_d);
-        const int iw0 = tw * a.b_w * a.sw - a.pw;
-        const int ih0 = th * a.b_h * a.sh - a.ph;
-        const int id0 = td * a.b_d * a.sd - a.pd;
-        const int n0 = tn * a.b_n;
-        int kstep = 0;
-        for (int fd = 0; fd < a.kd; ++fd)
-          for (int fh = 0; fh < a.kh; ++fh)
-            for (int fw = 0; fw < a.kw; ++fw)
-              for (int ch = 0; ch < a.kchunks; ++ch, ++kstep) {
-                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-                const uint32_t fb = smem_u32(&full_bar[stage]);
-                mbar_expect_tx(fb, a.a_bytes + a.b_bytes);
-                const uint32_t sa = smem_base + stage * stage_bytes;
-                tma_load_5d(sa, &tmap_a, fb, ch * KC, iw0 + fw, ih0 + fh, id0 + fd, n0);
-                tma_load_2d(sa + A_STAGE, &tmap_b, fb, kstep * KC, nt * a.bn);
-                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
-              }
-      }
-    }
-  } else if (warp == 1) {
-    // =============================== MMA issuer =================================
-    // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) |
-                           ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t acc_phase[2] = {0u, 0u};
-    int buf = 0;
-    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      mbar_wait(smem_u32(&tmem_empty_bar[buf]), acc_phase[buf] ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + A_STAGE;
-#pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * 32, SBO, LAYOUT);
-            const uint64_t bd = make_smem_desc(sb + k * 32, SBO, LAYOUT);
-            tc_mma_bf16(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
-          }
-          tc_commit(smem_u32(&empty_bar[stage]));       // frees the smem stage when the MMAs retire
-          if (ks == ksteps - 1) tc_commit(smem_u32(&tmem_full_bar[buf]));
-        }
-        __syncwarp();
-        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
-      }
-      acc_phase[buf] ^= 1u;
-      buf ^= 1;
-    }
-  } else {
-    // =============================== epilogue ===================================
-    const int quad = warp % 4;                      // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;               // tile row = output pixel inside the brick
-    const int rw = row % a.b_w;
-    const int rh = (row / a.b_w) % a.b_h;
-    const int rd = (row / (a.b_w * a.b_h)) % a.b_d;
-    const int rn = row / (a.b_w * a.b_h * a.b_d);
-    uint32_t acc_phase[2] = {0u, 0u};
-    int buf = 0;
-    __nv_bfloat16* out0 = reinterpret_cast<__nv_bfloat16*>(a.ep.out0);
-    __nv_bfloat16* out1 = reinterpret_cast<__nv_bfloat16*>(a.ep.out1);
-    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(a.ep.res);
     for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int nt = (int)(tile % a.n_tiles_n);
       long long mt = tile / a.n_tiles_n;
@@ -281,30 +244,125 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
       const int td = (int)(mt % a.tiles_d);
       const int tn = (int)(mt / a.tiles_d);
-      const int ow = tw * a.b_w + rw, oh = th * a.b_h + rh, od = td * a.b_d + rd, on = tn * a.b_n + rn;
+      const int iw0 = tw * a.b_w * a.sw - a.pw;
+      const int ih0 = th * a.b_h * a.sh - a.ph;
+      const int id0 = td * a.b_d * a.sd - a.pd;
+      const int n0 = tn * a.b_n;
+      const int bcol = nt * a.bn;
+      int kcoord = 0;
+      for (int fd = 0; fd < a.kd; ++fd)
+        for (int fh = 0; fh < a.kh; ++fh)
+          for (int fw = 0; fw < a.kw; ++fw)
+            for (int ch = 0; ch < a.kchunks; ++ch, kcoord += KC) {
+              mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);          // empty[stage]
+              const uint32_t fb = bar_base + 8u * stage;                   // full[stage]
+              mbar_expect_tx_p(leader, fb, a.a_bytes + a.b_bytes);
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              tma_load_5d(leader, sa, &tmap_a, fb, ch * KC, iw0 + fw, ih0 + fh, id0 + fd, n0);
+              tma_load_2d(leader, sa + A_STAGE, &tmap_b, fb, kcoord, bcol);
+              if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
+    const uint32_t leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) |
+                           ((uint32_t)(TC_BM >> 4) << 24);
+    // descriptor template: everything but the 14-bit start address
+    const uint64_t desc_hi = make_smem_desc(0, SBO, LAYOUT);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
+    int buf = 0;
+    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const uint32_t aph = buf ? acc_phase1 : acc_phase0;
+      mbar_wait(bar_base + 128u + 16u + 8u * buf, aph ^ 1u);             // tmem_empty[buf]
+      tc_fence_after();
+      const uint32_t d_tmem = (uint32_t)buf * 256u;                       // TMEM base is 0 (asserted)
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(bar_base + 8u * stage, phase);                           // full[stage]
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        const uint64_t ad = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+        const uint64_t bd = desc_hi | (uint64_t)(((sa + A_STAGE) >> 4) & 0x3FFF);
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k)
+          tc_mma_bf16(leader, d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+        tc_commit(leader, bar_base + 64u + 8u * stage);                    // frees the smem stage when the MMAs retire
+        if (ks == ksteps - 1) tc_commit(leader, bar_base + 128u + 8u * buf);   // tmem_full[buf]
+        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (buf) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
+      buf ^= 1;
+    }
+  } else {
+    // =============================== epilogue ===================================
+    // TMEM -> registers -> scale/shift (+residual) -> ReLU -> bf16 -> swizzled smem staging tile
+    // -> one 5-D TMA store per EC-channel chunk (box = the output brick, clipped at the tensor
+    // edges by the TMA unit, written at the op's channel offset / leading dimension).
+    const int quad = warp % 4;                      // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;               // tile row = output pixel inside the brick
+    const int et = threadIdx.x - 64;                // 0..127 within the epilogue group
+    const bool store_thread = (et == 0);
+    const int rw = row % a.b_w;
+    const int rh = (row / a.b_w) % a.b_h;
+    const int rd = (row / (a.b_w * a.b_h)) % a.b_d;
+    const int rn = row / (a.b_w * a.b_h * a.b_d);
+    // swizzle of the 16-byte chunk index inside a staged row (Swizzle<B,4,3> on byte addresses)
+    const int swz = (EC == 64) ? (row & 7) : (EC == 32 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+    const bool has_out1 = a.ep.out1 != nullptr;
+    const uint32_t slot_bytes = STG_BYTES * (has_out1 ? 2u : 1u);
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(a.ep.res);
+    uint32_t acc_phase[2] = {0u, 0u};
+    int buf = 0;
+    int slot = 0;
+    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int nt = (int)(tile % a.n_tiles_n);
+      long long mt = tile / a.n_tiles_n;
+      const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
+      const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
+      const int td = (int)(mt % a.tiles_d);
+      const int tn = (int)(mt / a.tiles_d);
+      const int ow0 = tw * a.b_w, oh0 = th * a.b_h, od0 = td * a.b_d, on0 = tn * a.b_n;
+      const int col_base = nt * a.bn;
+      // residual addressing (only rows that exist may be read)
+      const int ow = ow0 + rw, oh = oh0 + rh, od = od0 + rd, on = on0 + rn;
       const bool valid = (rn < a.b_n) && ow < a.Wo && oh < a.Ho && od < a.Do && on < a.n_batch;
       const long long pix = (((long long)on * a.Do + od) * a.Ho + oh) * a.Wo + ow;
-      const int col_base = nt * a.bn;
 
-      mbar_wait(smem_u32(&tmem_full_bar[buf]), acc_phase[buf]);
+      // per-tile epilogue parameters -> smem (previous tile's readers are past their last barrier)
+      for (int i = et; i < a.bn; i += 128) {
+        const int c = min(col_base + i, a.Co - 1);
+        s_par[0][i] = a.ep.scale0 ? __ldg(a.ep.scale0 + c) : 1.f;
+        s_par[1][i] = a.ep.shift0 ? __ldg(a.ep.shift0 + c) : 0.f;
+        s_par[2][i] = a.ep.scale1 ? __ldg(a.ep.scale1 + c) : 1.f;
+        s_par[3][i] = a.ep.shift1 ? __ldg(a.ep.shift1 + c) : 0.f;
+      }
+
+      mbar_wait(bar_base + 128u + 8u * buf, acc_phase[buf]);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 256u;
-      for (int c0 = 0; c0 < a.bn; c0 += 16) {
-        uint32_t r[16];
-        tc_ld16(t_row + (uint32_t)c0, r);
+      for (int c0 = 0; c0 < a.bn; c0 += EC) {
+        // the staging slot we are about to overwrite must have been read by its TMA store
+        if (store_thread) {
+          if (a.nslots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else               asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+        }
+        epi_bar();
+        uint32_t r[EC / 16][16];
+#pragma unroll
+        for (int q = 0; q < EC / 16; ++q) tc_ld16(t_row + (uint32_t)(c0 + q * 16), r[q]);
         tc_wait_ld();
-        const int col = col_base + c0;
-        if (valid && col < a.Co) {
+        const uint32_t s0 = stg_base + (uint32_t)slot * slot_bytes + (uint32_t)row * (EC * 2);
+#pragma unroll
+        for (int q = 0; q < EC / 16; ++q) {
           float y[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v = __uint_as_float(r[j]);
-            const int cj = min(col + j, a.Co - 1);       // clamp: tile may overhang Cout
-            if (a.ep.scale0) v *= __ldg(a.ep.scale0 + cj);
-            if (a.ep.shift0) v += __ldg(a.ep.shift0 + cj);
-            y[j] = v;
-          }
-          if (res) {
+          for (int j = 0; j < 16; ++j)
+            y[j] = fmaf(__uint_as_float(r[q][j]), s_par[0][c0 + q * 16 + j], s_par[1][c0 + q * 16 + j]);
+          const int col = col_base + c0 + q * 16;
+          if (res != nullptr && valid && col < a.Co) {
             const uint4* rp = reinterpret_cast<const uint4*>(res + pix * a.ep.res_ld + col);
             uint4 q0 = rp[0], q1 = make_uint4(0u, 0u, 0u, 0u);
             if (col + 8 < a.Co) q1 = rp[1];
@@ -314,34 +372,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = 0; j < 8; ++j) { y[j] += __bfloat162float(e0[j]); y[8 + j] += __bfloat162float(e1[j]); }
           }
           {
-            __align__(16) __nv_bfloat16 o[16];
+            uint32_t p[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = __float2bfloat16_rn(a.ep.relu0 ? fmaxf(y[j], 0.f) : y[j]);
-            uint4* op = reinterpret_cast<uint4*>(out0 + pix * a.out_ld + col);
-            op[0] = reinterpret_cast<const uint4*>(o)[0];
-            if (col + 8 < a.Co) op[1] = reinterpret_cast<const uint4*>(o)[1];
-          }
-          if (out1) {
-            __align__(16) __nv_bfloat16 o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float z = y[j];
-              const int cj = min(col + j, a.Co - 1);
-              if (a.ep.scale1) z *= __ldg(a.ep.scale1 + cj);
-              if (a.ep.shift1) z += __ldg(a.ep.shift1 + cj);
-              o[j] = __float2bfloat16_rn(a.ep.relu1 ? fmaxf(z, 0.f) : z);
+            for (int j = 0; j < 8; ++j) {
+              const float v0 = a.ep.relu0 ? fmaxf(y[2 * j], 0.f) : y[2 * j];
+              const float v1 = a.ep.relu0 ? fmaxf(y[2 * j + 1], 0.f) : y[2 * j + 1];
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              p[j] = *reinterpret_cast<uint32_t*>(&h);
             }
-            uint4* op = reinterpret_cast<uint4*>(out1 + pix * a.ep.out1_ld + col);
-            op[0] = reinterpret_cast<const uint4*>(o)[0];
-            if (col + 8 < a.Co) op[1] = reinterpret_cast<const uint4*>(o)[1];
+            const uint32_t c16 = (uint32_t)(2 * q);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + (((c16) ^ swz) << 4)), "r"(p[0]),
+                         "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + (((c16 + 1) ^ swz) << 4)), "r"(p[4]),
+                         "r"(p[5]), "r"(p[6]), "r"(p[7]) : "memory");
+          }
+          if (has_out1) {
+            uint32_t p[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float z0 = fmaf(y[2 * j], s_par[2][c0 + q * 16 + 2 * j], s_par[3][c0 + q * 16 + 2 * j]);
+              float z1 = fmaf(y[2 * j + 1], s_par[2][c0 + q * 16 + 2 * j + 1], s_par[3][c0 + q * 16 + 2 * j + 1]);
+              if (a.ep.relu1) { z0 = fmaxf(z0, 0.f); z1 = fmaxf(z1, 0.f); }
+              __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1);
+              p[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const uint32_t c16 = (uint32_t)(2 * q);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + STG_BYTES + (((c16) ^ swz) << 4)),
+                         "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + STG_BYTES + (((c16 + 1) ^ swz) << 4)),
+                         "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]) : "memory");
           }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_bar();
+        if (store_thread) {
+          const uint32_t src = stg_base + (uint32_t)slot * slot_bytes;
+          if (col_base + c0 < a.Co) {
+            tma_store_5d(&tmap_o0, src, col_base + c0, ow0, oh0, od0, on0);
+            if (has_out1) tma_store_5d(&tmap_o1, src + STG_BYTES, col_base + c0, ow0, oh0, od0, on0);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (++slot == a.nslots) slot = 0;
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+      mbar_arrive(bar_base + 144u + 8u * buf);
       acc_phase[buf] ^= 1u;
       buf ^= 1;
     }
+    if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -376,15 +455,35 @@ static CUtensorMapSwizzle swizzle_for(int kc) {
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, int max_batch, const WinGeom& g,
-                  int kc, int bn, const int brick[4]) {
+static int encode_out_map(PFN_encodeTiled enc, CUtensorMap* m, void* out, int ld, const WinGeom& g, int max_batch,
+                          int ec, const int brick[4]) {
+  // 5-D map over the NDHWC output (dims C,W,H,D,N), box = EC channels x the output brick
+  cuuint64_t dims[5] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.Do, (cuuint64_t)max_batch};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)g.Wo * ld * 2, (cuuint64_t)g.Ho * g.Wo * ld * 2,
+                           (cuuint64_t)g.Do * g.Ho * g.Wo * ld * 2};
+  cuuint32_t box[5] = {(cuuint32_t)ec, (cuuint32_t)brick[3], (cuuint32_t)brick[2], (cuuint32_t)brick[1], (cuuint32_t)brick[0]};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for(ec), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(out) failed: %d (dims %d,%d,%d,%d,%d ld %d box %u,%u,%u,%u,%u)", (int)r, g.Co, g.Wo,
+              g.Ho, g.Do, max_batch, ld, box[0], box[1], box[2], box[3], box[4]);
+    return CSE_ERR_CUDA;
+  }
+  return CSE_OK;
+}
+
+int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
+                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4]) {
   CSE_REQUIRE(kc == 16 || kc == 32 || kc == 64, "conv_tc: kc=%d must be 16/32/64", kc);
   CSE_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "conv_tc: bn=%d must be a multiple of 16 in [16,256]", bn);
   CSE_REQUIRE(g.Ci % 8 == 0 && g.in_ld % 8 == 0, "conv_tc: Cin=%d / ld=%d must be multiples of 8", g.Ci, g.in_ld);
   CSE_REQUIRE(g.in_wpitch == 0 || g.in_wpitch * g.in_ld >= (g.Wi - 1) * g.in_ld + g.Ci,
               "conv_tc: row pitch %d too small for W=%d, window %d", g.in_wpitch, g.Wi, g.Ci);
   CSE_REQUIRE(g.Co % 8 == 0 && g.out_ld % 8 == 0, "conv_tc: Cout=%d / ld=%d must be multiples of 8", g.Co, g.out_ld);
-  CSE_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)w_packed % 16) == 0, "conv_tc: pointers must be 16B aligned");
+  CSE_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)w_packed % 16) == 0 && ((uintptr_t)out0 % 16) == 0 &&
+                  ((uintptr_t)out1 % 16) == 0 && out1_ld % 8 == 0,
+              "conv_tc: pointers must be 16B aligned");
   CSE_REQUIRE(g.sd >= 1 && g.sd <= 8 && g.sh >= 1 && g.sh <= 8 && g.sw >= 1 && g.sw <= 8, "conv_tc: stride out of range");
   const int rows = brick[0] * brick[1] * brick[2] * brick[3];
   CSE_REQUIRE(rows >= 1 && rows <= TC_BM, "conv_tc: brick %dx%dx%dx%d exceeds 128 rows", brick[0], brick[1], brick[2], brick[3]);
@@ -398,6 +497,8 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, int max_b
   d->tiles_d = ceil_div(g.Do, brick[1]);
   d->tiles_h = ceil_div(g.Ho, brick[2]);
   d->tiles_w = ceil_div(g.Wo, brick[3]);
+  d->ec = (bn % 64 == 0) ? 64 : (bn % 32 == 0 ? 32 : 16);
+  d->has_out1 = out1 != nullptr;
 
   // A: 5-D map over the NDHWC activation (dims C,W,H,D,N).  With stride s the box spans b*s
   // input positions and elementStrides = s picks every s-th one (b elements land in smem).
@@ -435,32 +536,53 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, int max_b
       return CSE_ERR_CUDA;
     }
   }
+  int rc = encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick);
+  if (rc) return rc;
+  rc = encode_out_map(enc, &d->tmap_o1, d->has_out1 ? out1 : out0, d->has_out1 ? out1_ld : g.out_ld, g, max_batch, d->ec,
+                      brick);
+  if (rc) return rc;
+
+  // shared memory: [pipeline stages][epilogue staging slots]; 227 KB per CTA minus static + alignment slack
   const size_t a_stage = (size_t)TC_BM * kc * 2;
   const size_t b_stage = (((size_t)bn * kc * 2) + 1023) & ~(size_t)1023;
   const size_t stage = a_stage + b_stage;
-  const size_t budget = 200 * 1024;
+  const size_t slot = (size_t)TC_BM * d->ec * 2 * (d->has_out1 ? 2 : 1);
+  d->nslots = (slot >= 16384) ? 2 : 4;
+  const size_t staging = slot * d->nslots;
+  const size_t budget = 220 * 1024 - staging;
   int stages = (int)(budget / stage);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   CSE_REQUIRE(stages >= 2, "conv_tc: tile too large for shared memory");
   d->stages = stages;
-  d->smem_bytes = stage * stages + 1024;   // + alignment slack
+  d->stage_region = (uint32_t)(stage * stages);
+  d->smem_bytes = stage * stages + staging + 1024;   // + alignment slack
   return CSE_OK;
 }
 
-template <int KC>
+template <int KC, int EC>
 static int launch_tc_t(const ConvTcDesc& d, const ConvTcArgs& args, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CSE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CSE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<KC><<<grid, TC_THREADS, d.smem_bytes, st>>>(d.tmap_a, d.tmap_b, args);
+  conv_tc_kernel<KC, EC><<<grid, TC_THREADS, d.smem_bytes, st>>>(d.tmap_a, d.tmap_b, d.tmap_o0, d.tmap_o1, args);
   CSE_CUDA(cudaGetLastError());
   return CSE_OK;
 }
 
+template <int KC>
+static int launch_tc_kc(const ConvTcDesc& d, const ConvTcArgs& a, int grid, cudaStream_t st) {
+  switch (d.ec) {
+    case 64: return launch_tc_t<KC, 64>(d, a, grid, st);
+    case 32: return launch_tc_t<KC, 32>(d, a, grid, st);
+    default: return launch_tc_t<KC, 16>(d, a, grid, st);
+  }
+}
+
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st) {
   CSE_REQUIRE(n >= 0 && n <= d.max_batch, "conv_tc: n=%d exceeds max_batch=%d", n, d.max_batch);
+  CSE_REQUIRE((ep.out1 != nullptr) == d.has_out1, "conv_tc: second output does not match the built descriptor");
   if (n == 0) return CSE_OK;
   const WinGeom& g = d.g;
   ConvTcArgs a;
@@ -476,13 +598,14 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   a.stages = d.stages;
   a.a_bytes = (uint32_t)(d.brick[0] * d.brick[1] * d.brick[2] * d.brick[3] * d.kc * 2);
   a.b_bytes = (uint32_t)(d.bn * d.kc * 2);
-  a.out_ld = g.out_ld;
+  a.stage_region = d.stage_region;
+  a.nslots = d.nslots;
   a.ep = ep;
   int grid = (int)(a.num_tiles < (long long)sm_count ? a.num_tiles : (long long)sm_count);
   switch (d.kc) {
-    case 64: return launch_tc_t<64>(d, a, grid, st);
-    case 32: return launch_tc_t<32>(d, a, grid, st);
-    default: return launch_tc_t<16>(d, a, grid, st);
+    case 64: return launch_tc_kc<64>(d, a, grid, st);
+    case 32: return launch_tc_kc<32>(d, a, grid, st);
+    default: return launch_tc_kc<16>(d, a, grid, st);
   }
 }
 
