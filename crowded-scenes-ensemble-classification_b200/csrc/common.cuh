@@ -81,7 +81,8 @@ struct ConvTcDesc {            // built once at plan finalize
   CUtensorMap tmap_a, tmap_b, tmap_o0, tmap_o1;
   int ec, nslots;              // epilogue chunk width (channels per TMA store) and staging slots
   bool has_out1;
-  uint32_t stage_region;
+  int halo;                    // (kd,kh)-halo'd A brick: one pipeline stage per tile
+  uint32_t stage_region, a_bytes, b_bytes, a_stage, stage_bytes;
   WinGeom g;
   int kc, bn, n_tiles_n;       // K chunk (channels), N tile, number of N tiles
   int kchunks;                 // chunks per tap = ceil(Ci/kc)
@@ -92,7 +93,7 @@ struct ConvTcDesc {            // built once at plan finalize
   int max_batch;
 };
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
-                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4]);
+                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo);
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);
 
 }  // namespace cse

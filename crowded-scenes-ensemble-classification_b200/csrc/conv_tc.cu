@@ -155,9 +155,11 @@ struct ConvTcArgs {
   int b_n, b_d, b_h, b_w;          // brick
   int tiles_d, tiles_h, tiles_w;
   int n_batch;                     // clips in this launch
-  long long num_tiles;             // m_tiles * n_tiles_n
+  int num_tiles;                   // m_tiles * n_tiles_n
   int stages;
   uint32_t a_bytes, b_bytes;       // TMA bytes per stage
+  uint32_t a_stage, stage_bytes;   // smem bytes of the A region / of a whole stage (1024-aligned)
+  int halo;                        // 1: one stage per tile holds the (kd,kh)-halo'd A brick + all taps of B
   uint32_t stage_region;           // bytes of the A/B pipeline region (1024-aligned)
   int nslots;                      // staging slots for the TMA-store epilogue
   Epilogue ep;
@@ -182,7 +184,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr uint32_t ROW_BYTES = KC * 2;
   constexpr uint32_t SBO = 8 * ROW_BYTES;
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : (KC == 32 ? 4u : 6u);
-  constexpr uint32_t A_STAGE = TC_BM * ROW_BYTES;
   constexpr uint32_t STG_BYTES = TC_BM * EC * 2;       // one staged [128][EC] bf16 tile
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -195,8 +196,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int lane = threadIdx.x % 32;
   // 1024-byte aligned base for the swizzled tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_stage_bytes = (uint32_t)a.bn * ROW_BYTES;
-  const uint32_t stage_bytes = A_STAGE + ((b_stage_bytes + 1023u) & ~1023u);
+  const uint32_t A_STAGE = a.a_stage;
+  const uint32_t stage_bytes = a.stage_bytes;
   const uint32_t stg_base = smem_base + a.stage_region;
 
   const uint32_t bar_base = smem_u32(bars);
@@ -237,18 +238,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      const int nt = (int)(tile % a.n_tiles_n);
-      long long mt = tile / a.n_tiles_n;
-      const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
-      const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
-      const int td = (int)(mt % a.tiles_d);
-      const int tn = (int)(mt / a.tiles_d);
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int nt = tile % a.n_tiles_n;
+      int mt = tile / a.n_tiles_n;
+      const int tw = mt % a.tiles_w; mt /= a.tiles_w;
+      const int th = mt % a.tiles_h; mt /= a.tiles_h;
+      const int td = mt % a.tiles_d;
+      const int tn = mt / a.tiles_d;
       const int iw0 = tw * a.b_w * a.sw - a.pw;
       const int ih0 = th * a.b_h * a.sh - a.ph;
       const int id0 = td * a.b_d * a.sd - a.pd;
       const int n0 = tn * a.b_n;
       const int bcol = nt * a.bn;
+      if (a.halo) {
+        // halo mode: the A box carries kd-1 / kh-1 extra planes / rows; every (fd,fh) tap is a
+        // swizzle-atom-aligned row offset into it, so one load feeds all taps of the tile
+        mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);
+        const uint32_t fb = bar_base + 8u * stage;
+        mbar_expect_tx_p(leader, fb, a.a_bytes + a.b_bytes);
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        tma_load_5d(leader, sa, &tmap_a, fb, 0, iw0, ih0, id0, n0);
+        const uint32_t b_fd = (uint32_t)(a.kh * a.bn) * ROW_BYTES;
+        for (int fd = 0; fd < a.kd; ++fd)
+          tma_load_2d(leader, sa + A_STAGE + fd * b_fd, &tmap_b, fb, 0, (nt * a.kd + fd) * a.kh * a.bn);
+        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        continue;
+      }
       int kcoord = 0;
       for (int fd = 0; fd < a.kd; ++fd)
         for (int fh = 0; fh < a.kh; ++fh)
@@ -275,11 +290,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t phase = 0;
     uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     int buf = 0;
-    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const uint32_t aph = buf ? acc_phase1 : acc_phase0;
       mbar_wait(bar_base + 128u + 16u + 8u * buf, aph ^ 1u);             // tmem_empty[buf]
       tc_fence_after();
       const uint32_t d_tmem = (uint32_t)buf * 256u;                       // TMEM base is 0 (asserted)
+      if (a.halo) {
+        mbar_wait(bar_base + 8u * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+        const uint64_t bd0 = desc_hi | (uint64_t)(((sa + A_STAGE) >> 4) & 0x3FFF);
+        const uint32_t a_fh = ((uint32_t)a.b_w * ROW_BYTES) >> 4;                       // one brick row of pixels
+        const uint32_t a_fd = ((uint32_t)(a.b_h + a.kh - 1) * a.b_w * ROW_BYTES) >> 4;  // one halo plane
+        const uint32_t b_tap = ((uint32_t)a.bn * ROW_BYTES) >> 4;
+        uint32_t tap = 0;
+        for (int fd = 0; fd < a.kd; ++fd)
+          for (int fh = 0; fh < a.kh; ++fh, ++tap) {
+            const uint64_t ad = ad0 + (uint64_t)(fd * a_fd + fh * a_fh);
+            const uint64_t bd = bd0 + (uint64_t)(tap * b_tap);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k)
+              tc_mma_bf16(leader, d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (tap > 0 || k > 0) ? 1u : 0u);
+          }
+        tc_commit(leader, bar_base + 64u + 8u * stage);
+        tc_commit(leader, bar_base + 128u + 8u * buf);
+        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        if (buf) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
+        buf ^= 1;
+        continue;
+      }
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(bar_base + 8u * stage, phase);                           // full[stage]
         tc_fence_after();
@@ -317,13 +357,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase[2] = {0u, 0u};
     int buf = 0;
     int slot = 0;
-    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      const int nt = (int)(tile % a.n_tiles_n);
-      long long mt = tile / a.n_tiles_n;
-      const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
-      const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
-      const int td = (int)(mt % a.tiles_d);
-      const int tn = (int)(mt / a.tiles_d);
+    int last_nt = -1;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int nt = tile % a.n_tiles_n;
+      int mt = tile / a.n_tiles_n;
+      const int tw = mt % a.tiles_w; mt /= a.tiles_w;
+      const int th = mt % a.tiles_h; mt /= a.tiles_h;
+      const int td = mt % a.tiles_d;
+      const int tn = mt / a.tiles_d;
       const int ow0 = tw * a.b_w, oh0 = th * a.b_h, od0 = td * a.b_d, on0 = tn * a.b_n;
       const int col_base = nt * a.bn;
       // residual addressing (only rows that exist may be read)
@@ -331,7 +372,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool valid = (rn < a.b_n) && ow < a.Wo && oh < a.Ho && od < a.Do && on < a.n_batch;
       const long long pix = (((long long)on * a.Do + od) * a.Ho + oh) * a.Wo + ow;
 
-      // per-tile epilogue parameters -> smem (previous tile's readers are past their last barrier)
+      // epilogue parameters of this N tile -> smem (previous tile's readers are past their last
+      // barrier); only when the N tile changed
+      if (nt != last_nt)
       for (int i = et; i < a.bn; i += 128) {
         const int c = min(col_base + i, a.Co - 1);
         s_par[0][i] = a.ep.scale0 ? __ldg(a.ep.scale0 + c) : 1.f;
@@ -339,6 +382,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         s_par[2][i] = a.ep.scale1 ? __ldg(a.ep.scale1 + c) : 1.f;
         s_par[3][i] = a.ep.shift1 ? __ldg(a.ep.shift1 + c) : 0.f;
       }
+      last_nt = nt;
 
       mbar_wait(bar_base + 128u + 8u * buf, acc_phase[buf]);
       tc_fence_after();
@@ -474,7 +518,7 @@ static int encode_out_map(PFN_encodeTiled enc, CUtensorMap* m, void* out, int ld
 }
 
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
-                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4]) {
+                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo) {
   CSE_REQUIRE(kc == 16 || kc == 32 || kc == 64, "conv_tc: kc=%d must be 16/32/64", kc);
   CSE_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "conv_tc: bn=%d must be a multiple of 16 in [16,256]", bn);
   CSE_REQUIRE(g.Ci % 8 == 0 && g.in_ld % 8 == 0, "conv_tc: Cin=%d / ld=%d must be multiples of 8", g.Ci, g.in_ld);
@@ -499,6 +543,13 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   d->tiles_w = ceil_div(g.Wo, brick[3]);
   d->ec = (bn % 64 == 0) ? 64 : (bn % 32 == 0 ? 32 : 16);
   d->has_out1 = out1 != nullptr;
+  d->halo = halo;
+  const int taps = g.kd * g.kh * g.kw;
+  if (halo) {
+    CSE_REQUIRE(g.kw == 1 && d->kchunks == 1 && g.sd == 1 && g.sh == 1 && g.sw == 1 && brick[0] == 1 && brick[1] == 1 &&
+                    brick[3] % 8 == 0 && g.kh * bn <= 256,
+                "conv_tc: halo mode needs kw=1, Cin<=kc, stride 1, brick (1,1,h,w%%8==0), kh*bn<=256");
+  }
 
   // A: 5-D map over the NDHWC activation (dims C,W,H,D,N).  With stride s the box spans b*s
   // input positions and elementStrides = s picks every s-th one (b elements land in smem).
@@ -511,6 +562,7 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
                              (cuuint64_t)g.Di * g.Hi * wp * g.in_ld * 2};
     cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(brick[3] * g.sw), (cuuint32_t)(brick[2] * g.sh),
                          (cuuint32_t)(brick[1] * g.sd), (cuuint32_t)brick[0]};
+    if (halo) { box[2] = (cuuint32_t)(brick[2] + g.kh - 1); box[3] = (cuuint32_t)(brick[1] + g.kd - 1); }
     cuuint32_t estr[5] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, (cuuint32_t)g.sd, 1};
     CUresult r = enc(&d->tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -523,10 +575,11 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   }
   // B: [Cout_pad][Ktot] bf16, K-major
   {
-    const long long ktot = (long long)g.kd * g.kh * g.kw * d->kchunks * kc;
-    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(d->n_tiles_n * bn)};
+    // halo mode packs B as [n_tile][tap][bn][kc]: one box = the kh taps of one fd plane
+    const long long ktot = halo ? kc : (long long)taps * d->kchunks * kc;
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(d->n_tiles_n * bn) * (halo ? taps : 1)};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(halo ? g.kh * bn : bn)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&d->tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -543,9 +596,22 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   if (rc) return rc;
 
   // shared memory: [pipeline stages][epilogue staging slots]; 227 KB per CTA minus static + alignment slack
-  const size_t a_stage = (size_t)TC_BM * kc * 2;
-  const size_t b_stage = (((size_t)bn * kc * 2) + 1023) & ~(size_t)1023;
+  size_t a_stage = (size_t)TC_BM * kc * 2;
+  size_t b_stage = (((size_t)bn * kc * 2) + 1023) & ~(size_t)1023;
+  d->a_bytes = (uint32_t)(rows * kc * 2);
+  d->b_bytes = (uint32_t)(bn * kc * 2);
+  if (halo) {
+    const size_t halo_rows = (size_t)brick[3] * (brick[2] + g.kh - 1) * (brick[1] + g.kd - 1);
+    d->a_bytes = (uint32_t)(halo_rows * kc * 2);
+    d->b_bytes = (uint32_t)((size_t)taps * bn * kc * 2);
+    // the last tap reads 128 rows starting (kd-1) planes + (kh-1) rows in: stays inside the halo box
+    a_stage = (d->a_bytes + 1023) & ~(size_t)1023;
+    b_stage = (d->b_bytes + 1023) & ~(size_t)1023;
+    CSE_REQUIRE(((size_t)bn * kc * 2) % 1024 == 0 || taps == 1, "conv_tc: halo B taps must be 1024-byte multiples");
+  }
+  d->a_stage = (uint32_t)a_stage;
   const size_t stage = a_stage + b_stage;
+  d->stage_bytes = (uint32_t)stage;
   const size_t slot = (size_t)TC_BM * d->ec * 2 * (d->has_out1 ? 2 : 1);
   d->nslots = (slot >= 16384) ? 2 : 4;
   const size_t staging = slot * d->nslots;
@@ -594,14 +660,16 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   a.tiles_d = d.tiles_d; a.tiles_h = d.tiles_h; a.tiles_w = d.tiles_w;
   a.n_batch = n;
   const long long m_tiles = (long long)ceil_div(n, d.brick[0]) * d.tiles_d * d.tiles_h * d.tiles_w;
-  a.num_tiles = m_tiles * d.n_tiles_n;
+  CSE_REQUIRE(m_tiles * d.n_tiles_n < (1LL << 31), "conv_tc: too many tiles");
+  a.num_tiles = (int)(m_tiles * d.n_tiles_n);
   a.stages = d.stages;
-  a.a_bytes = (uint32_t)(d.brick[0] * d.brick[1] * d.brick[2] * d.brick[3] * d.kc * 2);
-  a.b_bytes = (uint32_t)(d.bn * d.kc * 2);
+  a.a_bytes = d.a_bytes; a.b_bytes = d.b_bytes;
+  a.a_stage = d.a_stage; a.stage_bytes = d.stage_bytes;
+  a.halo = d.halo;
   a.stage_region = d.stage_region;
   a.nslots = d.nslots;
   a.ep = ep;
-  int grid = (int)(a.num_tiles < (long long)sm_count ? a.num_tiles : (long long)sm_count);
+  int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
   switch (d.kc) {
     case 64: return launch_tc_kc<64>(d, a, grid, st);
     case 32: return launch_tc_kc<32>(d, a, grid, st);

@@ -181,7 +181,8 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
         const long long rows = (long long)ceil_div(g.Co, o.bn > 0 ? o.bn : 16) * o.bn;
         if ((rc = check_span(p, o.w_off, ktot * rows, CSE_BF16, "tc weights", true))) return rc;
         rc = conv_tc_build(&po.tc, p->ws + o.in0_off, p->wts + o.w_off, p->ws + o.out0_off,
-                           o.out1_off >= 0 ? p->ws + o.out1_off : nullptr, o.out1_ld, nb, g, o.kc, o.bn, o.brick);
+                           o.out1_off >= 0 ? p->ws + o.out1_off : nullptr, o.out1_ld, nb, g, o.kc, o.bn, o.brick,
+                           o.tc_halo);
         if (rc) return rc;
         po.has_tc = true;
       } else {

@@ -26,7 +26,7 @@ class DeviceEnsemble:
         self.torch = torch
         self.graph = graph
         self.max_batch = int(max_batch)
-        self.micro_batch = int(micro_batch) if micro_batch else min(self.max_batch, 32)
+        self.micro_batch = int(micro_batch) if micro_batch else min(self.max_batch, 128)
         self.members: List[Member] = []
         shared = None
         for w in weight_sets:

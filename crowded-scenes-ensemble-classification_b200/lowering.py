@@ -91,6 +91,7 @@ class DevOp:
     kc: int = 0
     bn: int = 0
     brick: Tuple[int, int, int, int] = (0, 0, 0, 0)
+    halo: int = 0
     w_blob: int = -1
     scale0: int = -1
     shift0: int = -1
@@ -155,7 +156,7 @@ class Plan:
             s.src_dims[:] = op.src_dims
             s.pre_mean[:] = tuple(op.pre_mean)
             s.pre_scale[:] = tuple(op.pre_scale)
-            s.kc, s.bn = op.kc, op.bn
+            s.kc, s.bn, s.tc_halo = op.kc, op.bn, op.halo
             s.brick[:] = op.brick
             bo = self.blob_offsets
             s.w_off = bo[op.w_blob] if op.w_blob >= 0 else -1
@@ -249,11 +250,37 @@ def pack_tc_weights(kernel: np.ndarray, kc: int, bn: int, n_tiles: int) -> np.nd
     return to_bf16_bits(w)
 
 
+def pack_tc_weights_halo(kernel: np.ndarray, kc: int, bn: int, n_tiles: int) -> np.ndarray:
+    """Keras [kd,kh,1,Ci,Co] -> [n_tile][tap][bn][kc] bf16 bits (halo mode: all taps of an N tile
+    are consecutive row blocks of one 2-D tensor with kc columns)."""
+    kd, kh, kw, ci, co = kernel.shape
+    assert kw == 1 and ci <= kc
+    taps = kd * kh
+    w = np.zeros((n_tiles * bn, taps, kc), np.float32)
+    w[:co, :, :ci] = kernel.reshape(taps, ci, co).transpose(2, 0, 1)
+    w = w.reshape(n_tiles, bn, taps, kc).transpose(0, 2, 1, 3)
+    return to_bf16_bits(np.ascontiguousarray(w).reshape(n_tiles * taps * bn, kc))
+
+
+def choose_brick_hw(ho: int, wo: int) -> Tuple[int, int, int, int]:
+    """Brick (1,1,h,w) with w % 8 == 0 (halo mode: a one-row shift must be a whole swizzle atom)."""
+    best, best_key = None, None
+    for bw in range(8, min(_round_up(wo, 8), 128) + 1, 8):
+        for bh in range(1, 128 // bw + 1):
+            tiles = -(-ho // bh) * -(-wo // bw)
+            key = (tiles, -bw)
+            if best_key is None or key < best_key:
+                best, best_key = (1, 1, bh, bw), key
+    return best
+
+
 class Lowerer:
     def __init__(self, g: Graph, weights: Dict[str, List[np.ndarray]], precision: str = "bf16",
                  max_batch: int = 8, tc: bool = True, tc_strided: bool = False,
-                 crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True):
+                 crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
+                 stem_halo: bool = True):
         self.keep_all = keep_all
+        self.stem_halo = stem_halo
         self.packed_stem = packed_stem
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
@@ -403,7 +430,7 @@ class Lowerer:
 
     def _conv_like(self, name, x: TRef, kernel, bias, k, s, pads, out_dims, chain_bn, relu, final_name,
                    layers, out_dtype=None, residual: Optional[TRef] = None, flops=0.0,
-                   second: Optional[Tuple[np.ndarray, np.ndarray, int, str]] = None):
+                   second: Optional[Tuple[np.ndarray, np.ndarray, int, str]] = None, halo: bool = False):
         """Emit one CONV3D op.  chain_bn = (bn_weights, has_gamma) or None."""
         co = kernel.shape[-1]
         out_dtype = self.act if out_dtype is None else out_dtype
@@ -421,8 +448,13 @@ class Lowerer:
             kc = choose_kc(ci)
             bn, n_tiles = choose_bn(co)
             op.engine, op.w_dtype, op.kc, op.bn = rt.ENGINE_TCGEN05, rt.BF16, kc, bn
-            op.brick = choose_brick(self.nb, *out_dims)
-            op.w_blob = self.blob(pack_tc_weights(kernel, kc, bn, n_tiles))
+            if halo and kernel.shape[2] == 1 and ci <= kc and kernel.shape[1] * bn <= 256 and (bn * kc * 2) % 1024 == 0:
+                op.halo = 1
+                op.brick = choose_brick_hw(out_dims[1], out_dims[2])
+                op.w_blob = self.blob(pack_tc_weights_halo(kernel, kc, bn, n_tiles))
+            else:
+                op.brick = choose_brick(self.nb, *out_dims)
+                op.w_blob = self.blob(pack_tc_weights(kernel, kc, bn, n_tiles))
         else:
             op.engine = rt.ENGINE_DIRECT
             kflat = kernel.reshape(-1, co)
@@ -497,7 +529,7 @@ class Lowerer:
         view = TRef(x.buf, 0, 32, 8, x.dims, x.dtype, x.wpitch, x.wpad)
         saved = self.tc_strided
         op = self._conv_like(node.name, view, k2, bias, (3, 3, 1), (1, 1, 1), (1, 1, 0), out_dims, chain_bn, relu,
-                             final, layers, flops=flops)
+                             final, layers, flops=flops, halo=self.stem_halo)
         if op.engine != rt.ENGINE_TCGEN05:
             raise RuntimeError("packed stem must lower to the tcgen05 engine")
         for l in layers:
