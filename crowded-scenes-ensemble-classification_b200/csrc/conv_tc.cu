@@ -14,8 +14,8 @@
 //   (tcgen05.ld -> scale/shift -> +residual -> ReLU -> bf16 -> global) overlaps the main loop
 //   of tile i+1.  Persistent grid: one CTA per SM, static round-robin over tiles.
 //
-//   Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-//   warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+//   Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+//   warps 2..9 = epilogue (TMEM lane quadrant = warp_idx % 4, two warps per quadrant).
 //
 // Replaces the cuDNN FP32 Conv3D the reference reaches through Keras/TF
 // (train.py:653-658, 1230-1258, 1294-1298 ...), with the fused bias / BatchNormalization /
@@ -24,7 +24,7 @@
 
 namespace cse {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_BM = 128;
 constexpr int TC_MAX_STAGES = 8;
 constexpr uint32_t TC_TMEM_COLS = 512;
@@ -131,6 +131,11 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (sm_100 format, version 1).
@@ -160,6 +165,8 @@ struct ConvTcArgs {
   uint32_t a_bytes, b_bytes;       // TMA bytes per stage
   uint32_t a_stage, stage_bytes;   // smem bytes of the A region / of a whole stage (1024-aligned)
   int halo;                        // 1: one stage per tile holds the (kd,kh)-halo'd A brick + all taps of B
+  int b_resident;                  // halo mode, single N tile: B is loaded once per CTA, stages hold A only
+  uint32_t b_region;               // smem offset of the resident B tile
   uint32_t stage_region;           // bytes of the A/B pipeline region (1024-aligned)
   int nslots;                      // staging slots for the TMA-store epilogue
   Epilogue ep;
@@ -172,7 +179,7 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
       ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // KC = channels per pipeline stage (16 -> SWIZZLE_32B, 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B)
 // EC = output channels per epilogue chunk = TMA-store box width (16/32/64, same swizzle family)
@@ -188,9 +195,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // barriers: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty  (byte offsets 0/64/128/144)
-  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 5];   // [20] = resident-B full barrier (byte 160)
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_par[4][256];                      // scale0, shift0, scale1, shift1 of the N tile
+  __shared__ __align__(16) float s_par[2][4][256];                   // per epilogue group: scale0, shift0, scale1, shift1
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -210,6 +217,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(bar_base + 128u + 8u * b, 1);
       mbar_init(bar_base + 144u + 8u * b, 128);
     }
+    mbar_init(bar_base + 160u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -238,6 +246,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
+    if (a.b_resident) {
+      // the whole (single N tile) weight matrix stays in shared memory for the CTA's lifetime
+      const uint32_t bb = bar_base + 160u;
+      mbar_expect_tx_p(leader, bb, a.b_bytes);
+      const uint32_t b_fd = (uint32_t)(a.kh * a.bn) * ROW_BYTES;
+      for (int fd = 0; fd < a.kd; ++fd)
+        tma_load_2d(leader, smem_base + a.b_region + fd * b_fd, &tmap_b, bb, 0, fd * a.kh * a.bn);
+    }
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int nt = tile % a.n_tiles_n;
       int mt = tile / a.n_tiles_n;
@@ -255,12 +271,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // swizzle-atom-aligned row offset into it, so one load feeds all taps of the tile
         mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);
         const uint32_t fb = bar_base + 8u * stage;
-        mbar_expect_tx_p(leader, fb, a.a_bytes + a.b_bytes);
+        mbar_expect_tx_p(leader, fb, a.b_resident ? a.a_bytes : a.a_bytes + a.b_bytes);
         const uint32_t sa = smem_base + stage * stage_bytes;
         tma_load_5d(leader, sa, &tmap_a, fb, 0, iw0, ih0, id0, n0);
-        const uint32_t b_fd = (uint32_t)(a.kh * a.bn) * ROW_BYTES;
-        for (int fd = 0; fd < a.kd; ++fd)
-          tma_load_2d(leader, sa + A_STAGE + fd * b_fd, &tmap_b, fb, 0, (nt * a.kd + fd) * a.kh * a.bn);
+        if (!a.b_resident) {
+          const uint32_t b_fd = (uint32_t)(a.kh * a.bn) * ROW_BYTES;
+          for (int fd = 0; fd < a.kd; ++fd)
+            tma_load_2d(leader, sa + A_STAGE + fd * b_fd, &tmap_b, fb, 0, (nt * a.kd + fd) * a.kh * a.bn);
+        }
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         continue;
       }
@@ -290,6 +308,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t phase = 0;
     uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     int buf = 0;
+    if (a.b_resident) {
+      mbar_wait(bar_base + 160u, 0u);
+      tc_fence_after();
+    }
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const uint32_t aph = buf ? acc_phase1 : acc_phase0;
       mbar_wait(bar_base + 128u + 16u + 8u * buf, aph ^ 1u);             // tmem_empty[buf]
@@ -300,7 +322,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         const uint32_t sa = smem_base + stage * stage_bytes;
         const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
-        const uint64_t bd0 = desc_hi | (uint64_t)(((sa + A_STAGE) >> 4) & 0x3FFF);
+        const uint32_t sb = a.b_resident ? (smem_base + a.b_region) : (sa + A_STAGE);
+        const uint64_t bd0 = desc_hi | (uint64_t)((sb >> 4) & 0x3FFF);
         const uint32_t a_fh = ((uint32_t)a.b_w * ROW_BYTES) >> 4;                       // one brick row of pixels
         const uint32_t a_fd = ((uint32_t)(a.b_h + a.kh - 1) * a.b_w * ROW_BYTES) >> 4;  // one halo plane
         const uint32_t b_tap = ((uint32_t)a.bn * ROW_BYTES) >> 4;
@@ -341,24 +364,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // TMEM -> registers -> scale/shift (+residual) -> ReLU -> bf16 -> swizzled smem staging tile
     // -> one 5-D TMA store per EC-channel chunk (box = the output brick, clipped at the tensor
     // edges by the TMA unit, written at the op's channel offset / leading dimension).
+    // Two independent epilogue groups of 4 warps (one warp per TMEM lane quadrant each): group g
+    // owns accumulator buffer g and drains the CTA's tiles g, g+2, ... so the latency chain of
+    // one tile's epilogue (barrier -> tcgen05.ld -> math -> staging -> TMA store) overlaps the
+    // other group's, and both overlap the MMAs of the following tiles.
+    const int grp = (warp - 2) / 4;
     const int quad = warp % 4;                      // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;               // tile row = output pixel inside the brick
-    const int et = threadIdx.x - 64;                // 0..127 within the epilogue group
+    const int et = threadIdx.x - 64 - grp * 128;    // 0..127 within the group
     const bool store_thread = (et == 0);
     const int rw = row % a.b_w;
     const int rh = (row / a.b_w) % a.b_h;
     const int rd = (row / (a.b_w * a.b_h)) % a.b_d;
     const int rn = row / (a.b_w * a.b_h * a.b_d);
     // swizzle of the 16-byte chunk index inside a staged row (Swizzle<B,4,3> on byte addresses)
-    const int swz = (EC == 64) ? (row & 7) : (EC == 32 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+    const uint32_t swz = (EC == 64) ? (row & 7) : (EC == 32 ? ((row >> 1) & 3) : ((row >> 2) & 1));
     const bool has_out1 = a.ep.out1 != nullptr;
+    const bool has_scale0 = a.ep.scale0 != nullptr;
+    const bool relu0 = a.ep.relu0 != 0, relu1 = a.ep.relu1 != 0;
     const uint32_t slot_bytes = STG_BYTES * (has_out1 ? 2u : 1u);
+    const uint32_t my_stg = stg_base + (uint32_t)grp * (uint32_t)a.nslots * slot_bytes;
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(a.ep.res);
-    uint32_t acc_phase[2] = {0u, 0u};
-    int buf = 0;
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+    float (*par)[256] = s_par[grp];
+    const uint32_t bar_id = 1u + (uint32_t)grp;
+    const int buf = grp;
+    uint32_t acc_phase = 0u;
     int slot = 0;
     int last_nt = -1;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
       const int nt = tile % a.n_tiles_n;
       int mt = tile / a.n_tiles_n;
       const int tw = mt % a.tiles_w; mt /= a.tiles_w;
@@ -367,90 +403,100 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int tn = mt / a.tiles_d;
       const int ow0 = tw * a.b_w, oh0 = th * a.b_h, od0 = td * a.b_d, on0 = tn * a.b_n;
       const int col_base = nt * a.bn;
-      // residual addressing (only rows that exist may be read)
-      const int ow = ow0 + rw, oh = oh0 + rh, od = od0 + rd, on = on0 + rn;
-      const bool valid = (rn < a.b_n) && ow < a.Wo && oh < a.Ho && od < a.Do && on < a.n_batch;
-      const long long pix = (((long long)on * a.Do + od) * a.Ho + oh) * a.Wo + ow;
-
-      // epilogue parameters of this N tile -> smem (previous tile's readers are past their last
-      // barrier); only when the N tile changed
-      if (nt != last_nt)
-      for (int i = et; i < a.bn; i += 128) {
-        const int c = min(col_base + i, a.Co - 1);
-        s_par[0][i] = a.ep.scale0 ? __ldg(a.ep.scale0 + c) : 1.f;
-        s_par[1][i] = a.ep.shift0 ? __ldg(a.ep.shift0 + c) : 0.f;
-        s_par[2][i] = a.ep.scale1 ? __ldg(a.ep.scale1 + c) : 1.f;
-        s_par[3][i] = a.ep.shift1 ? __ldg(a.ep.shift1 + c) : 0.f;
+      bool use_res = false;
+      long long pix = 0;
+      if (res != nullptr) {                         // residual addressing (only rows that exist may be read)
+        const int ow = ow0 + rw, oh = oh0 + rh, od = od0 + rd, on = on0 + rn;
+        use_res = (rn < a.b_n) && ow < a.Wo && oh < a.Ho && od < a.Do && on < a.n_batch;
+        pix = (((long long)on * a.Do + od) * a.Ho + oh) * a.Wo + ow;
       }
-      last_nt = nt;
 
-      mbar_wait(bar_base + 128u + 8u * buf, acc_phase[buf]);
+      // epilogue parameters of this N tile -> smem (this group's previous readers are past their
+      // last barrier); only when the N tile changed
+      if (nt != last_nt) {
+        for (int i = et; i < a.bn; i += 128) {
+          const int c = min(col_base + i, a.Co - 1);
+          par[0][i] = has_scale0 ? __ldg(a.ep.scale0 + c) : 1.f;
+          par[1][i] = a.ep.shift0 ? __ldg(a.ep.shift0 + c) : 0.f;
+          par[2][i] = a.ep.scale1 ? __ldg(a.ep.scale1 + c) : 1.f;
+          par[3][i] = a.ep.shift1 ? __ldg(a.ep.shift1 + c) : 0.f;
+        }
+        last_nt = nt;
+      }
+
+      mbar_wait(bar_base + 128u + 8u * buf, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 256u;
       for (int c0 = 0; c0 < a.bn; c0 += EC) {
         // the staging slot we are about to overwrite must have been read by its TMA store
         if (store_thread) {
-          if (a.nslots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else               asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+          if (a.nslots == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else               asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
-        epi_bar();
-        uint32_t r[EC / 16][16];
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        uint32_t r[EC];
 #pragma unroll
-        for (int q = 0; q < EC / 16; ++q) tc_ld16(t_row + (uint32_t)(c0 + q * 16), r[q]);
+        for (int q = 0; q < EC / 16; ++q) tc_ld16(t_row + (uint32_t)(c0 + q * 16), *reinterpret_cast<uint32_t(*)[16]>(&r[q * 16]));
         tc_wait_ld();
-        const uint32_t s0 = stg_base + (uint32_t)slot * slot_bytes + (uint32_t)row * (EC * 2);
+        const uint32_t s0 = my_stg + (uint32_t)slot * slot_bytes + (uint32_t)row * (EC * 2);
 #pragma unroll
-        for (int q = 0; q < EC / 16; ++q) {
-          float y[16];
+        for (int g8 = 0; g8 < EC / 8; ++g8) {        // groups of 8 columns = one 16-byte staged chunk
+          float y[8];
+          const float4 sh_a = *reinterpret_cast<const float4*>(&par[1][c0 + g8 * 8]);
+          const float4 sh_b = *reinterpret_cast<const float4*>(&par[1][c0 + g8 * 8 + 4]);
+          const float shv[8] = {sh_a.x, sh_a.y, sh_a.z, sh_a.w, sh_b.x, sh_b.y, sh_b.z, sh_b.w};
+          if (has_scale0) {
+            const float4 sc_a = *reinterpret_cast<const float4*>(&par[0][c0 + g8 * 8]);
+            const float4 sc_b = *reinterpret_cast<const float4*>(&par[0][c0 + g8 * 8 + 4]);
+            const float scv[8] = {sc_a.x, sc_a.y, sc_a.z, sc_a.w, sc_b.x, sc_b.y, sc_b.z, sc_b.w};
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            y[j] = fmaf(__uint_as_float(r[q][j]), s_par[0][c0 + q * 16 + j], s_par[1][c0 + q * 16 + j]);
-          const int col = col_base + c0 + q * 16;
-          if (res != nullptr && valid && col < a.Co) {
-            const uint4* rp = reinterpret_cast<const uint4*>(res + pix * a.ep.res_ld + col);
-            uint4 q0 = rp[0], q1 = make_uint4(0u, 0u, 0u, 0u);
-            if (col + 8 < a.Co) q1 = rp[1];
-            const __nv_bfloat16* e0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
-            const __nv_bfloat16* e1 = reinterpret_cast<const __nv_bfloat16*>(&q1);
+            for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(r[g8 * 8 + j]), scv[j], shv[j]);
+          } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { y[j] += __bfloat162float(e0[j]); y[8 + j] += __bfloat162float(e1[j]); }
+            for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[g8 * 8 + j]) + shv[j];
           }
-          {
-            uint32_t p[8];
+          const int col = col_base + c0 + g8 * 8;
+          if (use_res && col < a.Co) {
+            const uint4 q0 = *reinterpret_cast<const uint4*>(res + pix * a.ep.res_ld + col);
+            const __nv_bfloat16* e0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float v0 = a.ep.relu0 ? fmaxf(y[2 * j], 0.f) : y[2 * j];
-              const float v1 = a.ep.relu0 ? fmaxf(y[2 * j + 1], 0.f) : y[2 * j + 1];
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            for (int j = 0; j < 8; ++j) y[j] += __bfloat162float(e0[j]);
+          }
+          const uint32_t c16 = (uint32_t)g8;
+          {
+            uint32_t p[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+              if (relu0) h = __hmax2(h, zero2);
               p[j] = *reinterpret_cast<uint32_t*>(&h);
             }
-            const uint32_t c16 = (uint32_t)(2 * q);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + (((c16) ^ swz) << 4)), "r"(p[0]),
-                         "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + (((c16 + 1) ^ swz) << 4)), "r"(p[4]),
-                         "r"(p[5]), "r"(p[6]), "r"(p[7]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + ((c16 ^ swz) << 4)), "r"(p[0]), "r"(p[1]),
+                         "r"(p[2]), "r"(p[3]) : "memory");
           }
           if (has_out1) {
-            uint32_t p[8];
+            const float4 s1a = *reinterpret_cast<const float4*>(&par[2][c0 + g8 * 8]);
+            const float4 s1b = *reinterpret_cast<const float4*>(&par[2][c0 + g8 * 8 + 4]);
+            const float4 t1a = *reinterpret_cast<const float4*>(&par[3][c0 + g8 * 8]);
+            const float4 t1b = *reinterpret_cast<const float4*>(&par[3][c0 + g8 * 8 + 4]);
+            const float s1[8] = {s1a.x, s1a.y, s1a.z, s1a.w, s1b.x, s1b.y, s1b.z, s1b.w};
+            const float t1[8] = {t1a.x, t1a.y, t1a.z, t1a.w, t1b.x, t1b.y, t1b.z, t1b.w};
+            uint32_t p[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float z0 = fmaf(y[2 * j], s_par[2][c0 + q * 16 + 2 * j], s_par[3][c0 + q * 16 + 2 * j]);
-              float z1 = fmaf(y[2 * j + 1], s_par[2][c0 + q * 16 + 2 * j + 1], s_par[3][c0 + q * 16 + 2 * j + 1]);
-              if (a.ep.relu1) { z0 = fmaxf(z0, 0.f); z1 = fmaxf(z1, 0.f); }
-              __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1);
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(fmaf(y[2 * j], s1[2 * j], t1[2 * j]),
+                                                       fmaf(y[2 * j + 1], s1[2 * j + 1], t1[2 * j + 1]));
+              if (relu1) h = __hmax2(h, zero2);
               p[j] = *reinterpret_cast<uint32_t*>(&h);
             }
-            const uint32_t c16 = (uint32_t)(2 * q);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + STG_BYTES + (((c16) ^ swz) << 4)),
-                         "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + STG_BYTES + (((c16 + 1) ^ swz) << 4)),
-                         "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + STG_BYTES + ((c16 ^ swz) << 4)), "r"(p[0]),
+                         "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        epi_bar();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (store_thread) {
-          const uint32_t src = stg_base + (uint32_t)slot * slot_bytes;
+          const uint32_t src = my_stg + (uint32_t)slot * slot_bytes;
           if (col_base + c0 < a.Co) {
             tma_store_5d(&tmap_o0, src, col_base + c0, ow0, oh0, od0, on0);
             if (has_out1) tma_store_5d(&tmap_o1, src + STG_BYTES, col_base + c0, ow0, oh0, od0, on0);
@@ -461,8 +507,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       mbar_arrive(bar_base + 144u + 8u * buf);
-      acc_phase[buf] ^= 1u;
-      buf ^= 1;
+      acc_phase ^= 1u;
     }
     if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -610,18 +655,21 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
     CSE_REQUIRE(((size_t)bn * kc * 2) % 1024 == 0 || taps == 1, "conv_tc: halo B taps must be 1024-byte multiples");
   }
   d->a_stage = (uint32_t)a_stage;
-  const size_t stage = a_stage + b_stage;
+  d->b_resident = (halo && d->n_tiles_n == 1) ? 1 : 0;
+  const size_t resident = d->b_resident ? b_stage : 0;
+  const size_t stage = d->b_resident ? a_stage : a_stage + b_stage;
   d->stage_bytes = (uint32_t)stage;
   const size_t slot = (size_t)TC_BM * d->ec * 2 * (d->has_out1 ? 2 : 1);
-  d->nslots = (slot >= 16384) ? 2 : 4;
-  const size_t staging = slot * d->nslots;
-  const size_t budget = 220 * 1024 - staging;
+  d->nslots = (slot >= 16384) ? 1 : 2;               // per epilogue group (two groups)
+  const size_t staging = slot * d->nslots * 2;
+  const size_t budget = 214 * 1024 - staging - resident;
   int stages = (int)(budget / stage);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   CSE_REQUIRE(stages >= 2, "conv_tc: tile too large for shared memory");
   d->stages = stages;
-  d->stage_region = (uint32_t)(stage * stages);
-  d->smem_bytes = stage * stages + staging + 1024;   // + alignment slack
+  d->b_region = (uint32_t)(stage * stages);
+  d->stage_region = (uint32_t)(stage * stages + resident);
+  d->smem_bytes = stage * stages + resident + staging + 1024;   // + alignment slack
   return CSE_OK;
 }
 
@@ -629,7 +677,7 @@ template <int KC, int EC>
 static int launch_tc_t(const ConvTcDesc& d, const ConvTcArgs& args, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CSE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+    CSE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));
     attr_set = true;
   }
   conv_tc_kernel<KC, EC><<<grid, TC_THREADS, d.smem_bytes, st>>>(d.tmap_a, d.tmap_b, d.tmap_o0, d.tmap_o1, args);
@@ -665,7 +713,7 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   a.stages = d.stages;
   a.a_bytes = d.a_bytes; a.b_bytes = d.b_bytes;
   a.a_stage = d.a_stage; a.stage_bytes = d.stage_bytes;
-  a.halo = d.halo;
+  a.halo = d.halo; a.b_resident = d.b_resident; a.b_region = d.b_region;
   a.stage_region = d.stage_region;
   a.nslots = d.nslots;
   a.ep = ep;

@@ -488,9 +488,59 @@ preprocess_kernel(const uint8_t* __restrict__ src, TO* __restrict__ out, long lo
   }
 }
 
+// Packed-stem variant: output pixel w carries its 3 horizontal neighbours (w-1, w, w+1; zero
+// outside the row) x C channels, tightly packed (index j*C + c) and zero-padded to 16 channels
+// -> [n,T,H,W,16] bf16 (32 B per pixel).  The 3 kw taps of a 3x3x3 stem conv then are one
+// contiguous, aligned K=16 chunk per pixel.
+__global__ void __launch_bounds__(256)
+preprocess_unroll_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, long long total,
+                         PreArgs a) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  long long t = idx;
+  const int w = (int)(t % a.Wo); t /= a.Wo;
+  const int h = (int)(t % a.Ho); t /= a.Ho;
+  const int d = (int)(t % a.To); const long long nn = t / a.To;
+  __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) v[c] = __float2bfloat16_rn(0.f);
+  const long long row = ((nn * a.T + (d + a.t0)) * a.H + (h + a.h0)) * a.W + a.w0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int ws = w - 1 + j;
+    if (ws >= 0 && ws < a.Wo) {
+      const uint8_t* s = src + (row + ws) * a.C;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < a.C) v[j * a.C + c] = __float2bfloat16_rn(((float)s[c] - a.mean[c]) * a.scale[c]);
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + idx * 16);
+  o[0] = reinterpret_cast<const uint4*>(v)[0];
+  o[1] = reinterpret_cast<const uint4*>(v)[1];
+}
+
 int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int t0, int h0, int w0,
                       int To, int Ho, int Wo, const float* mean, const float* scale, void* out,
-                      int out_dt, int out_ld, cudaStream_t st, int wpitch, int wpad) {
+                      int out_dt, int out_ld, cudaStream_t st, int wpitch, int wpad, int unroll_w) {
+  if (unroll_w > 0) {
+    CSE_REQUIRE(unroll_w == 3 && out_dt == CSE_BF16 && out_ld == 16 && C <= 4 && wpitch <= 0,
+                "preprocess: unroll_w supports k=3, bf16, out_ld=16, C<=4");
+    CSE_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + To <= T && h0 + Ho <= H && w0 + Wo <= W,
+                "preprocess: crop outside clip");
+    PreArgs a;
+    a.T = T; a.H = H; a.W = W; a.C = C; a.t0 = t0; a.h0 = h0; a.w0 = w0;
+    a.To = To; a.Ho = Ho; a.Wo = Wo; a.out_ld = out_ld; a.wpitch = Wo; a.wpad = 0;
+    for (int c = 0; c < 4; ++c) {
+      a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
+      a.scale[c] = (scale && c < C) ? scale[c] : 1.f;
+    }
+    const long long total = (long long)n * To * Ho * Wo;
+    if (total == 0) return CSE_OK;
+    preprocess_unroll_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
+    CSE_CUDA(cudaGetLastError());
+    return CSE_OK;
+  }
   CSE_REQUIRE(C >= 1 && C <= 4, "preprocess: C=%d not in 1..4", C);
   CSE_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + To <= T && h0 + Ho <= H && w0 + Wo <= W,
               "preprocess: crop (%d,%d,%d)+(%d,%d,%d) outside clip (%d,%d,%d)", t0, h0, w0, To, Ho, Wo, T, H, W);

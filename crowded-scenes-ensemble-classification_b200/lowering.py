@@ -58,6 +58,7 @@ class TRef:
     dtype: int
     wpitch: int = 0          # row pitch in pixels (0 = dims[2]); > W for the W-padded packed-stem input
     wpad: int = 0            # zero columns on the left of each row
+    unroll_w: int = 0        # packed stem: channels hold unroll_w neighbouring pixels x 8 channels
 
     @property
     def esize(self) -> int:
@@ -141,7 +142,7 @@ class Plan:
             s.out_dims[:] = tuple(o0.dims) + (o0.C,)
             s.out_ld, s.out_dtype, s.out0_off = o0.ld, o0.dtype, o0.byte_off()
             if op.kind == rt.OP_PREPROCESS:
-                s.out_wpitch, s.out_wpad = o0.wpitch, o0.wpad
+                s.out_wpitch, s.out_wpad, s.pre_unroll_w = o0.wpitch, o0.wpad, o0.unroll_w
             if op.in1 is not None:
                 s.in1_ld, s.in1_off = op.in1.ld, op.in1.byte_off()
             else:
@@ -278,8 +279,9 @@ class Lowerer:
     def __init__(self, g: Graph, weights: Dict[str, List[np.ndarray]], precision: str = "bf16",
                  max_batch: int = 8, tc: bool = True, tc_strided: bool = False,
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
-                 stem_halo: bool = True):
+                 stem_halo: bool = True, stem_unroll: bool = True):
         self.keep_all = keep_all
+        self.stem_unroll = stem_unroll
         self.stem_halo = stem_halo
         self.packed_stem = packed_stem
         if precision not in ("bf16", "fp32"):
@@ -416,9 +418,20 @@ class Lowerer:
         first = self.g.nodes[cons[0]] if len(cons) == 1 else None
         if (self.use_tc and self.packed_stem and first is not None and first.op == "conv3d" and c <= 8
                 and first.attrs["k"] == (3, 3, 3) and first.attrs["s"] == (1, 1, 1)
-                and first.attrs["padding"] == "same" and first.attrs["filters"] % 8 == 0):
-            # packed stem: rows padded with zero columns so that the 3 kw taps of a pixel are
-            # 3 (+1 zero-weighted) neighbouring 8-channel pixels = one contiguous 32-wide K chunk
+                and first.attrs["padding"] == "same" and first.attrs["filters"] % 8 == 0 and c <= 4):
+            # packed stem: the 3 kw taps of a pixel become one contiguous 32-wide K chunk
+            # Either materialised by the pre-processing kernel ([.., W, 16]: 3 pixels x C channels
+            # tightly packed, K = 16 per (fd,fh) tap) or read through an overlapping-stride TMA view of
+            # the W-padded [.., W+4, 8] tensor (3 + 1 zero-weighted 8-channel pixels, K = 32 per tap).
+            if self.stem_unroll:
+                b = self.new_buf(node.name, (t, h, w), 16, self.act)
+                out = TRef(b, 0, c, 16, (t, h, w), self.act, 0, 0, 3)
+                mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
+                scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
+                self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
+                                src_dims=(t, h, w, c), pre_mean=mean, pre_scale=scale, layers=(node.name,)))
+                self.val[node.name] = out
+                return
             wpad, wpitch = 1, w + 4
         b = self.new_buf(node.name, (t, h, wpitch or w), ld, self.act)
         out = TRef(b, 0, c, ld, (t, h, w), self.act, wpitch, wpad)
@@ -493,7 +506,7 @@ class Lowerer:
             final = nxt.name
         out_dims = node.out_shape[:3]
         flops = g.conv_dense_flops()[node.name]
-        if x.wpitch:
+        if x.wpitch or x.unroll_w:
             self._packed_stem_conv(node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops)
             return
         # residual fusion: conv (no bn/relu tail) whose only consumer is add([shortcut, this])
@@ -522,11 +535,19 @@ class Lowerer:
         [.., W, 32] with pixel stride 8.  The conv becomes k=(3,3,1), Cin=32 with zero weights for
         the 4th pixel and the padded channels."""
         kd, kh, kw, ci, co = kernel.shape
-        assert (kd, kh, kw) == (3, 3, 3) and x.wpad == 1 and x.ld == 8
-        k2 = np.zeros((3, 3, 1, 32, co), np.float32)
-        for j in range(3):
-            k2[:, :, 0, j * 8:j * 8 + ci, :] = kernel[:, :, j, :, :]
-        view = TRef(x.buf, 0, 32, 8, x.dims, x.dtype, x.wpitch, x.wpad)
+        assert (kd, kh, kw) == (3, 3, 3)
+        if x.unroll_w:
+            assert 3 * ci <= 16
+            k2 = np.zeros((3, 3, 1, 16, co), np.float32)
+            for j in range(3):
+                k2[:, :, 0, j * ci:(j + 1) * ci, :] = kernel[:, :, j, :, :]
+            view = TRef(x.buf, 0, 16, 16, x.dims, x.dtype)
+        else:
+            k2 = np.zeros((3, 3, 1, 32, co), np.float32)
+            for j in range(3):
+                k2[:, :, 0, j * 8:j * 8 + ci, :] = kernel[:, :, j, :, :]
+            assert x.wpad == 1 and x.ld == 8
+            view = TRef(x.buf, 0, 32, 8, x.dims, x.dtype, x.wpitch, x.wpad)
         saved = self.tc_strided
         op = self._conv_like(node.name, view, k2, bias, (3, 3, 1), (1, 1, 1), (1, 1, 0), out_dims, chain_bn, relu,
                              final, layers, flops=flops, halo=self.stem_halo)

@@ -124,7 +124,8 @@ class Member:
         wp = ref.wpitch or w
         nelem = n * d * h * wp * ref.ld
         flat = self.workspace[start:start + nelem * es].view(tdt)
-        t = flat.view(n, d, h, wp, ref.ld)[:, :, :, ref.wpad:ref.wpad + w, ref.coff:ref.coff + ref.C]
+        coff = ref.coff + (ref.C if getattr(ref, "unroll_w", 0) else 0)  # unrolled stem input: slot 1 = the pixel itself
+        t = flat.view(n, d, h, wp, ref.ld)[:, :, :, ref.wpad:ref.wpad + w, coff:coff + ref.C]
         return t.float().cpu().numpy()
 
     # ---- host-level API -------------------------------------------------------- #

@@ -83,6 +83,9 @@ typedef struct cse_op {
   int32_t in_wpitch;         /* row pitch of in0 in pixels (0 = W): reading a W-padded tensor (TCGEN05 packed stem) */
   int32_t out_wpitch;        /* PREPROCESS: output row pitch in pixels (0 = W); pad columns are written as zeros */
   int32_t out_wpad;          /* PREPROCESS: zero columns on the left of every output row */
+  int32_t pre_unroll_w;      /* PREPROCESS: 3 = every output pixel carries its neighbours w-1,w,w+1 (zero outside
+                                the row), C channels each, packed j*C+c and zero-padded to out_ld = 16 (packed stem) */
+  int32_t reserved[3];
   int32_t tc_halo;           /* TCGEN05: 1 = (kd,kh)-halo'd A brick, weights packed [n_tile][tap][bn][kc] (packed stem) */
   int64_t in0_off, in1_off;  /* workspace byte offsets (-1 = none); in1 = residual for CONV3D, 2nd addend for ADD */
   int64_t out0_off, out1_off;

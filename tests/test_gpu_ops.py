@@ -150,16 +150,17 @@ def test_conv_tcgen05_vs_oracle(dhw, cin, cout, k, nb):
     assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
 
 
+@pytest.mark.parametrize("unroll", [True, False])
 @pytest.mark.parametrize("dhw,c,cout,nb", [((4, 16, 16), 3, 64, 2), ((3, 9, 13), 3, 24, 3), ((5, 8, 8), 2, 64, 2)])
-def test_conv_tcgen05_packed_stem(dhw, c, cout, nb):
+def test_conv_tcgen05_packed_stem(dhw, c, cout, nb, unroll):
     """First-layer 3x3x3 conv on the C<=8 uint8 clip (C3D conv1): kw taps folded into a 32-wide K
     chunk read through an overlapping-stride TMA view of the W-padded pre-processed clip."""
     def build(g):
         x = g.input(dhw + (c,), name="in")
         g.conv3d(x, cout, (3, 3, 3), (1, 1, 1), "same", True, "relu", name="c")
-    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c)
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c, stem_unroll=unroll)
     op = [o for o in m.plan.ops if o.name == "c"][0]
-    assert op.engine == rt.ENGINE_TCGEN05 and op.in0.wpitch == dhw[2] + 4
+    assert op.engine == rt.ENGINE_TCGEN05 and (op.in0.ld == 16 if unroll else op.in0.wpitch == dhw[2] + 4)
     xs = clips(8, nb, dhw + (c,))
     run(m, [xs])
     xin = torch.as_tensor(m.read_tensor(m.plan.tensors["in"], nb), dtype=T64)
