@@ -80,9 +80,11 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
 struct ConvTcDesc {            // built once at plan finalize
   CUtensorMap tmap_a, tmap_b, tmap_o0, tmap_o1;
   int ec, nslots;              // epilogue chunk width (channels per TMA store) and staging slots
+  uint32_t slot_bytes;
   bool has_out1;
   int halo;                    // (kd,kh)-halo'd A brick: one pipeline stage per tile
   int b_resident;              // halo + single N tile: weights stay in smem for the CTA's lifetime
+  int pool[3], pool_dims[3], pool_zero;   // fused MaxPooling3D (window == stride) and its output dims
   uint32_t stage_region, a_bytes, b_bytes, a_stage, stage_bytes, b_region;
   WinGeom g;
   int kc, bn, n_tiles_n;       // K chunk (channels), N tile, number of N tiles
@@ -94,7 +96,8 @@ struct ConvTcDesc {            // built once at plan finalize
   int max_batch;
 };
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
-                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo);
+                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
+                  const int pool_dims[3], int pool_zero);
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);
 
 }  // namespace cse

@@ -169,6 +169,9 @@ struct ConvTcArgs {
   uint32_t b_region;               // smem offset of the resident B tile
   uint32_t stage_region;           // bytes of the A/B pipeline region (1024-aligned)
   int nslots;                      // staging slots for the TMA-store epilogue
+  uint32_t slot_bytes;             // bytes of one staging slot (full tile [+ out1 tile] [+ pooled tile])
+  int pool_d, pool_h, pool_w;      // fused MaxPooling3D window (= stride); 0 = no pooling
+  int pool_zero;                   // rows outside the conv output count as 0 (ZeroPadding3D before the pool)
   Epilogue ep;
 };
 
@@ -382,11 +385,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool has_out1 = a.ep.out1 != nullptr;
     const bool has_scale0 = a.ep.scale0 != nullptr;
     const bool relu0 = a.ep.relu0 != 0, relu1 = a.ep.relu1 != 0;
-    const uint32_t slot_bytes = STG_BYTES * (has_out1 ? 2u : 1u);
+    const uint32_t slot_bytes = a.slot_bytes;
     const uint32_t my_stg = stg_base + (uint32_t)grp * (uint32_t)a.nslots * slot_bytes;
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(a.ep.res);
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     float (*par)[256] = s_par[grp];
+    // fused MaxPooling3D (window == stride, windows never straddle a brick)
+    const bool pooled = a.pool_d > 0;
+    const int pwin = pooled ? a.pool_d * a.pool_h * a.pool_w : 1;
+    const int pb_w = pooled ? a.b_w / a.pool_w : 1, pb_h = pooled ? a.b_h / a.pool_h : 1,
+              pb_d = pooled ? a.b_d / a.pool_d : 1;
+    const int prows = pooled ? (a.b_n * pb_d * pb_h * pb_w) : 0;
+    const uint32_t pool_stg_off = STG_BYTES;        // pooled tile lives right after the full tile of a slot
     const uint32_t bar_id = 1u + (uint32_t)grp;
     const int buf = grp;
     uint32_t acc_phase = 0u;
@@ -403,11 +413,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int tn = mt / a.tiles_d;
       const int ow0 = tw * a.b_w, oh0 = th * a.b_h, od0 = td * a.b_d, on0 = tn * a.b_n;
       const int col_base = nt * a.bn;
-      bool use_res = false;
+      bool use_res = false, row_valid = true;
       long long pix = 0;
-      if (res != nullptr) {                         // residual addressing (only rows that exist may be read)
+      if (res != nullptr || pooled) {               // rows that exist in the conv output
         const int ow = ow0 + rw, oh = oh0 + rh, od = od0 + rd, on = on0 + rn;
-        use_res = (rn < a.b_n) && ow < a.Wo && oh < a.Ho && od < a.Do && on < a.n_batch;
+        row_valid = (rn < a.b_n) && ow < a.Wo && oh < a.Ho && od < a.Do && on < a.n_batch;
+        use_res = row_valid && res != nullptr;
         pix = (((long long)on * a.Do + od) * a.Ho + oh) * a.Wo + ow;
       }
 
@@ -430,8 +441,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int c0 = 0; c0 < a.bn; c0 += EC) {
         // the staging slot we are about to overwrite must have been read by its TMA store
         if (store_thread) {
-          if (a.nslots == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          else               asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          switch (a.nslots) {
+            case 1: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+            case 2: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+            case 3: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+            default: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+          }
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         uint32_t r[EC];
@@ -470,6 +485,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
               if (relu0) h = __hmax2(h, zero2);
               p[j] = *reinterpret_cast<uint32_t*>(&h);
+              if (pooled && !row_valid) p[j] = a.pool_zero ? 0u : 0xFF80FF80u;   // 0 or -inf for rows outside the tensor
             }
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + ((c16 ^ swz) << 4)), "r"(p[0]), "r"(p[1]),
                          "r"(p[2]), "r"(p[3]) : "memory");
@@ -493,13 +509,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                          "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
           }
         }
+        if (pooled) {
+          // window max over the staged tile -> pooled tile [prows][EC] (same swizzle family), then store that
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          const uint32_t full = my_stg + (uint32_t)slot * slot_bytes;
+          const uint32_t pst = full + pool_stg_off;
+          constexpr int V = EC / 8;                   // 16-byte vectors per row
+          for (int v = et; v < prows * V; v += 128) {
+            const int p = v / V, cv = v % V;
+            int q = p;
+            const int pw_ = q % pb_w; q /= pb_w;
+            const int ph_ = q % pb_h; q /= pb_h;
+            const int pd_ = q % pb_d; const int pn_ = q / pb_d;
+            uint32_t m0 = 0xFF80FF80u, m1 = 0xFF80FF80u, m2 = 0xFF80FF80u, m3 = 0xFF80FF80u;   // -inf, -inf
+            for (int i = 0; i < a.pool_d; ++i)
+              for (int j = 0; j < a.pool_h; ++j)
+                for (int l = 0; l < a.pool_w; ++l) {
+                  const int r2 = ((pn_ * a.b_d + pd_ * a.pool_d + i) * a.b_h + ph_ * a.pool_h + j) * a.b_w + pw_ * a.pool_w + l;
+                  const uint32_t sw2 = (EC == 64) ? (r2 & 7) : (EC == 32 ? ((r2 >> 1) & 3) : ((r2 >> 2) & 1));
+                  uint32_t x0, x1, x2, x3;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                               : "r"(full + (uint32_t)r2 * (EC * 2) + (((uint32_t)cv ^ sw2) << 4)));
+                  __nv_bfloat162 t;
+                  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m0), *reinterpret_cast<__nv_bfloat162*>(&x0)); m0 = *reinterpret_cast<uint32_t*>(&t);
+                  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m1), *reinterpret_cast<__nv_bfloat162*>(&x1)); m1 = *reinterpret_cast<uint32_t*>(&t);
+                  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m2), *reinterpret_cast<__nv_bfloat162*>(&x2)); m2 = *reinterpret_cast<uint32_t*>(&t);
+                  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m3), *reinterpret_cast<__nv_bfloat162*>(&x3)); m3 = *reinterpret_cast<uint32_t*>(&t);
+                }
+            const uint32_t swp = (EC == 64) ? (p & 7) : (EC == 32 ? ((p >> 1) & 3) : ((p >> 2) & 1));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pst + (uint32_t)p * (EC * 2) + (((uint32_t)cv ^ swp) << 4)),
+                         "r"(m0), "r"(m1), "r"(m2), "r"(m3) : "memory");
+          }
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (store_thread) {
           const uint32_t src = my_stg + (uint32_t)slot * slot_bytes;
           if (col_base + c0 < a.Co) {
-            tma_store_5d(&tmap_o0, src, col_base + c0, ow0, oh0, od0, on0);
-            if (has_out1) tma_store_5d(&tmap_o1, src + STG_BYTES, col_base + c0, ow0, oh0, od0, on0);
+            if (pooled) {
+              tma_store_5d(&tmap_o0, src + pool_stg_off, col_base + c0, ow0 / a.pool_w, oh0 / a.pool_h, od0 / a.pool_d, on0);
+            } else {
+              tma_store_5d(&tmap_o0, src, col_base + c0, ow0, oh0, od0, on0);
+              if (has_out1) tma_store_5d(&tmap_o1, src + STG_BYTES, col_base + c0, ow0, oh0, od0, on0);
+            }
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -545,12 +597,16 @@ static CUtensorMapSwizzle swizzle_for(int kc) {
 }
 
 static int encode_out_map(PFN_encodeTiled enc, CUtensorMap* m, void* out, int ld, const WinGeom& g, int max_batch,
-                          int ec, const int brick[4]) {
+                          int ec, const int brick[4], const int pool[3] = nullptr, const int pdims[3] = nullptr) {
   // 5-D map over the NDHWC output (dims C,W,H,D,N), box = EC channels x the output brick
-  cuuint64_t dims[5] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.Do, (cuuint64_t)max_batch};
-  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)g.Wo * ld * 2, (cuuint64_t)g.Ho * g.Wo * ld * 2,
-                           (cuuint64_t)g.Do * g.Ho * g.Wo * ld * 2};
-  cuuint32_t box[5] = {(cuuint32_t)ec, (cuuint32_t)brick[3], (cuuint32_t)brick[2], (cuuint32_t)brick[1], (cuuint32_t)brick[0]};
+  // (with a fused pool: the pooled tensor and the pooled brick)
+  const int Do = pool ? pdims[0] : g.Do, Ho = pool ? pdims[1] : g.Ho, Wo = pool ? pdims[2] : g.Wo;
+  const int bd = pool ? brick[1] / pool[0] : brick[1], bh = pool ? brick[2] / pool[1] : brick[2],
+            bw = pool ? brick[3] / pool[2] : brick[3];
+  cuuint64_t dims[5] = {(cuuint64_t)g.Co, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)Do, (cuuint64_t)max_batch};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)Wo * ld * 2, (cuuint64_t)Ho * Wo * ld * 2,
+                           (cuuint64_t)Do * Ho * Wo * ld * 2};
+  cuuint32_t box[5] = {(cuuint32_t)ec, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)brick[0]};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle_for(ec), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -563,7 +619,8 @@ static int encode_out_map(PFN_encodeTiled enc, CUtensorMap* m, void* out, int ld
 }
 
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
-                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo) {
+                  int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
+                  const int pool_dims[3], int pool_zero) {
   CSE_REQUIRE(kc == 16 || kc == 32 || kc == 64, "conv_tc: kc=%d must be 16/32/64", kc);
   CSE_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "conv_tc: bn=%d must be a multiple of 16 in [16,256]", bn);
   CSE_REQUIRE(g.Ci % 8 == 0 && g.in_ld % 8 == 0, "conv_tc: Cin=%d / ld=%d must be multiples of 8", g.Ci, g.in_ld);
@@ -634,7 +691,17 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
       return CSE_ERR_CUDA;
     }
   }
-  int rc = encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick);
+  const bool pooled = pool && pool[0] > 0;
+  for (int i = 0; i < 3; ++i) { d->pool[i] = pooled ? pool[i] : 0; d->pool_dims[i] = pooled ? pool_dims[i] : 0; }
+  d->pool_zero = pooled ? pool_zero : 0;
+  if (pooled) {
+    CSE_REQUIRE(out1 == nullptr, "conv_tc: fused pooling does not support a second output");
+    CSE_REQUIRE(brick[1] % pool[0] == 0 && brick[2] % pool[1] == 0 && brick[3] % pool[2] == 0,
+                "conv_tc: brick %dx%dx%d is not a multiple of the pool window %dx%dx%d", brick[1], brick[2], brick[3],
+                pool[0], pool[1], pool[2]);
+  }
+  int rc = pooled ? encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick, pool, pool_dims)
+                  : encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick);
   if (rc) return rc;
   rc = encode_out_map(enc, &d->tmap_o1, d->has_out1 ? out1 : out0, d->has_out1 ? out1_ld : g.out_ld, g, max_batch, d->ec,
                       brick);
@@ -659,11 +726,22 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   const size_t resident = d->b_resident ? b_stage : 0;
   const size_t stage = d->b_resident ? a_stage : a_stage + b_stage;
   d->stage_bytes = (uint32_t)stage;
-  const size_t slot = (size_t)TC_BM * d->ec * 2 * (d->has_out1 ? 2 : 1);
-  d->nslots = (slot >= 16384) ? 1 : 2;               // per epilogue group (two groups)
-  const size_t staging = slot * d->nslots * 2;
-  const size_t budget = 214 * 1024 - staging - resident;
-  int stages = (int)(budget / stage);
+  size_t slot = (size_t)TC_BM * d->ec * 2 * (d->has_out1 ? 2 : 1);
+  if (pooled) slot += (((size_t)TC_BM / (pool[0] * pool[1] * pool[2])) * d->ec * 2 + 1023) & ~(size_t)1023;
+  // staging slots per epilogue group (two groups): as many as fit (<= 4) while the load pipeline
+  // keeps >= 4 stages (3 for the widest tiles); a TMA store only releases its slot once it has
+  // read it, so more slots = more stores in flight
+  d->slot_bytes = (uint32_t)slot;
+  const int want_stages = (stage >= 48 * 1024) ? 3 : 4;
+  int stages = 0;
+  size_t staging = 0;
+  for (int ns = 4; ns >= 1; --ns) {
+    staging = slot * ns * 2;
+    if (staging + resident + 2 * stage > 214 * 1024) continue;
+    stages = (int)((214 * 1024 - staging - resident) / stage);
+    d->nslots = ns;
+    if (stages >= want_stages) break;
+  }
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   CSE_REQUIRE(stages >= 2, "conv_tc: tile too large for shared memory");
   d->stages = stages;
@@ -714,8 +792,9 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   a.a_bytes = d.a_bytes; a.b_bytes = d.b_bytes;
   a.a_stage = d.a_stage; a.stage_bytes = d.stage_bytes;
   a.halo = d.halo; a.b_resident = d.b_resident; a.b_region = d.b_region;
+  a.pool_d = d.pool[0]; a.pool_h = d.pool[1]; a.pool_w = d.pool[2]; a.pool_zero = d.pool_zero;
   a.stage_region = d.stage_region;
-  a.nslots = d.nslots;
+  a.nslots = d.nslots; a.slot_bytes = d.slot_bytes;
   a.ep = ep;
   int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
   switch (d.kc) {

@@ -93,6 +93,9 @@ class DevOp:
     bn: int = 0
     brick: Tuple[int, int, int, int] = (0, 0, 0, 0)
     halo: int = 0
+    pool_k: Tuple[int, int, int] = (0, 0, 0)
+    pool_zero: int = 0
+    conv_out_dims: Optional[Tuple[int, int, int]] = None   # conv's own output dims when a pool is fused
     w_blob: int = -1
     scale0: int = -1
     shift0: int = -1
@@ -139,8 +142,12 @@ class Plan:
                 s.in_wpitch = i0.wpitch
             else:
                 s.in0_off = -1
-            s.out_dims[:] = tuple(o0.dims) + (o0.C,)
+            s.out_dims[:] = tuple(op.conv_out_dims or o0.dims) + (o0.C,)
             s.out_ld, s.out_dtype, s.out0_off = o0.ld, o0.dtype, o0.byte_off()
+            if op.pool_k[0] > 0:
+                s.pool_k[:] = op.pool_k
+                s.pool_dims[:] = tuple(o0.dims)
+                s.pool_zero = op.pool_zero
             if op.kind == rt.OP_PREPROCESS:
                 s.out_wpitch, s.out_wpad, s.pre_unroll_w = o0.wpitch, o0.wpad, o0.unroll_w
             if op.in1 is not None:
@@ -221,14 +228,16 @@ def choose_bn(co: int) -> Tuple[int, int]:
     return bn, n_tiles
 
 
-def choose_brick(nb: int, do: int, ho: int, wo: int) -> Tuple[int, int, int, int]:
-    """Output-pixel brick (n,d,h,w), product <= 128, minimising the number of M tiles."""
+def choose_brick(nb: int, do: int, ho: int, wo: int, mult=(1, 1, 1)) -> Tuple[int, int, int, int]:
+    """Output-pixel brick (n,d,h,w), product <= 128, minimising the number of M tiles.  `mult`:
+    the (d,h,w) brick dims must be multiples of a fused pool window."""
     best, best_key = None, None
-    for bw in range(1, min(wo, 128) + 1):
+    md, mh, mw = mult
+    for bw in range(mw, min(_round_up(wo, mw), 128) + 1, mw):
         tw = -(-wo // bw)
-        for bh in range(1, min(ho, 128 // bw) + 1):
+        for bh in range(mh, min(_round_up(ho, mh), 128 // bw) + 1, mh):
             th = -(-ho // bh)
-            for bd in range(1, min(do, 128 // (bw * bh)) + 1):
+            for bd in range(md, min(_round_up(do, md), 128 // (bw * bh)) + 1, md):
                 td = -(-do // bd)
                 bn_ = max(1, min(nb, 128 // (bw * bh * bd)))
                 tn = -(-nb // bn_)
@@ -263,11 +272,14 @@ def pack_tc_weights_halo(kernel: np.ndarray, kc: int, bn: int, n_tiles: int) -> 
     return to_bf16_bits(np.ascontiguousarray(w).reshape(n_tiles * taps * bn, kc))
 
 
-def choose_brick_hw(ho: int, wo: int) -> Tuple[int, int, int, int]:
+def choose_brick_hw(ho: int, wo: int, mult=(1, 1, 1)) -> Optional[Tuple[int, int, int, int]]:
     """Brick (1,1,h,w) with w % 8 == 0 (halo mode: a one-row shift must be a whole swizzle atom)."""
     best, best_key = None, None
-    for bw in range(8, min(_round_up(wo, 8), 128) + 1, 8):
-        for bh in range(1, 128 // bw + 1):
+    if mult[0] != 1:
+        return None
+    step_w = 8 * mult[2] // math.gcd(8, mult[2])
+    for bw in range(step_w, min(_round_up(wo, step_w), 128) + 1, step_w):
+        for bh in range(mult[1], 128 // bw + 1, mult[1]):
             tiles = -(-ho // bh) * -(-wo // bw)
             key = (tiles, -bw)
             if best_key is None or key < best_key:
@@ -277,10 +289,11 @@ def choose_brick_hw(ho: int, wo: int) -> Tuple[int, int, int, int]:
 
 class Lowerer:
     def __init__(self, g: Graph, weights: Dict[str, List[np.ndarray]], precision: str = "bf16",
-                 max_batch: int = 8, tc: bool = True, tc_strided: bool = False,
+                 max_batch: int = 8, tc: bool = True, tc_strided: bool = True,
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
-                 stem_halo: bool = True, stem_unroll: bool = True):
+                 stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True):
         self.keep_all = keep_all
+        self.fuse_pool = fuse_pool and precision == "bf16" and tc
         self.stem_unroll = stem_unroll
         self.stem_halo = stem_halo
         self.packed_stem = packed_stem
@@ -443,30 +456,37 @@ class Lowerer:
 
     def _conv_like(self, name, x: TRef, kernel, bias, k, s, pads, out_dims, chain_bn, relu, final_name,
                    layers, out_dtype=None, residual: Optional[TRef] = None, flops=0.0,
-                   second: Optional[Tuple[np.ndarray, np.ndarray, int, str]] = None, halo: bool = False):
-        """Emit one CONV3D op.  chain_bn = (bn_weights, has_gamma) or None."""
+                   second: Optional[Tuple[np.ndarray, np.ndarray, int, str]] = None, halo: bool = False,
+                   pool=None):
+        """Emit one CONV3D op.  chain_bn = (bn_weights, has_gamma) or None.
+        pool = (window, pooled_dims, pad_is_zero): MaxPooling3D fused into the tcgen05 epilogue."""
         co = kernel.shape[-1]
         out_dtype = self.act if out_dtype is None else out_dtype
         scale, shift = fold_bn(bias, chain_bn[0] if chain_bn else None, chain_bn[1] if chain_bn else False, co)
-        out0 = self.out_ref(final_name, out_dims, co, out_dtype)
+        out0 = self.out_ref(final_name, pool[1] if pool else out_dims, co, out_dtype)
         op = DevOp(rt.OP_CONV3D, name, x, residual, out0, k=tuple(k), s=tuple(s), pad=tuple(pads),
                    relu0=int(relu), layers=tuple(layers), flops=flops)
+        mult = (1, 1, 1)
+        if pool:
+            op.pool_k, op.pool_zero, op.conv_out_dims = tuple(pool[0]), int(pool[2]), tuple(out_dims)
+            mult = tuple(pool[0])
         op.scale0, op.shift0 = self.fblob(scale), self.fblob(shift)
         ci = x.C
-        tc_ok = (self.use_tc and x.dtype == rt.BF16 and out_dtype == rt.BF16 and ci % 8 == 0 and x.ld % 8 == 0
-                 and x.coff % 8 == 0 and co % 8 == 0 and co >= 16 and out0.ld % 8 == 0 and out0.coff % 8 == 0
-                 and (self.tc_strided or tuple(s) == (1, 1, 1))
-                 and (residual is None or (residual.ld % 8 == 0 and residual.coff % 8 == 0)))
+        tc_ok = self._tc_ok(x, co, s, out_dtype, residual) and out0.ld % 8 == 0 and out0.coff % 8 == 0
+        if pool and not tc_ok:
+            raise RuntimeError("fused pooling was planned for a conv that cannot use the tcgen05 engine")
         if tc_ok:
             kc = choose_kc(ci)
             bn, n_tiles = choose_bn(co)
             op.engine, op.w_dtype, op.kc, op.bn = rt.ENGINE_TCGEN05, rt.BF16, kc, bn
-            if halo and kernel.shape[2] == 1 and ci <= kc and kernel.shape[1] * bn <= 256 and (bn * kc * 2) % 1024 == 0:
+            hw_brick = choose_brick_hw(out_dims[1], out_dims[2], mult) if halo else None
+            if (hw_brick is not None and kernel.shape[2] == 1 and ci <= kc and kernel.shape[1] * bn <= 256
+                    and (bn * kc * 2) % 1024 == 0):
                 op.halo = 1
-                op.brick = choose_brick_hw(out_dims[1], out_dims[2])
+                op.brick = hw_brick
                 op.w_blob = self.blob(pack_tc_weights_halo(kernel, kc, bn, n_tiles))
             else:
-                op.brick = choose_brick(self.nb, *out_dims)
+                op.brick = choose_brick(self.nb, *out_dims, mult=mult)
                 op.w_blob = self.blob(pack_tc_weights(kernel, kc, bn, n_tiles))
         else:
             op.engine = rt.ENGINE_DIRECT
@@ -483,6 +503,36 @@ class Lowerer:
             op.scale1, op.shift1, op.relu1 = self.fblob(sc1), self.fblob(sh1), int(relu1)
         self.emit(op)
         return op
+
+    def _tc_ok(self, x: TRef, co: int, s, out_dtype: int, residual: Optional[TRef]) -> bool:
+        return (self.use_tc and x.dtype == rt.BF16 and out_dtype == rt.BF16 and x.C % 8 == 0 and x.ld % 8 == 0
+                and x.coff % 8 == 0 and co % 8 == 0 and co >= 16
+                and (self.tc_strided or tuple(s) == (1, 1, 1))
+                and (residual is None or (residual.ld % 8 == 0 and residual.coff % 8 == 0)))
+
+    def _fusable_pool(self, final: str, out_dims):
+        """MaxPooling3D (window == stride, 'valid', optionally behind a ZeroPadding3D that only pads at
+        the end) that is the sole consumer of `final` -> (window, pooled dims, pad_is_zero, layer names)."""
+        if not self.fuse_pool:
+            return None
+        names, zero, cur, dims = [], False, final, tuple(out_dims)
+        zp = self.sole_consumer(cur, "zeropad")
+        if zp is not None:
+            pads = zp.attrs["pads"]
+            if any(p[0] != 0 for p in pads):
+                return None
+            names.append(zp.name)
+            zero, cur = True, zp.name
+            dims = zp.out_shape[:3]
+        mp = self.sole_consumer(cur, "maxpool")
+        if mp is None or mp.attrs["padding"] != "valid" or tuple(mp.attrs["k"]) != tuple(mp.attrs["s"]):
+            return None
+        k = tuple(mp.attrs["k"])
+        if any(128 % kk for kk in k) or k[0] * k[1] * k[2] > 16:
+            return None
+        if mp.name in self.place or (zp is not None and zp.name in self.place):
+            return None
+        return k, tuple(mp.out_shape[:3]), zero, names + [mp.name]
 
     def _conv3d(self, node: Node):
         g = self.g
@@ -506,8 +556,15 @@ class Lowerer:
             final = nxt.name
         out_dims = node.out_shape[:3]
         flops = g.conv_dense_flops()[node.name]
+        pool = None
+        if x.wpitch or x.unroll_w or self._tc_ok(x, kernel.shape[-1], node.attrs["s"], self.act, None):
+            fp = self._fusable_pool(final, out_dims)
+            if fp is not None and final not in self.place:
+                pool = fp[:3]
+                layers = layers + fp[3]
+                final = fp[3][-1]
         if x.wpitch or x.unroll_w:
-            self._packed_stem_conv(node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops)
+            self._packed_stem_conv(node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops, pool)
             return
         # residual fusion: conv (no bn/relu tail) whose only consumer is add([shortcut, this])
         add = self.sole_consumer(final, "add") if (chain_bn is None and not relu) else None
@@ -521,13 +578,13 @@ class Lowerer:
             self._fused_residual(node, add, x, kernel, bias, out_dims, flops)
             return
         self._conv_like(node.name, x, kernel, bias, node.attrs["k"], node.attrs["s"], node.attrs["pads_before"],
-                        out_dims, chain_bn, relu, final, layers, flops=flops)
+                        out_dims, chain_bn, relu, final, layers, flops=flops, pool=pool)
         ref = self.ops[-1].out0
         for l in layers:
             self.val[l] = ref
             self.done.add(l)
 
-    def _packed_stem_conv(self, node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops):
+    def _packed_stem_conv(self, node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops, pool=None):
         """3x3x3 'same' stem on a C<=8 input (C3D conv1, train.py:1230): the kw taps are folded into
         the channel axis.  The input rows carry one zero column on the left (x.wpad) and >= 2 on the
         right, channels padded to 8, so the window (w-1 .. w+2) x 8 channels of output pixel w is
@@ -550,7 +607,7 @@ class Lowerer:
             view = TRef(x.buf, 0, 32, 8, x.dims, x.dtype, x.wpitch, x.wpad)
         saved = self.tc_strided
         op = self._conv_like(node.name, view, k2, bias, (3, 3, 1), (1, 1, 1), (1, 1, 0), out_dims, chain_bn, relu,
-                             final, layers, flops=flops, halo=self.stem_halo)
+                             final, layers, flops=flops, halo=self.stem_halo, pool=pool)
         if op.engine != rt.ENGINE_TCGEN05:
             raise RuntimeError("packed stem must lower to the tcgen05 engine")
         for l in layers:

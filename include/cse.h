@@ -85,7 +85,10 @@ typedef struct cse_op {
   int32_t out_wpad;          /* PREPROCESS: zero columns on the left of every output row */
   int32_t pre_unroll_w;      /* PREPROCESS: 3 = every output pixel carries its neighbours w-1,w,w+1 (zero outside
                                 the row), C channels each, packed j*C+c and zero-padded to out_ld = 16 (packed stem) */
-  int32_t reserved[3];
+  int32_t pool_k[3];         /* TCGEN05: fused MaxPooling3D window (= stride, 'valid'); 0 = none.  out0 is then the
+                                pooled tensor [n, pool_dims, Cout]; out_dims stay the conv's own output dims */
+  int32_t pool_dims[3];      /* D,H,W of the pooled output */
+  int32_t pool_zero;         /* 1 = positions beyond the conv output count as 0 (ZeroPadding3D in front of the pool) */
   int32_t tc_halo;           /* TCGEN05: 1 = (kd,kh)-halo'd A brick, weights packed [n_tile][tap][bn][kc] (packed stem) */
   int64_t in0_off, in1_off;  /* workspace byte offsets (-1 = none); in1 = residual for CONV3D, 2nd addend for ADD */
   int64_t out0_off, out1_off;

@@ -172,6 +172,43 @@ def test_conv_tcgen05_packed_stem(dhw, c, cout, nb, unroll):
     assert err <= 2.0 ** -7, "rel err %g" % err
 
 
+POOL_FUSED = [  # (in dhw, cin, cout, pool k, zeropad, nb)
+    ((4, 8, 8), 64, 128, (2, 2, 2), False, 2),
+    ((4, 16, 16), 64, 64, (1, 2, 2), False, 2),
+    ((2, 7, 7), 64, 512, (2, 2, 2), True, 3),       # C3D conv5b -> zeropad5 -> pool5
+    ((4, 14, 14), 32, 96, (2, 2, 2), False, 2),
+    ((5, 9, 9), 16, 48, (2, 2, 2), False, 2),       # odd dims: 'valid' pooling drops the last row / plane
+]
+
+
+@pytest.mark.parametrize("dhw,cin,cout,pk,zp,nb", POOL_FUSED)
+def test_conv_tcgen05_fused_maxpool(dhw, cin, cout, pk, zp, nb):
+    """MaxPooling3D (window == stride, 'valid') fused into the conv epilogue; conv outputs are signed
+    (no ReLU) so the 0-valued padding of ZeroPadding3D is distinguishable from -inf padding."""
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, cin, (1, 1, 1), (1, 1, 1), "same", True, "relu", name="pre")
+        x = g.conv3d(x, cout, (3, 3, 3), (1, 1, 1), "same", True, None, name="c")
+        if zp:
+            x = g.zeropad(x, ((0, 0), (0, 1), (0, 1)), name="z")
+        g.maxpool(x, pk, pk, "valid", name="p")
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * 3, mean=[128.0] * 3)
+    op = [o for o in m.plan.ops if o.name == "c"][0]
+    assert op.engine == rt.ENGINE_TCGEN05 and op.pool_k == tuple(pk) and len(m.plan.ops) == 3
+    run(m, [clips(10, nb, dhw + (3,))])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], nb), dtype=T64)
+    kern, bias = w["c"]
+    y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (1, 1, 1), "same")
+    y = bf16_round(y.numpy())                       # the kernel pools bf16-rounded conv outputs
+    if zp:
+        y = O.zeropad3d(y, ((0, 0), (0, 1), (0, 1)))
+    exp = O.maxpool3d(y, pk, pk, "valid").numpy()
+    got = m.read_tensor(m.plan.tensors["p"], nb)
+    assert got.shape == exp.shape
+    err = np.abs(got - exp).max() / np.abs(exp).max()
+    assert err <= 2.0 ** -7, "rel err %g" % err
+
+
 STRIDED_TC = [((6, 12, 12), 16, 32, (3, 3, 3), (2, 2, 2), "same"), ((4, 8, 8), 64, 128, (1, 1, 1), (2, 2, 2), "valid"),
               ((1, 7, 7), 64, 128, (1, 1, 1), (1, 2, 2), "valid"), ((5, 9, 9), 32, 64, (3, 3, 3), (2, 2, 2), "same")]
 
