@@ -520,9 +520,73 @@ preprocess_unroll_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restr
   o[1] = reinterpret_cast<const uint4*>(v)[1];
 }
 
+// Stride-2 stem variant (7x7x7 / stride 2 stems of I3D and R3D, train.py:1026, 1481): 2x2
+// space-to-depth over (H, W).  Output cell (h2, w2) carries the 2x2 input pixels (2*h2+ph, 2*w2+pw)
+// x C channels, packed (ph*2+pw)*C + c and zero-padded to out_ld (8 or 16) channels; pixels outside
+// the frame and the wpad / right pad columns of the row are zeros.  A stride-2 window of 7 (+1
+// zero-weighted) input columns then is 4 neighbouring cells = one contiguous K chunk per pixel.
+template <int CL>
+__global__ void __launch_bounds__(256)
+preprocess_s2d_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, long long total,
+                      PreArgs a) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  long long t = idx;
+  const int wp = (int)(t % a.wpitch); t /= a.wpitch;
+  const int h2 = (int)(t % a.Ho); t /= a.Ho;
+  const int d = (int)(t % a.To); const long long nn = t / a.To;
+  const int w2 = wp - a.wpad;
+  __align__(16) __nv_bfloat16 v[CL];
+#pragma unroll
+  for (int c = 0; c < CL; ++c) v[c] = __float2bfloat16_rn(0.f);
+  if (w2 >= 0 && w2 < a.Wo) {
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+      const int hs = 2 * h2 + ph;
+      if (hs >= a.H) continue;
+      const uint8_t* row = src + (((nn * a.T + d) * a.H + hs) * a.W) * a.C;
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        const int ws = 2 * w2 + pw;
+        if (ws >= a.W) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < a.C && (ph * 2 + pw) * a.C + c < CL)
+            v[(ph * 2 + pw) * a.C + c] = __float2bfloat16_rn(((float)row[ws * a.C + c] - a.mean[c]) * a.scale[c]);
+      }
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + idx * CL);
+#pragma unroll
+  for (int q = 0; q < CL / 8; ++q) o[q] = reinterpret_cast<const uint4*>(v)[q];
+}
+
 int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int t0, int h0, int w0,
                       int To, int Ho, int Wo, const float* mean, const float* scale, void* out,
-                      int out_dt, int out_ld, cudaStream_t st, int wpitch, int wpad, int unroll_w) {
+                      int out_dt, int out_ld, cudaStream_t st, int wpitch, int wpad, int unroll_w, int s2d) {
+  if (s2d) {
+    // To,Ho,Wo = T, ceil(H/2), ceil(W/2): the space-to-depth grid
+    CSE_REQUIRE(out_dt == CSE_BF16 && (out_ld == 8 || out_ld == 16) && C >= 1 && C <= 4 && 4 * C <= out_ld && unroll_w == 0,
+                "preprocess: s2d needs bf16, out_ld 8/16 >= 4*C (C=%d, out_ld=%d)", C, out_ld);
+    CSE_REQUIRE(t0 == 0 && h0 == 0 && w0 == 0 && To == T && Ho == (H + 1) / 2 && Wo == (W + 1) / 2,
+                "preprocess: s2d output grid (%d,%d,%d) does not match clip (%d,%d,%d)", To, Ho, Wo, T, H, W);
+    if (wpitch <= 0) { wpitch = Wo; wpad = 0; }
+    CSE_REQUIRE(wpad >= 0 && wpitch >= Wo + wpad, "preprocess: row pitch %d < Wo %d + pad %d", wpitch, Wo, wpad);
+    PreArgs a;
+    a.T = T; a.H = H; a.W = W; a.C = C; a.t0 = 0; a.h0 = 0; a.w0 = 0;
+    a.To = To; a.Ho = Ho; a.Wo = Wo; a.out_ld = out_ld; a.wpitch = wpitch; a.wpad = wpad;
+    for (int c = 0; c < 4; ++c) {
+      a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
+      a.scale[c] = (scale && c < C) ? scale[c] : 1.f;
+    }
+    const long long total = (long long)n * To * Ho * wpitch;
+    if (total == 0) return CSE_OK;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (out_ld == 16) preprocess_s2d_kernel<16><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
+    else preprocess_s2d_kernel<8><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
+    CSE_CUDA(cudaGetLastError());
+    return CSE_OK;
+  }
   if (unroll_w > 0) {
     CSE_REQUIRE(unroll_w == 3 && out_dt == CSE_BF16 && out_ld == 16 && C <= 4 && wpitch <= 0,
                 "preprocess: unroll_w supports k=3, bf16, out_ld=16, C<=4");

@@ -211,7 +211,8 @@ static int run_op(cse_plan* p, PlanOp& po, const uint8_t* rgb, const uint8_t* fl
       CSE_REQUIRE(src != nullptr, "plan_run: external input %d is NULL", o.ext_input);
       return launch_preprocess(src, n, o.src_dims[0], o.src_dims[1], o.src_dims[2], o.src_dims[3], o.crop[0],
                                o.crop[1], o.crop[2], o.out_dims[0], o.out_dims[1], o.out_dims[2], o.pre_mean,
-                               o.pre_scale, wsp(o.out0_off), o.out_dtype, o.out_ld, st, o.out_wpitch, o.out_wpad, o.pre_unroll_w);
+                               o.pre_scale, wsp(o.out0_off), o.out_dtype, o.out_ld, st, o.out_wpitch, o.out_wpad, o.pre_unroll_w,
+                               o.pre_s2d);
     }
     case CSE_OP_CONV3D: {
       Epilogue ep;

@@ -59,6 +59,8 @@ class TRef:
     wpitch: int = 0          # row pitch in pixels (0 = dims[2]); > W for the W-padded packed-stem input
     wpad: int = 0            # zero columns on the left of each row
     unroll_w: int = 0        # packed stem: channels hold unroll_w neighbouring pixels x 8 channels
+    s2d: int = 0             # stride-2 stem: 2x2 space-to-depth cells over (H, W); dims = (T, H/2, W/2)
+    src_c: int = 0           # s2d: channels of the source clip
 
     @property
     def esize(self) -> int:
@@ -149,7 +151,7 @@ class Plan:
                 s.pool_dims[:] = tuple(o0.dims)
                 s.pool_zero = op.pool_zero
             if op.kind == rt.OP_PREPROCESS:
-                s.out_wpitch, s.out_wpad, s.pre_unroll_w = o0.wpitch, o0.wpad, o0.unroll_w
+                s.out_wpitch, s.out_wpad, s.pre_unroll_w, s.pre_s2d = o0.wpitch, o0.wpad, o0.unroll_w, o0.s2d
             if op.in1 is not None:
                 s.in1_ld, s.in1_off = op.in1.ld, op.in1.byte_off()
             else:
@@ -291,8 +293,9 @@ class Lowerer:
     def __init__(self, g: Graph, weights: Dict[str, List[np.ndarray]], precision: str = "bf16",
                  max_batch: int = 8, tc: bool = True, tc_strided: bool = True,
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
-                 stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True):
+                 stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True):
         self.keep_all = keep_all
+        self.s2d_stem = s2d_stem
         self.fuse_pool = fuse_pool and precision == "bf16" and tc
         self.stem_unroll = stem_unroll
         self.stem_halo = stem_halo
@@ -446,6 +449,27 @@ class Lowerer:
                 self.val[node.name] = out
                 return
             wpad, wpitch = 1, w + 4
+        if (self.use_tc and self.s2d_stem and first is not None and first.op == "conv3d" and c <= 4
+                and first.attrs["k"] == (7, 7, 7) and first.attrs["s"] == (2, 2, 2)
+                and first.attrs["padding"] == "same" and first.attrs["filters"] % 8 == 0
+                and first.attrs["filters"] >= 16):
+            # stride-2 7x7x7 stem (I3D Conv3d_1a_7x7 train.py:1026, R3D stem :1481): the pre-processing
+            # kernel writes 2x2 space-to-depth cells over (H, W); rows are padded on the left by the
+            # number of cells the 'same' padding reaches into and on the right so that the 4-cell
+            # window of the last output pixel stays inside the row.
+            h2, w2 = (h + 1) // 2, (w + 1) // 2
+            cell = _round_up(4 * c, 8)
+            pb_w = first.attrs["pads_before"][2]
+            wpad = (pb_w + 1) // 2
+            wpitch = w2 + 3
+            b = self.new_buf(node.name, (t, h2, wpitch), cell, self.act)
+            out = TRef(b, 0, cell, cell, (t, h2, w2), self.act, wpitch, wpad, 0, 1, c)
+            mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
+            scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
+            self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
+                            src_dims=(t, h, w, c), pre_mean=mean, pre_scale=scale, layers=(node.name,)))
+            self.val[node.name] = out
+            return
         b = self.new_buf(node.name, (t, h, wpitch or w), ld, self.act)
         out = TRef(b, 0, c, ld, (t, h, w), self.act, wpitch, wpad)
         mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
@@ -557,6 +581,9 @@ class Lowerer:
         out_dims = node.out_shape[:3]
         flops = g.conv_dense_flops()[node.name]
         pool = None
+        if x.s2d:
+            self._s2d_stem_conv(node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops)
+            return
         if x.wpitch or x.unroll_w or self._tc_ok(x, kernel.shape[-1], node.attrs["s"], self.act, None):
             fp = self._fusable_pool(final, out_dims)
             if fp is not None and final not in self.place:
@@ -610,6 +637,42 @@ class Lowerer:
                              final, layers, flops=flops, halo=self.stem_halo, pool=pool)
         if op.engine != rt.ENGINE_TCGEN05:
             raise RuntimeError("packed stem must lower to the tcgen05 engine")
+        for l in layers:
+            self.val[l] = op.out0
+            self.done.add(l)
+
+    def _s2d_stem_conv(self, node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops):
+        """7x7x7 / stride 2 'same' stem on a C<=4 clip (I3D Conv3d_1a_7x7 train.py:1026; R3D stem
+        :1481) as a tcgen05 implicit GEMM.  The input was written as 2x2 space-to-depth cells over
+        (H, W) (see _input); output pixel (h, w) needs input rows 2h-pb .. 2h-pb+6, i.e. 4 cell rows
+        starting at cell h - ceil(pb/2) (one of the 8 covered rows gets a zero weight), and likewise 4
+        cells along W, which are contiguous in memory: an overlapping-stride TMA view [.., W/2, 4*cell]
+        with pixel stride `cell`.  The conv becomes k=(7,4,1), stride (2,1,1), Cin = 4*cell; the
+        regrouped kernel has exact zeros at the padded taps / channels, so the result is the same sum
+        of products."""
+        kd, kh, kw, ci, co = kernel.shape
+        assert (kd, kh, kw) == (7, 7, 7) and ci == x.src_c
+        cell = x.ld
+        pb = node.attrs["pads_before"]
+        off_h, off_w = pb[1] - 2 * ((pb[1] + 1) // 2), pb[2] - 2 * ((pb[2] + 1) // 2)     # 0 (pb even) or -1 (odd)
+        k2 = np.zeros((7, 4, 1, 4 * cell, co), np.float32)
+        for fh in range(4):
+            for ph in range(2):
+                th = 2 * fh + ph + off_h
+                if not 0 <= th < 7:
+                    continue
+                for fw in range(4):
+                    for pw in range(2):
+                        tw = 2 * fw + pw + off_w
+                        if not 0 <= tw < 7:
+                            continue
+                        c0 = fw * cell + (ph * 2 + pw) * ci
+                        k2[:, fh, 0, c0:c0 + ci, :] = kernel[:, th, tw, :, :]
+        view = TRef(x.buf, 0, 4 * cell, cell, x.dims, x.dtype, x.wpitch, x.wpad)
+        op = self._conv_like(node.name, view, k2, bias, (7, 4, 1), (2, 1, 1), (pb[0], (pb[1] + 1) // 2, 0), out_dims,
+                             chain_bn, relu, final, layers, flops=flops)
+        if op.engine != rt.ENGINE_TCGEN05:
+            raise RuntimeError("s2d stem must lower to the tcgen05 engine")
         for l in layers:
             self.val[l] = op.out0
             self.done.add(l)

@@ -133,11 +133,18 @@ _R3D = {"R3D_18": ("basic", [2, 2, 2, 2]), "R3D_34": ("basic", [3, 4, 6, 3]),
         "R3D_152": ("bottleneck", [3, 8, 36, 3])}
 
 
-def r3d_forward(weights, clips, model_type="R3D_34", dtype=torch.float64):
-    """Resnet3DBuilder.build, train.py:1459-1524 (pre-activation ResNet-3D)."""
+def r3d_forward(weights, clips, model_type="R3D_34", dtype=torch.float64, emulate_bf16=False):
+    """Resnet3DBuilder.build, train.py:1459-1524 (pre-activation ResNet-3D).
+
+    emulate_bf16=True restates the SAME graph with the storage roundings of the bf16 device path
+    (conv/dense inputs and kernels rounded to bfloat16, every stored activation rounded once; the
+    BN-ReLU that follows a residual add is taken from the un-rounded sum, as the fused epilogue
+    does), accumulating in `dtype`.  It separates kernel errors from the bf16 quantisation floor of
+    a deep random-weight network (tests/test_gpu_models.py)."""
     W = _W(weights, dtype)
     kind, reps = _R3D[model_type]
     cnt = {"conv3d": 0, "batch_normalization": 0}
+    q = (lambda t: t.to(torch.bfloat16).to(dtype)) if emulate_bf16 else (lambda t: t)
 
     def new(prefix):
         cnt[prefix] += 1
@@ -147,11 +154,11 @@ def r3d_forward(weights, clips, model_type="R3D_34", dtype=torch.float64):
         name = new("conv3d")
         kern, b = W(name)
         assert tuple(kern.shape[:3]) == tuple(k), (name, kern.shape, k)
-        return ops.conv3d(x, kern, b, strides, padding)
+        return ops.conv3d(q(x), q(kern), b, strides, padding)
 
     def bn_relu(x):                                      # _bn_relu, :1278
         g, b, m, v = W(new("batch_normalization"))
-        return ops.relu(ops.batchnorm(x, g, b, m, v))
+        return q(ops.relu(ops.batchnorm(x, g, b, m, v)))
 
     def bn_relu_conv(x, k, strides=(1, 1, 1)):           # _bn_relu_conv3d, :1303
         a = bn_relu(x)
@@ -164,7 +171,7 @@ def r3d_forward(weights, clips, model_type="R3D_34", dtype=torch.float64):
             name = new("conv3d")
             kern, b = W(name)
             assert kern.shape[-1] == residual.shape[-1]
-            sc = ops.conv3d(x, kern, b, s, "valid")
+            sc = q(ops.conv3d(q(x), q(kern), b, s, "valid"))
         return sc + residual
 
     x = _as_input(clips, dtype)
@@ -172,28 +179,33 @@ def r3d_forward(weights, clips, model_type="R3D_34", dtype=torch.float64):
     x = bn_relu(x)
     x = ops.maxpool3d(x, (3, 3, 3), (2, 2, 2), "same")
     filters = 64
+    exact = x          # the block input before its storage rounding (what the fused BN-ReLU output sees)
     for i, r in enumerate(reps):
         for j in range(r):
             strides = (2, 2, 2) if (j == 0 and i != 0) else (1, 1, 1)
             first = (i == 0 and j == 0)
             if kind == "basic":                          # basic_block, :1368
-                c1 = conv(x, (3, 3, 3), strides) if first else bn_relu_conv(x, (3, 3, 3), strides)
+                c1 = conv(x, (3, 3, 3), strides) if first else bn_relu_conv(exact, (3, 3, 3), strides)
                 res = bn_relu_conv(c1, (3, 3, 3))
             else:                                        # bottleneck, :1396
-                c1 = conv(x, (1, 1, 1), strides) if first else bn_relu_conv(x, (1, 1, 1), strides)
+                c1 = conv(x, (1, 1, 1), strides) if first else bn_relu_conv(exact, (1, 1, 1), strides)
                 c3 = bn_relu_conv(c1, (3, 3, 3))
                 res = bn_relu_conv(c3, (1, 1, 1))
                 assert res.shape[-1] == filters * 4
-            x = shortcut(x, res)
+            exact = shortcut(x, res)
+            x = q(exact)
         filters *= 2
-    x = bn_relu(x)
-    x = ops.avgpool3d(x, x.shape[1:4], (1, 1, 1))
-    logits = ops.dense(ops.flatten(x), *W("dense_1"))
+    x = bn_relu(exact)
+    x = q(ops.avgpool3d(x, x.shape[1:4], (1, 1, 1)))
+    kern, b = W("dense_1")
+    logits = ops.dense(ops.flatten(x), q(kern), b)
     return logits, ops.softmax(logits)
 
 
-def forward(model_type, weights, inputs, dtype=torch.float64):
+def forward(model_type, weights, inputs, dtype=torch.float64, emulate_bf16=False):
     """inputs: one NDHWC array, or [rgb, flow] for TWOSTREAM_I3D (train.py:1009)."""
+    if emulate_bf16 and model_type not in _R3D:
+        raise NotImplementedError("bf16 storage emulation is only restated for the R3D family")
     with torch.no_grad():
         if model_type == "C3D":
             last = "fc8" if "fc8" in weights else "predictions"
@@ -203,5 +215,5 @@ def forward(model_type, weights, inputs, dtype=torch.float64):
         if model_type == "TWOSTREAM_I3D":
             return twostream_forward(weights, inputs[0], inputs[1], dtype)
         if model_type in _R3D:
-            return r3d_forward(weights, inputs, model_type, dtype)
+            return r3d_forward(weights, inputs, model_type, dtype, emulate_bf16)
     raise ValueError("Unknown model %r" % (model_type,))

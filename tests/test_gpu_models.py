@@ -42,6 +42,16 @@ def test_member_fp32_matches_oracle(mt, shape, n):
     assert np.array_equal(probs.argmax(1), exp_probs.numpy().argmax(1))
 
 
+# bf16 logit tolerance vs the fp64 oracle (north-star: 1e-2).  R3D_50 is the one exception: on this
+# 50-layer random-weight bottleneck net rounding ONLY the weights to bfloat16 already moves the
+# logits by 0.6 % and the full bf16 storage emulation of the oracle (no kernel involved) sits at
+# 0.7-1.5 % depending on the clip, i.e. the 1e-2 line runs through the quantisation floor itself.
+# (tests/test_oracle.py::test_bf16_quantisation_floor_r3d50 pins that statement on the CPU.)  Its
+# kernels are pinned per op in test_gpu_ops.py (2^-7 per element), the fp32 path pins the graph at
+# 1e-4, and the whole-net bf16 comparison uses 2e-2.
+BF16_TOL = {"R3D_50": 2e-2}
+
+
 @pytest.mark.parametrize("mt,shape,n", CASES)
 def test_member_bf16_matches_oracle(mt, shape, n):
     g = G.build_model_graph(mt, shape, 11)
@@ -50,8 +60,16 @@ def test_member_bf16_matches_oracle(mt, shape, n):
     exp_logits, exp_probs = OM.forward(mt, w, x, torch.float64)
     m = Member(g, w, precision="bf16", max_batch=4)
     assert any(o.engine == 2 for o in m.plan.ops), "tcgen05 engine not used"
+    stem = [o for o in m.plan.ops if o.kind == 2][0]
+    assert stem.engine == 2, "stem conv is not on the tcgen05 engine"
     probs, logits = m.predict(x, return_logits=True)
-    assert rel_err(logits, exp_logits.numpy()) <= 1e-2
+    assert rel_err(logits, exp_logits.numpy()) <= BF16_TOL.get(mt, 1e-2)
+    if mt.startswith("R3D"):
+        # the device result must be as close to the fp64 truth as the bf16-emulating oracle is
+        # (same storage roundings, fp64 accumulation), up to 2x
+        emu_logits, _ = OM.forward(mt, w, x, torch.float64, emulate_bf16=True)
+        floor = rel_err(emu_logits.numpy(), exp_logits.numpy())
+        assert rel_err(logits, exp_logits.numpy()) <= max(2.0 * floor, 5e-3)
 
 
 def test_twostream_matches_oracle():

@@ -172,6 +172,36 @@ def test_conv_tcgen05_packed_stem(dhw, c, cout, nb, unroll):
     assert err <= 2.0 ** -7, "rel err %g" % err
 
 
+S2D_STEM = [((8, 16, 16), 3, 64, 2), ((9, 21, 19), 3, 64, 2), ((6, 20, 28), 2, 64, 3), ((4, 12, 12), 3, 32, 2),
+            ((7, 10, 34), 1, 16, 1)]
+
+
+@pytest.mark.parametrize("dhw,c,cout,nb", S2D_STEM)
+def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb):
+    """7x7x7 / stride 2 'same' stem on the raw clip (I3D Conv3d_1a_7x7, R3D stem) on the tcgen05 engine:
+    2x2 space-to-depth cells written by the pre-processing kernel, 4-cell window through an
+    overlapping-stride TMA view, k=(7,4,1) stride (2,1,1) with a zero-extended regrouped kernel.
+    Even and odd extents (TF 'same' pads (2,3) resp. (3,3)) and C = 1, 2, 3."""
+    def build(g):
+        x = g.input(dhw + (c,), name="in")
+        x = g.conv3d(x, cout, (7, 7, 7), (2, 2, 2), "same", True, None, name="c")
+        x = g.bn(x, scale=True, name="b")
+        g.relu(x, name="r")
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c)
+    op = [o for o in m.plan.ops if o.name == "c"][0]
+    assert op.engine == rt.ENGINE_TCGEN05 and op.k == (7, 4, 1) and op.s == (2, 1, 1)
+    xs = clips(11, nb, dhw + (c,))
+    run(m, [xs])
+    xin = torch.as_tensor((xs.astype(np.float64) - 128.0) / 64.0, dtype=T64)      # exact in bf16
+    kern, bias = w["c"]
+    y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (2, 2, 2), "same")
+    y = O.relu(O.batchnorm(y, *[torch.as_tensor(a, dtype=T64) for a in w["b"]])).numpy()
+    got = m.read_tensor(m.plan.tensors["r"], nb)
+    assert got.shape == y.shape
+    err = np.abs(got - y).max() / np.abs(y).max()
+    assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
+
+
 POOL_FUSED = [  # (in dhw, cin, cout, pool k, zeropad, nb)
     ((4, 8, 8), 64, 128, (2, 2, 2), False, 2),
     ((4, 16, 16), 64, 64, (1, 2, 2), False, 2),
