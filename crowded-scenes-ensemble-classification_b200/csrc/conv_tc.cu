@@ -172,8 +172,72 @@ struct ConvTcArgs {
   uint32_t slot_bytes;             // bytes of one staging slot (full tile [+ out1 tile] [+ pooled tile])
   int pool_d, pool_h, pool_w;      // fused MaxPooling3D window (= stride); 0 = no pooling
   int pool_zero;                   // rows outside the conv output count as 0 (ZeroPadding3D before the pool)
+  int step1[5], step2[5];          // gridDim.x and 2*gridDim.x as mixed-radix digits (nt, tw, th, td, tn)
   Epilogue ep;
 };
+
+// Tile coordinates of a CTA's round-robin walk, advanced by digit-wise addition with carry
+// instead of five integer divisions per tile.
+struct TileIter {
+  int tile, nt, tw, th, td, tn;
+  __device__ __forceinline__ void init(const ConvTcArgs& a, int t0) {
+    tile = t0;
+    nt = t0 % a.n_tiles_n;
+    int mt = t0 / a.n_tiles_n;
+    tw = mt % a.tiles_w; mt /= a.tiles_w;
+    th = mt % a.tiles_h; mt /= a.tiles_h;
+    td = mt % a.tiles_d;
+    tn = mt / a.tiles_d;
+  }
+  __device__ __forceinline__ void advance(const ConvTcArgs& a, const int (&st)[5], int stride) {
+    tile += stride;
+    nt += st[0]; int c = nt >= a.n_tiles_n; nt -= c ? a.n_tiles_n : 0;
+    tw += st[1] + c; c = tw >= a.tiles_w; tw -= c ? a.tiles_w : 0;
+    th += st[2] + c; c = th >= a.tiles_h; th -= c ? a.tiles_h : 0;
+    td += st[3] + c; c = td >= a.tiles_d; td -= c ? a.tiles_d : 0;
+    tn += st[4] + c;
+  }
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// Fast epilogue math for one EC-wide chunk of a row (no residual, no second output):
+// y = acc*scale + shift -> (ReLU) -> bf16 -> swizzled staging row.
+template <int EC, bool SCALE, bool RELU>
+__device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[EC], const float (*par)[256], int c0, uint32_t s0,
+                                               uint32_t swz) {
+#pragma unroll
+  for (int g8 = 0; g8 < EC / 8; ++g8) {
+    const float4 sh_a = *reinterpret_cast<const float4*>(&par[1][c0 + g8 * 8]);
+    const float4 sh_b = *reinterpret_cast<const float4*>(&par[1][c0 + g8 * 8 + 4]);
+    const float shv[8] = {sh_a.x, sh_a.y, sh_a.z, sh_a.w, sh_b.x, sh_b.y, sh_b.z, sh_b.w};
+    float y[8];
+    if (SCALE) {
+      const float4 sc_a = *reinterpret_cast<const float4*>(&par[0][c0 + g8 * 8]);
+      const float4 sc_b = *reinterpret_cast<const float4*>(&par[0][c0 + g8 * 8 + 4]);
+      const float scv[8] = {sc_a.x, sc_a.y, sc_a.z, sc_a.w, sc_b.x, sc_b.y, sc_b.z, sc_b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(r[g8 * 8 + j]), scv[j], shv[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[g8 * 8 + j]) + shv[j];
+    }
+    uint32_t p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = RELU ? pack_bf16x2_relu(y[2 * j], y[2 * j + 1]) : pack_bf16x2(y[2 * j], y[2 * j + 1]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + (((uint32_t)g8 ^ swz) << 4)), "r"(p[0]), "r"(p[1]),
+                 "r"(p[2]), "r"(p[3]) : "memory");
+  }
+}
 
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3,
                                              int c4) {
@@ -257,17 +321,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int fd = 0; fd < a.kd; ++fd)
         tma_load_2d(leader, smem_base + a.b_region + fd * b_fd, &tmap_b, bb, 0, fd * a.kh * a.bn);
     }
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      const int nt = tile % a.n_tiles_n;
-      int mt = tile / a.n_tiles_n;
-      const int tw = mt % a.tiles_w; mt /= a.tiles_w;
-      const int th = mt % a.tiles_h; mt /= a.tiles_h;
-      const int td = mt % a.tiles_d;
-      const int tn = mt / a.tiles_d;
-      const int iw0 = tw * a.b_w * a.sw - a.pw;
-      const int ih0 = th * a.b_h * a.sh - a.ph;
-      const int id0 = td * a.b_d * a.sd - a.pd;
-      const int n0 = tn * a.b_n;
+    TileIter ti;
+    for (ti.init(a, blockIdx.x); ti.tile < a.num_tiles; ti.advance(a, a.step1, gridDim.x)) {
+      const int nt = ti.nt;
+      const int iw0 = ti.tw * a.b_w * a.sw - a.pw;
+      const int ih0 = ti.th * a.b_h * a.sh - a.ph;
+      const int id0 = ti.td * a.b_d * a.sd - a.pd;
+      const int n0 = ti.tn * a.b_n;
       const int bcol = nt * a.bn;
       if (a.halo) {
         // halo mode: the A box carries kd-1 / kh-1 extra planes / rows; every (fd,fh) tap is a
@@ -390,28 +450,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(a.ep.res);
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     float (*par)[256] = s_par[grp];
+    const bool fast = (res == nullptr) && !has_out1;            // no residual / second output: templated math
     // fused MaxPooling3D (window == stride, windows never straddle a brick)
     const bool pooled = a.pool_d > 0;
-    const int pwin = pooled ? a.pool_d * a.pool_h * a.pool_w : 1;
-    const int pb_w = pooled ? a.b_w / a.pool_w : 1, pb_h = pooled ? a.b_h / a.pool_h : 1,
-              pb_d = pooled ? a.b_d / a.pool_d : 1;
-    const int prows = pooled ? (a.b_n * pb_d * pb_h * pb_w) : 0;
     const uint32_t pool_stg_off = STG_BYTES;        // pooled tile lives right after the full tile of a slot
+    // The pooled tile is [prows][EC]; its 16-byte vectors are spread over the group's 128 threads.
+    // Everything that does not depend on the tile is computed once here: for each of this
+    // thread's (<= 4) vectors the first source row of its window and the destination offset.
+    constexpr int V = EC / 8;                       // 16-byte vectors per row
+    constexpr int PV_MAX = 4;
+    int pv_n = 0;
+    bool pool_precomputed = false;
+    int pv_r2_0 = 0, pv_r2_1 = 0, pv_r2_2 = 0, pv_r2_3 = 0;
+    uint32_t pv_cd_0 = 0, pv_cd_1 = 0, pv_cd_2 = 0, pv_cd_3 = 0;     // (dst offset << 4) | cv
+    if (pooled) {
+      const int pb_w = a.b_w / a.pool_w, pb_h = a.b_h / a.pool_h, pb_d = a.b_d / a.pool_d;
+      const int nvec = a.b_n * pb_d * pb_h * pb_w * V;
+      pool_precomputed = nvec <= PV_MAX * 128;
+      auto pre = [&](int k, int& r2_out, uint32_t& cd_out) {
+        const int v = et + k * 128;
+        if (v < nvec && pool_precomputed) {
+          const int p = v / V, cv = v % V;
+          int q = p;
+          const int pw_ = q % pb_w; q /= pb_w;
+          const int ph_ = q % pb_h; q /= pb_h;
+          const int pd_ = q % pb_d; const int pn_ = q / pb_d;
+          r2_out = ((pn_ * a.b_d + pd_ * a.pool_d) * a.b_h + ph_ * a.pool_h) * a.b_w + pw_ * a.pool_w;
+          const uint32_t swp = (EC == 64) ? (p & 7) : (EC == 32 ? ((p >> 1) & 3) : ((p >> 2) & 1));
+          cd_out = (((uint32_t)p * (EC * 2) + (((uint32_t)cv ^ swp) << 4)) << 4) | (uint32_t)cv;
+          pv_n = k + 1;
+        }
+      };
+      pre(0, pv_r2_0, pv_cd_0); pre(1, pv_r2_1, pv_cd_1); pre(2, pv_r2_2, pv_cd_2); pre(3, pv_r2_3, pv_cd_3);
+    }
     const uint32_t bar_id = 1u + (uint32_t)grp;
     const int buf = grp;
     uint32_t acc_phase = 0u;
     int slot = 0;
     int last_nt = -1;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
-      const int nt = tile % a.n_tiles_n;
-      int mt = tile / a.n_tiles_n;
-      const int tw = mt % a.tiles_w; mt /= a.tiles_w;
-      const int th = mt % a.tiles_h; mt /= a.tiles_h;
-      const int td = mt % a.tiles_d;
-      const int tn = mt / a.tiles_d;
-      const int ow0 = tw * a.b_w, oh0 = th * a.b_h, od0 = td * a.b_d, on0 = tn * a.b_n;
+    TileIter ti;
+    for (ti.init(a, blockIdx.x + grp * gridDim.x); ti.tile < a.num_tiles; ti.advance(a, a.step2, 2 * gridDim.x)) {
+      const int nt = ti.nt;
+      const int ow0 = ti.tw * a.b_w, oh0 = ti.th * a.b_h, od0 = ti.td * a.b_d, on0 = ti.tn * a.b_n;
       const int col_base = nt * a.bn;
       bool use_res = false, row_valid = true;
       long long pix = 0;
@@ -448,65 +528,87 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             default: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         uint32_t r[EC];
 #pragma unroll
         for (int q = 0; q < EC / 16; ++q) tc_ld16(t_row + (uint32_t)(c0 + q * 16), *reinterpret_cast<uint32_t(*)[16]>(&r[q * 16]));
         tc_wait_ld();
+        if (c0 + EC >= a.bn) {
+          // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp
+          // before the math / staging / store of this last chunk
+          tc_fence_before();
+          mbar_arrive(bar_base + 144u + 8u * buf);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         const uint32_t s0 = my_stg + (uint32_t)slot * slot_bytes + (uint32_t)row * (EC * 2);
-#pragma unroll
-        for (int g8 = 0; g8 < EC / 8; ++g8) {        // groups of 8 columns = one 16-byte staged chunk
-          float y[8];
-          const float4 sh_a = *reinterpret_cast<const float4*>(&par[1][c0 + g8 * 8]);
-          const float4 sh_b = *reinterpret_cast<const float4*>(&par[1][c0 + g8 * 8 + 4]);
-          const float shv[8] = {sh_a.x, sh_a.y, sh_a.z, sh_a.w, sh_b.x, sh_b.y, sh_b.z, sh_b.w};
+        if (fast) {
           if (has_scale0) {
-            const float4 sc_a = *reinterpret_cast<const float4*>(&par[0][c0 + g8 * 8]);
-            const float4 sc_b = *reinterpret_cast<const float4*>(&par[0][c0 + g8 * 8 + 4]);
-            const float scv[8] = {sc_a.x, sc_a.y, sc_a.z, sc_a.w, sc_b.x, sc_b.y, sc_b.z, sc_b.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(r[g8 * 8 + j]), scv[j], shv[j]);
+            if (relu0) epi_chunk_fast<EC, true, true>(r, par, c0, s0, swz);
+            else epi_chunk_fast<EC, true, false>(r, par, c0, s0, swz);
           } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[g8 * 8 + j]) + shv[j];
+            if (relu0) epi_chunk_fast<EC, false, true>(r, par, c0, s0, swz);
+            else epi_chunk_fast<EC, false, false>(r, par, c0, s0, swz);
           }
-          const int col = col_base + c0 + g8 * 8;
-          if (use_res && col < a.Co) {
-            const uint4 q0 = *reinterpret_cast<const uint4*>(res + pix * a.ep.res_ld + col);
-            const __nv_bfloat16* e0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
+          if (pooled && !row_valid) {               // rows outside the tensor: 0 (ZeroPadding3D) or -inf
+            const uint32_t kv = a.pool_zero ? 0u : 0xFF80FF80u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] += __bfloat162float(e0[j]);
+            for (int g8 = 0; g8 < EC / 8; ++g8)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(s0 + ((uint32_t)g8 << 4)), "r"(kv) : "memory");
           }
-          const uint32_t c16 = (uint32_t)g8;
-          {
-            uint32_t p[4];
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-              if (relu0) h = __hmax2(h, zero2);
-              p[j] = *reinterpret_cast<uint32_t*>(&h);
-              if (pooled && !row_valid) p[j] = a.pool_zero ? 0u : 0xFF80FF80u;   // 0 or -inf for rows outside the tensor
+          for (int g8 = 0; g8 < EC / 8; ++g8) {        // groups of 8 columns = one 16-byte staged chunk
+            float y[8];
+            const float4 sh_a = *reinterpret_cast<const float4*>(&par[1][c0 + g8 * 8]);
+            const float4 sh_b = *reinterpret_cast<const float4*>(&par[1][c0 + g8 * 8 + 4]);
+            const float shv[8] = {sh_a.x, sh_a.y, sh_a.z, sh_a.w, sh_b.x, sh_b.y, sh_b.z, sh_b.w};
+            if (has_scale0) {
+              const float4 sc_a = *reinterpret_cast<const float4*>(&par[0][c0 + g8 * 8]);
+              const float4 sc_b = *reinterpret_cast<const float4*>(&par[0][c0 + g8 * 8 + 4]);
+              const float scv[8] = {sc_a.x, sc_a.y, sc_a.z, sc_a.w, sc_b.x, sc_b.y, sc_b.z, sc_b.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(r[g8 * 8 + j]), scv[j], shv[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[g8 * 8 + j]) + shv[j];
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + ((c16 ^ swz) << 4)), "r"(p[0]), "r"(p[1]),
-                         "r"(p[2]), "r"(p[3]) : "memory");
-          }
-          if (has_out1) {
-            const float4 s1a = *reinterpret_cast<const float4*>(&par[2][c0 + g8 * 8]);
-            const float4 s1b = *reinterpret_cast<const float4*>(&par[2][c0 + g8 * 8 + 4]);
-            const float4 t1a = *reinterpret_cast<const float4*>(&par[3][c0 + g8 * 8]);
-            const float4 t1b = *reinterpret_cast<const float4*>(&par[3][c0 + g8 * 8 + 4]);
-            const float s1[8] = {s1a.x, s1a.y, s1a.z, s1a.w, s1b.x, s1b.y, s1b.z, s1b.w};
-            const float t1[8] = {t1a.x, t1a.y, t1a.z, t1a.w, t1b.x, t1b.y, t1b.z, t1b.w};
-            uint32_t p[4];
+            const int col = col_base + c0 + g8 * 8;
+            if (use_res && col < a.Co) {
+              const uint4 q0 = *reinterpret_cast<const uint4*>(res + pix * a.ep.res_ld + col);
+              const __nv_bfloat16* e0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(fmaf(y[2 * j], s1[2 * j], t1[2 * j]),
-                                                       fmaf(y[2 * j + 1], s1[2 * j + 1], t1[2 * j + 1]));
-              if (relu1) h = __hmax2(h, zero2);
-              p[j] = *reinterpret_cast<uint32_t*>(&h);
+              for (int j = 0; j < 8; ++j) y[j] += __bfloat162float(e0[j]);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + STG_BYTES + ((c16 ^ swz) << 4)), "r"(p[0]),
-                         "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
+            const uint32_t c16 = (uint32_t)g8;
+            {
+              uint32_t p[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                if (relu0) h = __hmax2(h, zero2);
+                p[j] = *reinterpret_cast<uint32_t*>(&h);
+                if (pooled && !row_valid) p[j] = a.pool_zero ? 0u : 0xFF80FF80u;   // 0 or -inf for rows outside the tensor
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + ((c16 ^ swz) << 4)), "r"(p[0]), "r"(p[1]),
+                           "r"(p[2]), "r"(p[3]) : "memory");
+            }
+            if (has_out1) {
+              const float4 s1a = *reinterpret_cast<const float4*>(&par[2][c0 + g8 * 8]);
+              const float4 s1b = *reinterpret_cast<const float4*>(&par[2][c0 + g8 * 8 + 4]);
+              const float4 t1a = *reinterpret_cast<const float4*>(&par[3][c0 + g8 * 8]);
+              const float4 t1b = *reinterpret_cast<const float4*>(&par[3][c0 + g8 * 8 + 4]);
+              const float s1[8] = {s1a.x, s1a.y, s1a.z, s1a.w, s1b.x, s1b.y, s1b.z, s1b.w};
+              const float t1[8] = {t1a.x, t1a.y, t1a.z, t1a.w, t1b.x, t1b.y, t1b.z, t1b.w};
+              uint32_t p[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(fmaf(y[2 * j], s1[2 * j], t1[2 * j]),
+                                                         fmaf(y[2 * j + 1], s1[2 * j + 1], t1[2 * j + 1]));
+                if (relu1) h = __hmax2(h, zero2);
+                p[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + STG_BYTES + ((c16 ^ swz) << 4)), "r"(p[0]),
+                           "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
+            }
           }
         }
         if (pooled) {
@@ -514,31 +616,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           const uint32_t full = my_stg + (uint32_t)slot * slot_bytes;
           const uint32_t pst = full + pool_stg_off;
-          constexpr int V = EC / 8;                   // 16-byte vectors per row
-          for (int v = et; v < prows * V; v += 128) {
-            const int p = v / V, cv = v % V;
-            int q = p;
-            const int pw_ = q % pb_w; q /= pb_w;
-            const int ph_ = q % pb_h; q /= pb_h;
-            const int pd_ = q % pb_d; const int pn_ = q / pb_d;
-            uint32_t m0 = 0xFF80FF80u, m1 = 0xFF80FF80u, m2 = 0xFF80FF80u, m3 = 0xFF80FF80u;   // -inf, -inf
-            for (int i = 0; i < a.pool_d; ++i)
-              for (int j = 0; j < a.pool_h; ++j)
-                for (int l = 0; l < a.pool_w; ++l) {
-                  const int r2 = ((pn_ * a.b_d + pd_ * a.pool_d + i) * a.b_h + ph_ * a.pool_h + j) * a.b_w + pw_ * a.pool_w + l;
-                  const uint32_t sw2 = (EC == 64) ? (r2 & 7) : (EC == 32 ? ((r2 >> 1) & 3) : ((r2 >> 2) & 1));
-                  uint32_t x0, x1, x2, x3;
-                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
-                               : "r"(full + (uint32_t)r2 * (EC * 2) + (((uint32_t)cv ^ sw2) << 4)));
-                  __nv_bfloat162 t;
-                  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m0), *reinterpret_cast<__nv_bfloat162*>(&x0)); m0 = *reinterpret_cast<uint32_t*>(&t);
-                  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m1), *reinterpret_cast<__nv_bfloat162*>(&x1)); m1 = *reinterpret_cast<uint32_t*>(&t);
-                  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m2), *reinterpret_cast<__nv_bfloat162*>(&x2)); m2 = *reinterpret_cast<uint32_t*>(&t);
-                  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m3), *reinterpret_cast<__nv_bfloat162*>(&x3)); m3 = *reinterpret_cast<uint32_t*>(&t);
+          if (pool_precomputed) {
+            auto pool_vec = [&](int r2b, uint32_t cd) {
+              const uint32_t cv = cd & 15u, dst = cd >> 4;
+              uint32_t m0 = 0xFF80FF80u, m1 = 0xFF80FF80u, m2 = 0xFF80FF80u, m3 = 0xFF80FF80u;   // -inf, -inf
+              for (int i = 0; i < a.pool_d; ++i)
+                for (int j = 0; j < a.pool_h; ++j) {
+                  const int rb = r2b + (i * a.b_h + j) * a.b_w;
+                  for (int l = 0; l < a.pool_w; ++l) {
+                    const int r2 = rb + l;
+                    const uint32_t sw2 = (EC == 64) ? (r2 & 7) : (EC == 32 ? ((r2 >> 1) & 3) : ((r2 >> 2) & 1));
+                    uint32_t x0, x1, x2, x3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                                 : "r"(full + (uint32_t)r2 * (EC * 2) + ((cv ^ sw2) << 4)));
+                    __nv_bfloat162 t;
+                    t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m0), *reinterpret_cast<__nv_bfloat162*>(&x0)); m0 = *reinterpret_cast<uint32_t*>(&t);
+                    t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m1), *reinterpret_cast<__nv_bfloat162*>(&x1)); m1 = *reinterpret_cast<uint32_t*>(&t);
+                    t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m2), *reinterpret_cast<__nv_bfloat162*>(&x2)); m2 = *reinterpret_cast<uint32_t*>(&t);
+                    t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m3), *reinterpret_cast<__nv_bfloat162*>(&x3)); m3 = *reinterpret_cast<uint32_t*>(&t);
+                  }
                 }
-            const uint32_t swp = (EC == 64) ? (p & 7) : (EC == 32 ? ((p >> 1) & 3) : ((p >> 2) & 1));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pst + (uint32_t)p * (EC * 2) + (((uint32_t)cv ^ swp) << 4)),
-                         "r"(m0), "r"(m1), "r"(m2), "r"(m3) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pst + dst), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+                           : "memory");
+            };
+            if (pv_n > 0) pool_vec(pv_r2_0, pv_cd_0);
+            if (pv_n > 1) pool_vec(pv_r2_1, pv_cd_1);
+            if (pv_n > 2) pool_vec(pv_r2_2, pv_cd_2);
+            if (pv_n > 3) pool_vec(pv_r2_3, pv_cd_3);
+          } else {
+            const int pb_w = a.b_w / a.pool_w, pb_h = a.b_h / a.pool_h, pb_d = a.b_d / a.pool_d;
+            const int prows = a.b_n * pb_d * pb_h * pb_w;
+            for (int v = et; v < prows * V; v += 128) {
+              const int p = v / V, cv = v % V;
+              int q = p;
+              const int pw_ = q % pb_w; q /= pb_w;
+              const int ph_ = q % pb_h; q /= pb_h;
+              const int pd_ = q % pb_d; const int pn_ = q / pb_d;
+              uint32_t m0 = 0xFF80FF80u, m1 = 0xFF80FF80u, m2 = 0xFF80FF80u, m3 = 0xFF80FF80u;   // -inf, -inf
+              for (int i = 0; i < a.pool_d; ++i)
+                for (int j = 0; j < a.pool_h; ++j)
+                  for (int l = 0; l < a.pool_w; ++l) {
+                    const int r2 = ((pn_ * a.b_d + pd_ * a.pool_d + i) * a.b_h + ph_ * a.pool_h + j) * a.b_w + pw_ * a.pool_w + l;
+                    const uint32_t sw2 = (EC == 64) ? (r2 & 7) : (EC == 32 ? ((r2 >> 1) & 3) : ((r2 >> 2) & 1));
+                    uint32_t x0, x1, x2, x3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                                 : "r"(full + (uint32_t)r2 * (EC * 2) + (((uint32_t)cv ^ sw2) << 4)));
+                    __nv_bfloat162 t;
+                    t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m0), *reinterpret_cast<__nv_bfloat162*>(&x0)); m0 = *reinterpret_cast<uint32_t*>(&t);
+                    t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m1), *reinterpret_cast<__nv_bfloat162*>(&x1)); m1 = *reinterpret_cast<uint32_t*>(&t);
+                    t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m2), *reinterpret_cast<__nv_bfloat162*>(&x2)); m2 = *reinterpret_cast<uint32_t*>(&t);
+                    t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m3), *reinterpret_cast<__nv_bfloat162*>(&x3)); m3 = *reinterpret_cast<uint32_t*>(&t);
+                  }
+              const uint32_t swp = (EC == 64) ? (p & 7) : (EC == 32 ? ((p >> 1) & 3) : ((p >> 2) & 1));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pst + (uint32_t)p * (EC * 2) + (((uint32_t)cv ^ swp) << 4)),
+                           "r"(m0), "r"(m1), "r"(m2), "r"(m3) : "memory");
+            }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -557,8 +689,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if (++slot == a.nslots) slot = 0;
       }
-      tc_fence_before();
-      mbar_arrive(bar_base + 144u + 8u * buf);
       acc_phase ^= 1u;
     }
     if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -797,6 +927,15 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   a.nslots = d.nslots; a.slot_bytes = d.slot_bytes;
   a.ep = ep;
   int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
+  {
+    const int radix[4] = {a.n_tiles_n, a.tiles_w, a.tiles_h, a.tiles_d};
+    for (int which = 0; which < 2; ++which) {
+      int v = grid * (which + 1);
+      int* st = which ? a.step2 : a.step1;
+      for (int i = 0; i < 4; ++i) { st[i] = v % radix[i]; v /= radix[i]; }
+      st[4] = v;
+    }
+  }
   switch (d.kc) {
     case 64: return launch_tc_kc<64>(d, a, grid, st);
     case 32: return launch_tc_kc<32>(d, a, grid, st);
