@@ -55,35 +55,66 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons of one GPU during the timed region: NVML in-thread
+    (no fork in the timed region), `nvidia-smi` as the fallback."""
+
+    REASONS = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4)]
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            self.rows.append((sm, self.max_sm, [name for name, bit in self.REASONS if mask & bit]))
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 6 and parts[0].isdigit():
+            self.rows.append((int(parts[0]), int(parts[1]) if parts[1].isdigit() else None,
+                              [name for (name, _), v in zip(self.REASONS, parts[2:6]) if v.lower().startswith("active")]))
+
+    def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                self._sample()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows if r[1]]
+        reasons = sorted({name for r in self.rows for name in r[2]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------- CPU reference arm
@@ -156,7 +187,9 @@ def run_ours(args):
         members = args.members
     g = G.build_model_graph(mt, shape, 11)
     weight_sets = [synthetic_weights(g, seed=100 + m) for m in range(members)]
-    ens = DeviceEnsemble(g, weight_sets, precision=args.precision, max_batch=batch, micro_batch=args.micro_batch)
+    lower_kw = json.loads(os.environ.get("CSE_LOWER_KW", "{}"))      # lowering experiments (e.g. {"fuse_pool": false})
+    ens = DeviceEnsemble(g, weight_sets, precision=args.precision, max_batch=batch, micro_batch=args.micro_batch,
+                         **lower_kw)
     del weight_sets
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     host = torch.randint(0, 256, (batch,) + tuple(shape), dtype=torch.uint8, generator=gen).pin_memory()
@@ -169,11 +202,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: clips are sharded over the ranks (members replicated); the one exchange of the path is
+    # the all-gather of the per-clip predictions (evaluate_ensemble.py:1262-1268 writes them all)
+    gathered = torch.empty((world * batch,), dtype=torch.int32, device="cuda") if world > 1 else None
+
     def step_resident():
-        return ens.predict_device([dev_in])
+        pred = ens.predict_device([dev_in])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pred)
+            return gathered
+        return pred
 
     def step_e2e():
-        return ens.predict_host([host])
+        if world == 1:
+            return ens.predict_host([host])
+        dev = host.to("cuda", non_blocking=True)
+        pred = ens.predict_device([dev])
+        dist.all_gather_into_tensor(gathered, pred)
+        return gathered.cpu().numpy()
 
     # ---- kernel-resident timing ----
     for _ in range(args.warmup):
@@ -250,6 +296,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "model": mt, "clip": list(shape), "members": members,
                        "batch_per_gpu": batch, "vote": "SUM", "classes": 11,
+                       "parallelism": "clips sharded over %d GPU(s), members replicated, 1 all-gather of int32 "
+                                      "predictions per step" % world,
                        "l2_policy": "input batch (%d MB uint8) and activations exceed the 126 MB L2" % (in_bytes >> 20)},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": batch * 4},
@@ -263,7 +311,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3d_ens", choices=sorted(WORKLOADS))
