@@ -148,7 +148,7 @@ def run_reference(args):
     if rank != 0:
         return
     mt, shape, members, batch = WORKLOADS[args.workload]
-    sample = 4 if mt == "C3D" else 2
+    sample = 8 if (mt == "C3D" or mt.startswith("R3D")) else 2
     v, sec, threads = cpu_reference_clips_per_s(mt, shape, members, sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "ensemble clips/sec", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
@@ -275,6 +275,13 @@ def run_ours(args):
                     "kernel_share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
                     "launches_per_step": len(tc),
                     "whole_step_model_tflops": members * g.total_flops() * batch / (ms / args.steps / 1e3) / 1e12}
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            tr = json.load(open(tpath)).get(args.workload)
+            if tr and tr.get("micro_batch") == ens.micro_batch and tr.get("launches_captured") == len(tc):
+                roofline["traffic"] = tr["dram_bytes_per_launch_avg"]
+                roofline["traffic_unit"] = "B per conv_tc launch (ncu dram read+write, avg over the member's launches)"
+                roofline["algorithmic_flops_per_launch_avg"] = tc_flops / (len(tc) * members * (batch // ens.micro_batch))
         if args.profile_out:
             with open(args.profile_out, "w") as f:
                 json.dump({"workload": args.workload, "batch": batch, "members": members, "micro_batch": ens.micro_batch,
@@ -285,11 +292,11 @@ def run_ours(args):
                                for p in top]
         cpu = None
         if not args.no_cpu_baseline:
-            sample = 4
-            v, sec, threads = cpu_reference_clips_per_s(mt, shape, members, sample, 1, 1)
+            sample = 16 if mt in ("C3D",) or mt.startswith("R3D") else 4
+            v, sec, threads = cpu_reference_clips_per_s(mt, shape, members, sample, 2, 1)
             cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
-                   "sample": "%d clips x %d members, 1 warm-up + 1 timed pass, torch CPU fp32 oracle restatement"
-                             % (sample, members)}
+                   "sample": "%d clips x %d members per pass, 1 warm-up + 2 timed passes, torch CPU fp32 oracle "
+                             "restatement (Keras 2.2.4/TF 1.15 not installable offline)" % (sample, members)}
         line = {
             "metric": "ensemble clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

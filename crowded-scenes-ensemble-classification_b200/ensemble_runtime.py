@@ -58,7 +58,7 @@ class DeviceEnsemble:
             chunk = [x[i:i + mb] for x in inputs_u8]
             for j, m in enumerate(self.members):
                 m.forward_device(chunk, self.logits[j, i:i + mb], self.probs[j, i:i + mb])
-                launches += m.launches + 2          # + the two D2D copies of logits / probs
+                launches += m.launches              # kernels only (the two D2D copies of logits / probs are memcpys)
         self.last_launches = launches
         return n
 
