@@ -35,14 +35,29 @@ if ROOT not in sys.path:
 
 import numpy as np
 
+# name: (groups, clips per GPU per step); group = (model_type, clip shape, members, micro-batch)
+# members = folds - 1 = 4 per architecture, as the reference builds them for `-fn 5`
+# (evaluate_ensemble.py:1042-1049).
 WORKLOADS = {
-    # name: (model_type, input shape, members, batch per GPU)
-    "c3d_ens": ("C3D", (16, 112, 112, 3), 4, 256),
-    "c3d_single_b8": ("C3D", (16, 112, 112, 3), 1, 8),
-    "r3d34_ens": ("R3D_34", (16, 112, 112, 3), 4, 256),
-    "i3d20_ens": ("I3D", (20, 224, 224, 3), 4, 32),
-    "i3d64_ens": ("I3D", (64, 224, 224, 3), 4, 8),
+    "c3d_ens": ([("C3D", (16, 112, 112, 3), 4, 128)], 256),                       # BASELINE configs[1]
+    "c3d_single_b8": ([("C3D", (16, 112, 112, 3), 1, 8)], 8),                     # configs[0]
+    "r3d34_ens": ([("R3D_34", (16, 112, 112, 3), 4, 128)], 256),
+    "i3d20_ens": ([("I3D", (20, 224, 224, 3), 4, 32)], 32),                       # reference-true T=20 (train.py:1573)
+    "i3d64_ens": ([("I3D", (64, 224, 224, 3), 4, 8)], 8),                         # configs[2]
+    "twostream20_ens": ([("TWOSTREAM_I3D", (20, 224, 224, 0), 4, 16)], 32),
+    "twostream64_ens": ([("TWOSTREAM_I3D", (64, 224, 224, 0), 4, 8)], 8),         # configs[3]
+    "global_hetero": ([("C3D", (16, 112, 112, 3), 4, 128), ("I3D", (64, 224, 224, 3), 4, 8),
+                       ("R3D_34", (16, 112, 112, 3), 4, 128)], 256),              # configs[4] (per GPU)
+    "global_hetero_t20": ([("C3D", (16, 112, 112, 3), 4, 128), ("I3D", (20, 224, 224, 3), 4, 32),
+                           ("R3D_34", (16, 112, 112, 3), 4, 128)], 256),
 }
+
+
+def workload_config(name, groups, batch, world):
+    return {"workload": name, "models": [g[0] for g in groups], "clips": [list(g[1]) for g in groups],
+            "members": [g[2] for g in groups], "batch_per_gpu": batch, "vote": "SUM", "classes": 11,
+            "parallelism": "clips sharded over %d GPU(s), members replicated, 1 all-gather of int32 predictions per "
+                           "step" % world}
 
 
 def load_peaks():
@@ -118,7 +133,7 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_clips_per_s(model_type, shape, members, clips_per_step, steps, warmup, threads=None):
+def cpu_reference_clips_per_s(groups, clips_per_step, steps, warmup, threads=None):
     """Oracle port (torch CPU fp32) of the same ensemble: every member forward + numpy vote."""
     import torch
     from cse_b200 import graph as G
@@ -126,13 +141,17 @@ def cpu_reference_clips_per_s(model_type, shape, members, clips_per_step, steps,
     from oracle import models as OM, vote as OV
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    g = G.build_model_graph(model_type, shape, 11)
-    ws = [synthetic_weights(g, seed=100 + m) for m in range(members)]
-    x = np.random.default_rng(1234).integers(0, 256, (clips_per_step,) + tuple(shape), dtype=np.uint8)
+    rng = np.random.default_rng(1234)
+    prepared = []
+    for gi, (mt, shape, members, _) in enumerate(groups):
+        g = G.build_model_graph(mt, shape, 11)
+        ws = [synthetic_weights(g, seed=100 + 10 * gi + m) for m in range(members)]
+        xs = [rng.integers(0, 256, (clips_per_step,) + tuple(g.shape(n)), dtype=np.uint8) for n in g.inputs]
+        prepared.append((mt, ws, xs if len(xs) > 1 else xs[0]))
 
     def step():
-        probs = [OM.forward(model_type, w, x, torch.float32)[1].numpy() for w in ws]
-        return OV.ensemble_predictions(np.stack(probs).astype(np.float64), np.ones(members))
+        probs = [OM.forward(mt, w, x, torch.float32)[1].numpy() for mt, ws, x in prepared for w in ws]
+        return OV.ensemble_predictions(np.stack(probs).astype(np.float64), np.ones(len(probs)))
 
     for _ in range(warmup):
         step()
@@ -143,19 +162,26 @@ def cpu_reference_clips_per_s(model_type, shape, members, clips_per_step, steps,
     return clips_per_step * steps / dt, dt / steps, threads
 
 
+def cpu_sample_size(groups, budget_gflop=3000.0):
+    """Clips per CPU step: bounded so a step is a few seconds of host work."""
+    gflop = sum(m * {"C3D": 77.1, "R3D_34": 13.3}.get(mt, 222.3 * shape[0] / 64 * (2 if mt == "TWOSTREAM_I3D" else 1))
+                for mt, shape, m, _ in groups)
+    return max(1, min(32, int(budget_gflop / gflop)))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mt, shape, members, batch = WORKLOADS[args.workload]
-    sample = 8 if (mt == "C3D" or mt.startswith("R3D")) else 2
-    v, sec, threads = cpu_reference_clips_per_s(mt, shape, members, sample, args.steps, args.warmup)
+    groups, batch = WORKLOADS[args.workload]
+    sample = cpu_sample_size(groups)
+    v, sec, threads = cpu_reference_clips_per_s(groups, sample, args.steps, args.warmup)
+    members = sum(g[2] for g in groups)
     line = {
         "impl": "reference", "metric": "ensemble clips/sec", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": mt, "clip": list(shape), "members": members,
-                   "batch_per_gpu": batch, "vote": "SUM", "classes": 11},
+        "config": workload_config(args.workload, groups, batch, args.gpus),
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
                          "sample": "%d clips x %d members per step, torch CPU fp32 oracle restatement "
                                    "(Keras 2.2.4/TF 1.15 not installable offline)" % (sample, members)},
@@ -170,7 +196,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from cse_b200 import graph as G, runtime as rt
-    from cse_b200.ensemble_runtime import DeviceEnsemble
+    from cse_b200.ensemble_runtime import HeteroEnsemble
     from cse_b200.weights import synthetic_weights
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -180,21 +206,28 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rt.load_library()
-    mt, shape, members, batch = WORKLOADS[args.workload]
+    groups, batch = WORKLOADS[args.workload]
     if args.batch:
         batch = args.batch
     if args.members:
-        members = args.members
-    g = G.build_model_graph(mt, shape, 11)
-    weight_sets = [synthetic_weights(g, seed=100 + m) for m in range(members)]
+        groups = [(mt, shape, args.members, mb) for mt, shape, _, mb in groups]
+    if args.micro_batch:
+        groups = [(mt, shape, m, args.micro_batch) for mt, shape, m, _ in groups]
+    groups = [(mt, shape, m, min(mb, batch)) for mt, shape, m, mb in groups]
     lower_kw = json.loads(os.environ.get("CSE_LOWER_KW", "{}"))      # lowering experiments (e.g. {"fuse_pool": false})
-    ens = DeviceEnsemble(g, weight_sets, precision=args.precision, max_batch=batch, micro_batch=args.micro_batch,
-                         **lower_kw)
-    del weight_sets
+    built, graphs = [], []
+    for gi, (mt, shape, m, mb) in enumerate(groups):
+        g = G.build_model_graph(mt, shape, 11)
+        graphs.append(g)
+        built.append((g, [synthetic_weights(g, seed=100 + 10 * gi + j) for j in range(m)], mb))
+    ens = HeteroEnsemble(built, precision=args.precision, max_batch=batch, **lower_kw)
+    del built
+    members = ens.M
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    host = torch.randint(0, 256, (batch,) + tuple(shape), dtype=torch.uint8, generator=gen).pin_memory()
-    dev_in = host.cuda()
-    in_bytes = dev_in.numel()
+    host = [[torch.randint(0, 256, (batch,) + tuple(g.shape(n)), dtype=torch.uint8, generator=gen).pin_memory()
+             for n in g.inputs] for g in graphs]
+    dev_in = [[h.cuda() for h in hs] for hs in host]
+    in_bytes = sum(h.numel() for hs in host for h in hs)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -207,7 +240,7 @@ def run_ours(args):
     gathered = torch.empty((world * batch,), dtype=torch.int32, device="cuda") if world > 1 else None
 
     def step_resident():
-        pred = ens.predict_device([dev_in])
+        pred = ens.predict_device(dev_in)
         if world > 1:
             dist.all_gather_into_tensor(gathered, pred)
             return gathered
@@ -215,9 +248,9 @@ def run_ours(args):
 
     def step_e2e():
         if world == 1:
-            return ens.predict_host([host])
-        dev = host.to("cuda", non_blocking=True)
-        pred = ens.predict_device([dev])
+            return ens.predict_host(host)
+        dev = [[h.to("cuda", non_blocking=True) for h in hs] for hs in host]
+        pred = ens.predict_device(dev)
         dist.all_gather_into_tensor(gathered, pred)
         return gathered.cpu().numpy()
 
@@ -262,7 +295,7 @@ def run_ours(args):
 
     if rank == 0:
         peaks = load_peaks()
-        prof = ens.profile_ops([dev_in], iters=2)
+        prof = ens.profile_ops(dev_in, iters=2)
         tc = [p for p in prof if p["engine"] == "tcgen05"]
         tc_flops = sum(p["flops"] for p in tc)
         tc_ms = sum(p["ms"] for p in tc)
@@ -274,14 +307,15 @@ def run_ours(args):
                     "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (peaks["source"], peaks["bf16_burst"]),
                     "kernel_share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
                     "launches_per_step": len(tc),
-                    "whole_step_model_tflops": members * g.total_flops() * batch / (ms / args.steps / 1e3) / 1e12}
+                    "whole_step_model_tflops": sum(m * g.total_flops() for g, (_, _, m, _) in zip(graphs, groups)) * batch
+                                               / (ms / args.steps / 1e3) / 1e12}
         tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tpath):
             tr = json.load(open(tpath)).get(args.workload)
-            if tr and tr.get("micro_batch") == ens.micro_batch and tr.get("launches_captured") == len(tc):
+            if tr and [tr.get("micro_batch")] == ens.micro_batch and tr.get("launches_captured") == len(tc):
                 roofline["traffic"] = tr["dram_bytes_per_launch_avg"]
                 roofline["traffic_unit"] = "B per conv_tc launch (ncu dram read+write, avg over the member's launches)"
-                roofline["algorithmic_flops_per_launch_avg"] = tc_flops / (len(tc) * members * (batch // ens.micro_batch))
+                roofline["algorithmic_flops_per_launch_avg"] = tc_flops / (len(tc) * members * (batch // ens.micro_batch[0]))
         if args.profile_out:
             with open(args.profile_out, "w") as f:
                 json.dump({"workload": args.workload, "batch": batch, "members": members, "micro_batch": ens.micro_batch,
@@ -292,8 +326,8 @@ def run_ours(args):
                                for p in top]
         cpu = None
         if not args.no_cpu_baseline:
-            sample = 16 if mt in ("C3D",) or mt.startswith("R3D") else 4
-            v, sec, threads = cpu_reference_clips_per_s(mt, shape, members, sample, 2, 1)
+            sample = cpu_sample_size(groups, 6000.0)
+            v, sec, threads = cpu_reference_clips_per_s(groups, sample, 2, 1)
             cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
                    "sample": "%d clips x %d members per pass, 1 warm-up + 2 timed passes, torch CPU fp32 oracle "
                              "restatement (Keras 2.2.4/TF 1.15 not installable offline)" % (sample, members)}
@@ -301,11 +335,8 @@ def run_ours(args):
             "metric": "ensemble clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "model": mt, "clip": list(shape), "members": members,
-                       "batch_per_gpu": batch, "vote": "SUM", "classes": 11,
-                       "parallelism": "clips sharded over %d GPU(s), members replicated, 1 all-gather of int32 "
-                                      "predictions per step" % world,
-                       "l2_policy": "input batch (%d MB uint8) and activations exceed the 126 MB L2" % (in_bytes >> 20)},
+            "config": dict(workload_config(args.workload, groups, batch, world),
+                           l2_policy="input batch (%d MB uint8) and activations exceed the 126 MB L2" % (in_bytes >> 20)),
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": batch * 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -21,7 +21,7 @@ from .model import Member
 class DeviceEnsemble:
     def __init__(self, graph: Graph, weight_sets: Sequence[Dict[str, List[np.ndarray]]], precision: str = "bf16",
                  max_batch: int = 256, micro_batch: int = 0, device=None, vote_weights=None, vote_mode: str = "SUM",
-                 **lower_kw):
+                 probs_out=None, logits_out=None, **lower_kw):
         torch = rt.require_cuda()
         self.torch = torch
         self.graph = graph
@@ -37,8 +37,14 @@ class DeviceEnsemble:
         self.device = self.members[0].device
         self.nb_classes = self.members[0].nb_classes
         self.M = len(self.members)
-        self.probs = torch.empty((self.M, self.max_batch, self.nb_classes), dtype=torch.float32, device=self.device)
-        self.logits = torch.empty((self.M, self.max_batch, self.nb_classes), dtype=torch.float32, device=self.device)
+        shape = (self.M, self.max_batch, self.nb_classes)
+        # probs_out / logits_out: slices of a wider [sum M, N, C] buffer (heterogeneous ensembles)
+        for t in (probs_out, logits_out):
+            if t is not None and (tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise ValueError("external probability buffer must be contiguous float32 %r" % (shape,))
+        self.probs = probs_out if probs_out is not None else torch.empty(shape, dtype=torch.float32, device=self.device)
+        self.logits = logits_out if logits_out is not None else torch.empty(shape, dtype=torch.float32,
+                                                                             device=self.device)
         self.vote_mode = vote_mode
         self.vote_weights = None
         if vote_weights is not None:
@@ -110,4 +116,72 @@ class DeviceEnsemble:
         for k, op in enumerate(plan.ops):
             out.append({"name": op.name, "kind": rt.OP_NAMES[op.kind], "engine": eng[op.engine],
                         "ms": acc[k] / iters, "flops": op.flops * n * self.M})
+        return out
+
+
+class HeteroEnsemble:
+    """Global (heterogeneous) ensemble on one GPU: several architectures, each with its own clip
+    geometry and its fold members, voting together (global_evaluate_ensembles,
+    evaluate_ensemble.py:1329-1474: weights = ones(n_arch * (folds-1)), :1455).  Every group writes
+    its members' probabilities into its slice of one [sum M, N, C] buffer; one vote kernel reduces
+    it in member order (architecture order of the models list, then val-fold order)."""
+
+    def __init__(self, groups, precision: str = "bf16", max_batch: int = 256, device=None, vote_weights=None,
+                 vote_mode: str = "SUM", **lower_kw):
+        """groups: list of (graph, weight_sets, micro_batch)."""
+        torch = rt.require_cuda()
+        self.torch = torch
+        self.max_batch = int(max_batch)
+        classes = {g.shape(g.output)[-1] for g, _, _ in groups}
+        if len(classes) != 1:
+            raise ValueError("all architectures of a global ensemble must share nb_classes")
+        self.nb_classes = classes.pop()
+        self.M = sum(len(ws) for _, ws, _ in groups)
+        dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.probs = torch.empty((self.M, self.max_batch, self.nb_classes), dtype=torch.float32, device=dev)
+        self.logits = torch.empty_like(self.probs)
+        self.groups: List[DeviceEnsemble] = []
+        m0 = 0
+        for g, ws, mb in groups:
+            m1 = m0 + len(ws)
+            self.groups.append(DeviceEnsemble(g, ws, precision=precision, max_batch=self.max_batch, micro_batch=mb,
+                                              device=dev, probs_out=self.probs[m0:m1], logits_out=self.logits[m0:m1],
+                                              **lower_kw))
+            m0 = m1
+        self.device = dev
+        self.vote_mode = vote_mode
+        self.vote_weights = None
+        if vote_weights is not None:
+            self.vote_weights = torch.as_tensor(np.asarray(vote_weights, np.float64)).to(dev)
+        self.last_launches = 0
+
+    @property
+    def micro_batch(self):
+        return [g.micro_batch for g in self.groups]
+
+    def predict_device(self, group_inputs):
+        """group_inputs[k] = list of uint8 CUDA tensors for architecture k (same n for all)."""
+        n = group_inputs[0][0].shape[0]
+        launches = 0
+        for ens, inputs in zip(self.groups, group_inputs):
+            if inputs[0].shape[0] != n:
+                raise ValueError("every architecture must see the same clips")
+            ens.forward_members(inputs)
+            launches += ens.last_launches
+        probs = self.probs[:, :n].contiguous() if n != self.max_batch else self.probs
+        pred = rt.vote(probs, self.vote_weights, self.vote_mode)
+        self.last_launches = launches + 1
+        return pred
+
+    def predict_host(self, host_group_inputs):
+        dev = [[h.to(self.device, non_blocking=True) for h in inputs] for inputs in host_group_inputs]
+        return self.predict_device(dev).cpu().numpy()
+
+    def profile_ops(self, group_inputs, iters: int = 2):
+        out = []
+        for k, (ens, inputs) in enumerate(zip(self.groups, group_inputs)):
+            for p in ens.profile_ops(inputs, iters):
+                p = dict(p)
+                p["name"] = "%s/%s" % (ens.graph.name, p["name"])
+                out.append(p)
         return out
