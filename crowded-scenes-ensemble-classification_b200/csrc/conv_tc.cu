@@ -329,6 +329,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int id0 = ti.td * a.b_d * a.sd - a.pd;
       const int n0 = ti.tn * a.b_n;
       const int bcol = nt * a.bn;
+      if (a.halo == 2) {
+        // h-halo mode: one stage per (fd, channel chunk); the A box carries kh-1 extra rows, every fh
+        // tap is a swizzle-atom-aligned row offset into it; B holds the kh taps of that (fd, chunk)
+        for (int fd = 0; fd < a.kd; ++fd)
+          for (int ch = 0; ch < a.kchunks; ++ch) {
+            mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);
+            const uint32_t fb = bar_base + 8u * stage;
+            mbar_expect_tx_p(leader, fb, a.a_bytes + a.b_bytes);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            tma_load_5d(leader, sa, &tmap_a, fb, ch * KC, iw0, ih0, id0 + fd, n0);
+            tma_load_2d(leader, sa + A_STAGE, &tmap_b, fb, 0, ((nt * a.kd + fd) * a.kchunks + ch) * a.kh * a.bn);
+            if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+          }
+        continue;
+      }
       if (a.halo) {
         // halo mode: the A box carries kd-1 / kh-1 extra planes / rows; every (fd,fh) tap is a
         // swizzle-atom-aligned row offset into it, so one load feeds all taps of the tile
@@ -380,6 +395,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(bar_base + 128u + 16u + 8u * buf, aph ^ 1u);             // tmem_empty[buf]
       tc_fence_after();
       const uint32_t d_tmem = (uint32_t)buf * 256u;                       // TMEM base is 0 (asserted)
+      if (a.halo == 2) {
+        const int nst = a.kd * a.kchunks;
+        const uint32_t a_fh = ((uint32_t)a.b_w * ROW_BYTES) >> 4;          // one brick row of pixels
+        const uint32_t b_tap = ((uint32_t)a.bn * ROW_BYTES) >> 4;
+        uint32_t acc = 0u;
+        for (int st = 0; st < nst; ++st) {
+          mbar_wait(bar_base + 8u * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+          const uint64_t bd0 = desc_hi | (uint64_t)(((sa + A_STAGE) >> 4) & 0x3FFF);
+          for (int fh = 0; fh < a.kh; ++fh) {
+            const uint64_t ad = ad0 + (uint64_t)(fh * a_fh);
+            const uint64_t bd = bd0 + (uint64_t)(fh * b_tap);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              tc_mma_bf16(leader, d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, acc);
+              acc = 1u;
+            }
+          }
+          tc_commit(leader, bar_base + 64u + 8u * stage);
+          if (st == nst - 1) tc_commit(leader, bar_base + 128u + 8u * buf);
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (buf) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
+        buf ^= 1;
+        continue;
+      }
       if (a.halo) {
         mbar_wait(bar_base + 8u * stage, phase);
         tc_fence_after();
@@ -777,10 +820,16 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   d->has_out1 = out1 != nullptr;
   d->halo = halo;
   const int taps = g.kd * g.kh * g.kw;
-  if (halo) {
+  if (halo == 1) {
     CSE_REQUIRE(g.kw == 1 && d->kchunks == 1 && g.sd == 1 && g.sh == 1 && g.sw == 1 && brick[0] == 1 && brick[1] == 1 &&
                     brick[3] % 8 == 0 && g.kh * bn <= 256,
                 "conv_tc: halo mode needs kw=1, Cin<=kc, stride 1, brick (1,1,h,w%%8==0), kh*bn<=256");
+  } else if (halo == 2) {
+    CSE_REQUIRE(g.kw == 1 && g.sh == 1 && g.sw == 1 && brick[0] == 1 && brick[1] == 1 && brick[3] % 8 == 0 &&
+                    g.kh * bn <= 256,
+                "conv_tc: h-halo mode needs kw=1, stride 1 in H/W, brick (1,1,h,w%%8==0), kh*bn<=256");
+  } else {
+    CSE_REQUIRE(halo == 0, "conv_tc: unknown halo mode %d", halo);
   }
 
   // A: 5-D map over the NDHWC activation (dims C,W,H,D,N).  With stride s the box spans b*s
@@ -794,7 +843,8 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
                              (cuuint64_t)g.Di * g.Hi * wp * g.in_ld * 2};
     cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(brick[3] * g.sw), (cuuint32_t)(brick[2] * g.sh),
                          (cuuint32_t)(brick[1] * g.sd), (cuuint32_t)brick[0]};
-    if (halo) { box[2] = (cuuint32_t)(brick[2] + g.kh - 1); box[3] = (cuuint32_t)(brick[1] + g.kd - 1); }
+    if (halo == 1) { box[2] = (cuuint32_t)(brick[2] + g.kh - 1); box[3] = (cuuint32_t)(brick[1] + g.kd - 1); }
+    if (halo == 2) box[2] = (cuuint32_t)(brick[2] + g.kh - 1);
     cuuint32_t estr[5] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, (cuuint32_t)g.sd, 1};
     CUresult r = enc(&d->tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -808,8 +858,9 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   // B: [Cout_pad][Ktot] bf16, K-major
   {
     // halo mode packs B as [n_tile][tap][bn][kc]: one box = the kh taps of one fd plane
+    // h-halo mode packs B as [n_tile][fd][chunk][fh][bn][kc]: one box = the kh taps of one (fd, chunk)
     const long long ktot = halo ? kc : (long long)taps * d->kchunks * kc;
-    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(d->n_tiles_n * bn) * (halo ? taps : 1)};
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(d->n_tiles_n * bn) * (halo == 1 ? taps : (halo == 2 ? taps * d->kchunks : 1))};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(halo ? g.kh * bn : bn)};
     cuuint32_t estr[2] = {1, 1};
@@ -842,7 +893,14 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   size_t b_stage = (((size_t)bn * kc * 2) + 1023) & ~(size_t)1023;
   d->a_bytes = (uint32_t)(rows * kc * 2);
   d->b_bytes = (uint32_t)(bn * kc * 2);
-  if (halo) {
+  if (halo == 2) {
+    const size_t halo_rows = (size_t)brick[3] * (brick[2] + g.kh - 1);
+    d->a_bytes = (uint32_t)(halo_rows * kc * 2);
+    d->b_bytes = (uint32_t)((size_t)g.kh * bn * kc * 2);
+    a_stage = (d->a_bytes + 1023) & ~(size_t)1023;
+    b_stage = (d->b_bytes + 1023) & ~(size_t)1023;
+    CSE_REQUIRE(((size_t)bn * kc * 2) % 1024 == 0, "conv_tc: h-halo B taps must be 1024-byte multiples");
+  } else if (halo) {
     const size_t halo_rows = (size_t)brick[3] * (brick[2] + g.kh - 1) * (brick[1] + g.kd - 1);
     d->a_bytes = (uint32_t)(halo_rows * kc * 2);
     d->b_bytes = (uint32_t)((size_t)taps * bn * kc * 2);
@@ -852,7 +910,7 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
     CSE_REQUIRE(((size_t)bn * kc * 2) % 1024 == 0 || taps == 1, "conv_tc: halo B taps must be 1024-byte multiples");
   }
   d->a_stage = (uint32_t)a_stage;
-  d->b_resident = (halo && d->n_tiles_n == 1) ? 1 : 0;
+  d->b_resident = (halo == 1 && d->n_tiles_n == 1) ? 1 : 0;
   const size_t resident = d->b_resident ? b_stage : 0;
   const size_t stage = d->b_resident ? a_stage : a_stage + b_stage;
   d->stage_bytes = (uint32_t)stage;

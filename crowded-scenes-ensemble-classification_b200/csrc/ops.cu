@@ -281,6 +281,85 @@ pool_kernel(const T* __restrict__ in, T* __restrict__ out, long long total, WinG
   store_vec<T, V>(out + opix * g.out_ld + c, acc);
 }
 
+// bf16 max pooling, W-blocked: one thread produces WT consecutive output pixels of one 8-channel
+// vector.  The (kd, kh) taps are reduced once per input column (packed bf16x2 max, exact - no fp32
+// round trip), then each output combines its KW columns, so a 3x3x3 / stride-1 window costs
+// (WT+2)*9 16-byte loads per WT outputs instead of WT*27.  -inf ('same' padding, padded taps
+// ignored) or 0 (ZeroPadding3D) padding as in pool_kernel.
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+  uint4 r;
+  __nv_bfloat162 t;
+  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.x), *reinterpret_cast<__nv_bfloat162*>(&b.x)); r.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.y), *reinterpret_cast<__nv_bfloat162*>(&b.y)); r.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.z), *reinterpret_cast<__nv_bfloat162*>(&b.z)); r.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.w), *reinterpret_cast<__nv_bfloat162*>(&b.w)); r.w = *reinterpret_cast<uint32_t*>(&t);
+  return r;
+}
+
+template <int KW, int SW, int WT>
+__global__ void __launch_bounds__(256)
+maxpool_bf16_wblock_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long total,
+                           WinGeom g, int pad_is_zero, int wblocks) {
+  constexpr int NCOL = (WT - 1) * SW + KW;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = g.Co / 8;
+  const int c = (int)(idx % cv) * 8; long long t = idx / cv;
+  const int owb = (int)(t % wblocks); t /= wblocks;
+  const int oh = (int)(t % g.Ho); t /= g.Ho;
+  const int od = (int)(t % g.Do); const long long nn = t / g.Do;
+  const int ow0 = owb * WT;
+  const int iw0 = ow0 * SW - g.pw;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+  uint4 col[NCOL];
+#pragma unroll
+  for (int j = 0; j < NCOL; ++j) col[j] = ninf;
+  bool pad_dh = false;
+  for (int fd = 0; fd < g.kd; ++fd) {
+    const int id = od * g.sd - g.pd + fd;
+    if ((unsigned)id >= (unsigned)g.Di) { pad_dh = true; continue; }
+    for (int fh = 0; fh < g.kh; ++fh) {
+      const int ih = oh * g.sh - g.ph + fh;
+      if ((unsigned)ih >= (unsigned)g.Hi) { pad_dh = true; continue; }
+      const __nv_bfloat16* row = in + (((nn * g.Di + id) * g.Hi + ih) * (long long)g.Wi) * g.in_ld + c;
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) {
+        const int iw = iw0 + j;
+        if ((unsigned)iw < (unsigned)g.Wi)
+          col[j] = hmax8(col[j], *reinterpret_cast<const uint4*>(row + (long long)iw * g.in_ld));
+      }
+    }
+  }
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  __nv_bfloat16* orow = out + (((nn * g.Do + od) * g.Ho + oh) * (long long)g.Wo) * g.out_ld + c;
+#pragma unroll
+  for (int o = 0; o < WT; ++o) {
+    const int ow = ow0 + o;
+    if (ow >= g.Wo) break;
+    uint4 m = col[o * SW];
+    bool pad = pad_dh || (unsigned)(iw0 + o * SW) >= (unsigned)g.Wi;
+#pragma unroll
+    for (int fw = 1; fw < KW; ++fw) {
+      m = hmax8(m, col[o * SW + fw]);
+      pad = pad || (unsigned)(iw0 + o * SW + fw) >= (unsigned)g.Wi;
+    }
+    if (pad && pad_is_zero) m = hmax8(m, zero);
+    *reinterpret_cast<uint4*>(orow + (long long)ow * g.out_ld) = m;
+  }
+}
+
+template <int KW, int SW>
+static int maxpool_wblock(bool pad_is_zero, const void* in, void* out, int n, const WinGeom& g, cudaStream_t st) {
+  constexpr int WT = 4;
+  const int wblocks = ceil_div(g.Wo, WT);
+  const long long total = (long long)n * g.Do * g.Ho * wblocks * (g.Co / 8);
+  if (total == 0) return CSE_OK;
+  maxpool_bf16_wblock_kernel<KW, SW, WT><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, g, pad_is_zero ? 1 : 0, wblocks);
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}
+
 template <typename T, int V>
 static int pool_t(bool is_max, bool pad_is_zero, const void* in, void* out, int n, const WinGeom& g,
                   cudaStream_t st) {
@@ -308,6 +387,11 @@ int launch_pool(int dt, bool is_max, bool pad_is_zero, const void* in, void* out
     return pool_t<float, 1>(is_max, pad_is_zero, in, out, n, g, st);
   }
   if (dt == CSE_BF16) {
+    if (is_max && vec_ok(g.Co, g.in_ld, g.out_ld, 8, in, out, 2)) {
+      if (g.kw == 3 && g.sw == 1) return maxpool_wblock<3, 1>(pad_is_zero, in, out, n, g, st);
+      if (g.kw == 3 && g.sw == 2) return maxpool_wblock<3, 2>(pad_is_zero, in, out, n, g, st);
+      if (g.kw == 2 && g.sw == 2) return maxpool_wblock<2, 2>(pad_is_zero, in, out, n, g, st);
+    }
     if (vec_ok(g.Co, g.in_ld, g.out_ld, 8, in, out, 2))
       return pool_t<__nv_bfloat16, 8>(is_max, pad_is_zero, in, out, n, g, st);
     return pool_t<__nv_bfloat16, 1>(is_max, pad_is_zero, in, out, n, g, st);

@@ -181,7 +181,7 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
         CSE_REQUIRE(o.in_dtype == CSE_BF16 && o.out_dtype == CSE_BF16 && o.w_dtype == CSE_BF16,
                     "op %zu: tcgen05 engine needs bf16 in/out/weights", i);
         const int kchunks = ceil_div(g.Ci, o.kc > 0 ? o.kc : 64);
-        const long long ktot = (long long)g.kd * g.kh * g.kw * kchunks * o.kc;
+        const long long ktot = (long long)g.kd * g.kh * g.kw * kchunks * o.kc;   // same element count in every packing
         const long long rows = (long long)ceil_div(g.Co, o.bn > 0 ? o.bn : 16) * o.bn;
         if ((rc = check_span(p, o.w_off, ktot * rows, CSE_BF16, "tc weights", true))) return rc;
         rc = conv_tc_build(&po.tc, p->ws + o.in0_off, p->wts + o.w_off, p->ws + o.out0_off,

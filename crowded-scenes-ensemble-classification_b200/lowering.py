@@ -274,6 +274,30 @@ def pack_tc_weights_halo(kernel: np.ndarray, kc: int, bn: int, n_tiles: int) -> 
     return to_bf16_bits(np.ascontiguousarray(w).reshape(n_tiles * taps * bn, kc))
 
 
+def pack_tc_weights_hhalo(kernel: np.ndarray, kc: int, bn: int, n_tiles: int) -> np.ndarray:
+    """Keras [kd,kh,1,Ci,Co] -> [n_tile][fd][chunk][fh][bn][kc] bf16 bits (h-halo mode: the kh taps of one
+    (fd, channel chunk) are consecutive row blocks of one 2-D tensor with kc columns)."""
+    kd, kh, kw, ci, co = kernel.shape
+    assert kw == 1
+    nch = -(-ci // kc)
+    w = np.zeros((n_tiles * bn, kd, kh, nch * kc), np.float32)
+    w[:co, :, :, :ci] = kernel[:, :, 0, :, :].transpose(3, 0, 1, 2)
+    w = w.reshape(n_tiles, bn, kd, kh, nch, kc).transpose(0, 2, 4, 3, 1, 5)
+    return to_bf16_bits(np.ascontiguousarray(w).reshape(-1, kc))
+
+
+def choose_brick_hhalo(ho: int, wo: int, kh: int) -> Tuple[int, int, int, int]:
+    """Brick (1,1,h,w), w % 8 == 0, minimising the rows loaded per output plane (tiles x haloed box)."""
+    best, best_key = None, None
+    for bw in range(8, min(_round_up(wo, 8), 128) + 1, 8):
+        for bh in range(1, 128 // bw + 1):
+            tiles = -(-ho // bh) * -(-wo // bw)
+            key = (tiles * (bh + kh - 1) * bw, tiles, -bw)
+            if best_key is None or key < best_key:
+                best, best_key = (1, 1, bh, bw), key
+    return best
+
+
 def choose_brick_hw(ho: int, wo: int, mult=(1, 1, 1)) -> Optional[Tuple[int, int, int, int]]:
     """Brick (1,1,h,w) with w % 8 == 0 (halo mode: a one-row shift must be a whole swizzle atom)."""
     best, best_key = None, None
@@ -503,8 +527,13 @@ class Lowerer:
             kc = choose_kc(ci)
             bn, n_tiles = choose_bn(co)
             op.engine, op.w_dtype, op.kc, op.bn = rt.ENGINE_TCGEN05, rt.BF16, kc, bn
-            hw_brick = choose_brick_hw(out_dims[1], out_dims[2], mult) if halo else None
-            if (hw_brick is not None and kernel.shape[2] == 1 and ci <= kc and kernel.shape[1] * bn <= 256
+            hw_brick = choose_brick_hw(out_dims[1], out_dims[2], mult) if halo is True or halo == 1 else None
+            if (halo == 2 and kernel.shape[2] == 1 and tuple(s[1:]) == (1, 1) and kernel.shape[1] * bn <= 256
+                    and (bn * kc * 2) % 1024 == 0 and not pool):
+                op.halo = 2
+                op.brick = choose_brick_hhalo(out_dims[1], out_dims[2], kernel.shape[1])
+                op.w_blob = self.blob(pack_tc_weights_hhalo(kernel, kc, bn, n_tiles))
+            elif (hw_brick is not None and kernel.shape[2] == 1 and ci <= kc and kernel.shape[1] * bn <= 256
                     and (bn * kc * 2) % 1024 == 0):
                 op.halo = 1
                 op.brick = hw_brick
@@ -670,7 +699,7 @@ class Lowerer:
                         k2[:, fh, 0, c0:c0 + ci, :] = kernel[:, th, tw, :, :]
         view = TRef(x.buf, 0, 4 * cell, cell, x.dims, x.dtype, x.wpitch, x.wpad)
         op = self._conv_like(node.name, view, k2, bias, (7, 4, 1), (2, 1, 1), (pb[0], (pb[1] + 1) // 2, 0), out_dims,
-                             chain_bn, relu, final, layers, flops=flops)
+                             chain_bn, relu, final, layers, flops=flops, halo=2 if self.stem_halo else 0)
         if op.engine != rt.ENGINE_TCGEN05:
             raise RuntimeError("s2d stem must lower to the tcgen05 engine")
         for l in layers:

@@ -89,7 +89,8 @@ typedef struct cse_op {
                                 pooled tensor [n, pool_dims, Cout]; out_dims stay the conv's own output dims */
   int32_t pool_dims[3];      /* D,H,W of the pooled output */
   int32_t pool_zero;         /* 1 = positions beyond the conv output count as 0 (ZeroPadding3D in front of the pool) */
-  int32_t tc_halo;           /* TCGEN05: 1 = (kd,kh)-halo'd A brick, weights packed [n_tile][tap][bn][kc] (packed stem) */
+  int32_t tc_halo;           /* TCGEN05: 1 = (kd,kh)-halo'd A brick, weights packed [n_tile][tap][bn][kc] (packed stem);
+                                2 = kh-halo'd A brick, one stage per (fd, chunk), weights [n_tile][fd][chunk][fh][bn][kc] */
   int32_t pre_s2d;           /* PREPROCESS: 1 = 2x2 space-to-depth over (H,W) for the stride-2 7x7x7 stems: out_dims =
                                 T, ceil(H/2), ceil(W/2); cell channel (ph*2+pw)*C + c, zero-padded to out_ld = 8/16 */
   int64_t in0_off, in1_off;  /* workspace byte offsets (-1 = none); in1 = residual for CONV3D, 2nd addend for ADD */

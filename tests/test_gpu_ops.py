@@ -176,8 +176,9 @@ S2D_STEM = [((8, 16, 16), 3, 64, 2), ((9, 21, 19), 3, 64, 2), ((6, 20, 28), 2, 6
             ((7, 10, 34), 1, 16, 1)]
 
 
+@pytest.mark.parametrize("halo", [True, False])
 @pytest.mark.parametrize("dhw,c,cout,nb", S2D_STEM)
-def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb):
+def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb, halo):
     """7x7x7 / stride 2 'same' stem on the raw clip (I3D Conv3d_1a_7x7, R3D stem) on the tcgen05 engine:
     2x2 space-to-depth cells written by the pre-processing kernel, 4-cell window through an
     overlapping-stride TMA view, k=(7,4,1) stride (2,1,1) with a zero-extended regrouped kernel.
@@ -187,9 +188,10 @@ def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb):
         x = g.conv3d(x, cout, (7, 7, 7), (2, 2, 2), "same", True, None, name="c")
         x = g.bn(x, scale=True, name="b")
         g.relu(x, name="r")
-    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c)
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c, stem_halo=halo)
     op = [o for o in m.plan.ops if o.name == "c"][0]
     assert op.engine == rt.ENGINE_TCGEN05 and op.k == (7, 4, 1) and op.s == (2, 1, 1)
+    assert op.halo == (2 if halo else 0)      # h-halo: one A box per input plane feeds the 4 kh taps
     xs = clips(11, nb, dhw + (c,))
     run(m, [xs])
     xin = torch.as_tensor((xs.astype(np.float64) - 128.0) / 64.0, dtype=T64)      # exact in bf16
@@ -331,6 +333,23 @@ def test_zeropad_maxpool_and_avgpool():
     assert np.array_equal(m.read_tensor(m.plan.tensors["p"], 2), exp.astype(np.float32))
     avg = O.avgpool3d(xin, (2, 7, 7)).numpy()
     np.testing.assert_allclose(m.read_tensor(m.plan.tensors["avg"], 2), avg, rtol=1e-5, atol=1e-6)
+
+
+def test_zeropad_maxpool_bf16_wblocked():
+    """ZeroPadding3D + MaxPooling3D on the stand-alone W-blocked bf16 kernel (0-valued padding must win
+    over negative activations), ragged W (9 outputs -> partial last block)."""
+    dhw = (3, 6, 17)
+
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, 24, (1, 1, 1), (1, 1, 1), "same", True, None, name="pre")
+        z = g.zeropad(x, ((0, 0), (0, 1), (0, 1)), name="z")
+        g.maxpool(z, (2, 2, 2), (2, 2, 2), "valid", name="p")
+    g, w, m = make_member(build, "bf16", 2, tc=False, scale=[1 / 64.0] * 3, mean=[200.0] * 3)   # mostly negative
+    run(m, [clips(7, 2, dhw + (3,))])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], 2), dtype=T64)
+    exp = O.maxpool3d(O.zeropad3d(xin, ((0, 0), (0, 1), (0, 1))), (2, 2, 2), (2, 2, 2), "valid").numpy()
+    assert np.array_equal(m.read_tensor(m.plan.tensors["p"], 2), exp.astype(np.float32))
 
 
 # --------------------------------------------------------------------------- vote
