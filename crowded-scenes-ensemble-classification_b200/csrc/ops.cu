@@ -315,18 +315,33 @@ maxpool_bf16_wblock_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* 
 #pragma unroll
   for (int j = 0; j < NCOL; ++j) col[j] = ninf;
   bool pad_dh = false;
+  // column validity / clamped offsets are tap-independent
+  bool wok[NCOL];
+  long long woff[NCOL];
+#pragma unroll
+  for (int j = 0; j < NCOL; ++j) {
+    const int iw = iw0 + j;
+    wok[j] = (unsigned)iw < (unsigned)g.Wi;
+    woff[j] = (long long)min(max(iw, 0), g.Wi - 1) * g.in_ld;
+  }
   for (int fd = 0; fd < g.kd; ++fd) {
     const int id = od * g.sd - g.pd + fd;
-    if ((unsigned)id >= (unsigned)g.Di) { pad_dh = true; continue; }
+    const bool okd = (unsigned)id < (unsigned)g.Di;
+    const int idc = min(max(id, 0), g.Di - 1);
     for (int fh = 0; fh < g.kh; ++fh) {
       const int ih = oh * g.sh - g.ph + fh;
-      if ((unsigned)ih >= (unsigned)g.Hi) { pad_dh = true; continue; }
-      const __nv_bfloat16* row = in + (((nn * g.Di + id) * g.Hi + ih) * (long long)g.Wi) * g.in_ld + c;
+      const bool ok = okd && (unsigned)ih < (unsigned)g.Hi;
+      const int ihc = min(max(ih, 0), g.Hi - 1);
+      pad_dh = pad_dh || !ok;
+      const __nv_bfloat16* row = in + (((nn * g.Di + idc) * g.Hi + ihc) * (long long)g.Wi) * g.in_ld + c;
+      // all NCOL loads are issued before the first max (addresses are clamped, never predicated off)
+      uint4 v[NCOL];
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(row + woff[j]));
 #pragma unroll
       for (int j = 0; j < NCOL; ++j) {
-        const int iw = iw0 + j;
-        if ((unsigned)iw < (unsigned)g.Wi)
-          col[j] = hmax8(col[j], *reinterpret_cast<const uint4*>(row + (long long)iw * g.in_ld));
+        const uint4 x = (ok && wok[j]) ? v[j] : ninf;
+        col[j] = hmax8(col[j], x);
       }
     }
   }
