@@ -39,17 +39,17 @@ import numpy as np
 # members = folds - 1 = 4 per architecture, as the reference builds them for `-fn 5`
 # (evaluate_ensemble.py:1042-1049).
 WORKLOADS = {
-    "c3d_ens": ([("C3D", (16, 112, 112, 3), 4, 128)], 256),                       # BASELINE configs[1]
+    "c3d_ens": ([("C3D", (16, 112, 112, 3), 4, 256)], 256),                       # BASELINE configs[1]
     "c3d_single_b8": ([("C3D", (16, 112, 112, 3), 1, 8)], 8),                     # configs[0]
-    "r3d34_ens": ([("R3D_34", (16, 112, 112, 3), 4, 128)], 256),
-    "i3d20_ens": ([("I3D", (20, 224, 224, 3), 4, 32)], 32),                       # reference-true T=20 (train.py:1573)
-    "i3d64_ens": ([("I3D", (64, 224, 224, 3), 4, 8)], 8),                         # configs[2]
-    "twostream20_ens": ([("TWOSTREAM_I3D", (20, 224, 224, 0), 4, 16)], 32),
-    "twostream64_ens": ([("TWOSTREAM_I3D", (64, 224, 224, 0), 4, 8)], 8),         # configs[3]
-    "global_hetero": ([("C3D", (16, 112, 112, 3), 4, 128), ("I3D", (64, 224, 224, 3), 4, 8),
-                       ("R3D_34", (16, 112, 112, 3), 4, 128)], 256),              # configs[4] (per GPU)
-    "global_hetero_t20": ([("C3D", (16, 112, 112, 3), 4, 128), ("I3D", (20, 224, 224, 3), 4, 32),
-                           ("R3D_34", (16, 112, 112, 3), 4, 128)], 256),
+    "r3d34_ens": ([("R3D_34", (16, 112, 112, 3), 4, 256)], 256),
+    "i3d20_ens": ([("I3D", (20, 224, 224, 3), 4, 128)], 128),                     # reference-true T=20 (train.py:1573)
+    "i3d64_ens": ([("I3D", (64, 224, 224, 3), 4, 32)], 32),                       # configs[2]
+    "twostream20_ens": ([("TWOSTREAM_I3D", (20, 224, 224, 0), 4, 64)], 64),
+    "twostream64_ens": ([("TWOSTREAM_I3D", (64, 224, 224, 0), 4, 16)], 16),       # configs[3]
+    "global_hetero": ([("C3D", (16, 112, 112, 3), 4, 256), ("I3D", (64, 224, 224, 3), 4, 32),
+                       ("R3D_34", (16, 112, 112, 3), 4, 256)], 256),              # configs[4] (per GPU)
+    "global_hetero_t20": ([("C3D", (16, 112, 112, 3), 4, 256), ("I3D", (20, 224, 224, 3), 4, 128),
+                           ("R3D_34", (16, 112, 112, 3), 4, 256)], 256),
 }
 
 

@@ -224,10 +224,29 @@ def choose_kc(ci: int) -> int:
     return best
 
 
-def choose_bn(co: int) -> Tuple[int, int]:
-    n_tiles = -(-co // 256)
-    bn = _round_up(-(-co // n_tiles), 16)
-    return bn, n_tiles
+SM_COUNT = 148      # B200: persistent grid = one CTA per SM
+
+
+def choose_bn(co: int, m_tiles: int = 0) -> Tuple[int, int]:
+    """N tile (multiple of 16, <= 256) and number of N tiles.  With m_tiles given, the split that
+    minimises waves x per-tile cost on 148 SMs: a 128 x bn x 64 k-step costs max(MMA issue time,
+    operand bytes / L2->SM bandwidth), so narrower N tiles are cheaper per tile but re-read A, and
+    only pay off when the wide tiling would leave SMs idle (small-M layers: R3D stages 3-4, I3D 5x)."""
+    best, best_key = None, None
+    min_t = -(-co // 256)
+    for n_tiles in range(min_t, max(min_t + 1, 9)):
+        bn = _round_up(-(-co // n_tiles), 16)
+        if n_tiles > min_t and bn < 64:
+            break
+        if m_tiles <= 0:
+            return bn, n_tiles
+        mma = 4 * max(bn / 2.0, 48.0)                 # cycles per k-step: 4 x (128 x bn x 16)
+        l2 = (128 * 128 + bn * 128) / 85.0            # A + B bytes per k-step at ~85 B/clk/SM
+        waves = -(-(m_tiles * n_tiles) // SM_COUNT)
+        key = (waves * max(mma, l2), n_tiles)
+        if best_key is None or key < best_key:
+            best, best_key = (bn, n_tiles), key
+    return best
 
 
 def choose_brick(nb: int, do: int, ho: int, wo: int, mult=(1, 1, 1)) -> Tuple[int, int, int, int]:
@@ -317,8 +336,10 @@ class Lowerer:
     def __init__(self, g: Graph, weights: Dict[str, List[np.ndarray]], precision: str = "bf16",
                  max_batch: int = 8, tc: bool = True, tc_strided: bool = True,
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
-                 stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True):
+                 stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True,
+                 balance_n: bool = True):
         self.keep_all = keep_all
+        self.balance_n = balance_n
         self.s2d_stem = s2d_stem
         self.fuse_pool = fuse_pool and precision == "bf16" and tc
         self.stem_unroll = stem_unroll
@@ -525,7 +546,10 @@ class Lowerer:
             raise RuntimeError("fused pooling was planned for a conv that cannot use the tcgen05 engine")
         if tc_ok:
             kc = choose_kc(ci)
-            bn, n_tiles = choose_bn(co)
+            gen_brick = choose_brick(self.nb, *out_dims, mult=mult)
+            m_tiles = (-(-self.nb // gen_brick[0]) * -(-out_dims[0] // gen_brick[1]) * -(-out_dims[1] // gen_brick[2])
+                       * -(-out_dims[2] // gen_brick[3]))
+            bn, n_tiles = choose_bn(co, m_tiles if self.balance_n else 0)
             op.engine, op.w_dtype, op.kc, op.bn = rt.ENGINE_TCGEN05, rt.BF16, kc, bn
             hw_brick = choose_brick_hw(out_dims[1], out_dims[2], mult) if halo is True or halo == 1 else None
             if (halo == 2 and kernel.shape[2] == 1 and tuple(s[1:]) == (1, 1) and kernel.shape[1] * bn <= 256
@@ -539,7 +563,7 @@ class Lowerer:
                 op.brick = hw_brick
                 op.w_blob = self.blob(pack_tc_weights_halo(kernel, kc, bn, n_tiles))
             else:
-                op.brick = choose_brick(self.nb, *out_dims, mult=mult)
+                op.brick = gen_brick
                 op.w_blob = self.blob(pack_tc_weights(kernel, kc, bn, n_tiles))
         else:
             op.engine = rt.ENGINE_DIRECT
