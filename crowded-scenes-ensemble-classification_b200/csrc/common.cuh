@@ -82,6 +82,7 @@ struct ConvTcDesc {            // built once at plan finalize
   int ec, nslots;              // epilogue chunk width (channels per TMA store) and staging slots
   uint32_t slot_bytes;
   bool has_out1;
+  int pair_pool;               // pair-packed stem with the (1,2,2) max-pool done in registers
   int halo;                    // (kd,kh)-halo'd A brick: one pipeline stage per tile
   int b_resident;              // halo + single N tile: weights stay in smem for the CTA's lifetime
   int pool[3], pool_dims[3], pool_zero;   // fused MaxPooling3D (window == stride) and its output dims
@@ -97,7 +98,7 @@ struct ConvTcDesc {            // built once at plan finalize
 };
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
                   int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
-                  const int pool_dims[3], int pool_zero);
+                  const int pool_dims[3], int pool_zero, int pair_pool);
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);
 
 }  // namespace cse

@@ -172,6 +172,7 @@ struct ConvTcArgs {
   uint32_t slot_bytes;             // bytes of one staging slot (full tile [+ out1 tile] [+ pooled tile])
   int pool_d, pool_h, pool_w;      // fused MaxPooling3D window (= stride); 0 = no pooling
   int pool_zero;                   // rows outside the conv output count as 0 (ZeroPadding3D before the pool)
+  int pair_pool;                   // pair-packed stem: GEMM row = 2 output pixels (N = 2*Cout), (1,2,2) max-pool in registers
   int step1[5], step2[5];          // gridDim.x and 2*gridDim.x as mixed-radix digits (nt, tw, th, td, tn)
   Epilogue ep;
 };
@@ -317,9 +318,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // the whole (single N tile) weight matrix stays in shared memory for the CTA's lifetime
       const uint32_t bb = bar_base + 160u;
       mbar_expect_tx_p(leader, bb, a.b_bytes);
-      const uint32_t b_fd = (uint32_t)(a.kh * a.bn) * ROW_BYTES;
-      for (int fd = 0; fd < a.kd; ++fd)
-        tma_load_2d(leader, smem_base + a.b_region + fd * b_fd, &tmap_b, bb, 0, fd * a.kh * a.bn);
+      const uint32_t b_tap = (uint32_t)a.bn * ROW_BYTES;        // resident B: one box per (fd,fh) tap
+      for (int t = 0; t < a.kd * a.kh; ++t)
+        tma_load_2d(leader, smem_base + a.b_region + t * b_tap, &tmap_b, bb, 0, t * a.bn);
     }
     TileIter ti;
     for (ti.init(a, blockIdx.x); ti.tile < a.num_tiles; ti.advance(a, a.step1, gridDim.x)) {
@@ -549,7 +550,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // last barrier); only when the N tile changed
       if (nt != last_nt) {
         for (int i = et; i < a.bn; i += 128) {
-          const int c = min(col_base + i, a.Co - 1);
+          const int c = a.pair_pool ? (i % (a.bn >> 1)) : min(col_base + i, a.Co - 1);
           par[0][i] = has_scale0 ? __ldg(a.ep.scale0 + c) : 1.f;
           par[1][i] = a.ep.shift0 ? __ldg(a.ep.shift0 + c) : 0.f;
           par[2][i] = a.ep.scale1 ? __ldg(a.ep.scale1 + c) : 1.f;
@@ -561,6 +562,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(bar_base + 128u + 8u * buf, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 256u;
+      if (EC == 64 && a.pair_pool) {
+        // Pair-packed stem + MaxPooling3D (1,2,2): row = (h, pixel pair), columns [0,64) = left pixel,
+        // [64,128) = right pixel.  max over the pair in registers, + bias, (ReLU) -> bf16, max with the
+        // partner row (h ^ 1 = lane ^ b_w, same warp) by shuffle; max commutes with the monotone
+        // bias/ReLU/rounding, so the values equal pool(relu(conv + bias)) computed in bf16.
+        if (store_thread) {
+          switch (a.nslots) {
+            case 1: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+            case 2: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+            case 3: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+            default: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const int prow = (rh >> 1) * a.b_w + rw;                         // row of the pooled tile
+        const uint32_t pdst = my_stg + (uint32_t)slot * slot_bytes + (uint32_t)prow * 128u;
+        const uint32_t pswz = (uint32_t)(prow & 7);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t ra[16], rb[16];
+          tc_ld16(t_row + (uint32_t)(q * 16), ra);
+          tc_ld16(t_row + (uint32_t)(64 + q * 16), rb);
+          tc_wait_ld();
+          if (q == 3) {
+            tc_fence_before();
+            mbar_arrive(bar_base + 144u + 8u * buf);
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 sh = *reinterpret_cast<const float4*>(&par[1][q * 16 + i4 * 4]);
+            const float y0 = fmaxf(__uint_as_float(ra[i4 * 4 + 0]), __uint_as_float(rb[i4 * 4 + 0])) + sh.x;
+            const float y1 = fmaxf(__uint_as_float(ra[i4 * 4 + 1]), __uint_as_float(rb[i4 * 4 + 1])) + sh.y;
+            const float y2 = fmaxf(__uint_as_float(ra[i4 * 4 + 2]), __uint_as_float(rb[i4 * 4 + 2])) + sh.z;
+            const float y3 = fmaxf(__uint_as_float(ra[i4 * 4 + 3]), __uint_as_float(rb[i4 * 4 + 3])) + sh.w;
+            pk[i4 * 2 + 0] = relu0 ? pack_bf16x2_relu(y0, y1) : pack_bf16x2(y0, y1);
+            pk[i4 * 2 + 1] = relu0 ? pack_bf16x2_relu(y2, y3) : pack_bf16x2(y2, y3);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, pk[i], a.b_w);
+            const __nv_bfloat162 t = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&pk[i]),
+                                             *reinterpret_cast<const __nv_bfloat162*>(&other));
+            pk[i] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          if ((q >> 1) == (rh & 1)) {                                   // each lane of the row pair stages half the channels
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pdst + (((uint32_t)(2 * q) ^ pswz) << 4)), "r"(pk[0]),
+                         "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pdst + (((uint32_t)(2 * q + 1) ^ pswz) << 4)), "r"(pk[4]),
+                         "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (store_thread) {
+          tma_store_5d(&tmap_o0, my_stg + (uint32_t)slot * slot_bytes, 0, ow0, oh0 >> 1, od0, on0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (++slot == a.nslots) slot = 0;
+        acc_phase ^= 1u;
+        continue;
+      }
       for (int c0 = 0; c0 < a.bn; c0 += EC) {
         // the staging slot we are about to overwrite must have been read by its TMA store
         if (store_thread) {
@@ -793,7 +856,7 @@ static int encode_out_map(PFN_encodeTiled enc, CUtensorMap* m, void* out, int ld
 
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
                   int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
-                  const int pool_dims[3], int pool_zero) {
+                  const int pool_dims[3], int pool_zero, int pair_pool) {
   CSE_REQUIRE(kc == 16 || kc == 32 || kc == 64, "conv_tc: kc=%d must be 16/32/64", kc);
   CSE_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "conv_tc: bn=%d must be a multiple of 16 in [16,256]", bn);
   CSE_REQUIRE(g.Ci % 8 == 0 && g.in_ld % 8 == 0, "conv_tc: Cin=%d / ld=%d must be multiples of 8", g.Ci, g.in_ld);
@@ -819,10 +882,18 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   d->ec = (bn % 64 == 0) ? 64 : (bn % 32 == 0 ? 32 : 16);
   d->has_out1 = out1 != nullptr;
   d->halo = halo;
+  d->pair_pool = pair_pool;
+  if (pair_pool) {
+    // GEMM view: g.Wo = pixel pairs, g.Co = 2*Cout = bn = 128; pool_dims = D, H/2, W/2 (pairs)
+    CSE_REQUIRE(halo == 1 && bn == 128 && g.Co == 128 && d->n_tiles_n == 1 && out1 == nullptr && pool && pool[0] == 1 &&
+                    pool[1] == 2 && pool[2] == 1 && (brick[3] == 8 || brick[3] == 16) && brick[2] % 2 == 0 &&
+                    brick[2] * brick[3] == TC_BM && g.Ho % 2 == 0 && g.out_ld % 8 == 0,
+                "conv_tc: pair-pool stem needs halo mode, N = 128, brick (1,1,h,8|16) of 128 rows, even H");
+  }
   const int taps = g.kd * g.kh * g.kw;
   if (halo == 1) {
     CSE_REQUIRE(g.kw == 1 && d->kchunks == 1 && g.sd == 1 && g.sh == 1 && g.sw == 1 && brick[0] == 1 && brick[1] == 1 &&
-                    brick[3] % 8 == 0 && g.kh * bn <= 256,
+                    brick[3] % 8 == 0 && (g.kh * bn <= 256 || d->n_tiles_n == 1),
                 "conv_tc: halo mode needs kw=1, Cin<=kc, stride 1, brick (1,1,h,w%%8==0), kh*bn<=256");
   } else if (halo == 2) {
     CSE_REQUIRE(g.kw == 1 && g.sh == 1 && g.sw == 1 && brick[0] == 1 && brick[1] == 1 && brick[3] % 8 == 0 &&
@@ -862,7 +933,8 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
     const long long ktot = halo ? kc : (long long)taps * d->kchunks * kc;
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(d->n_tiles_n * bn) * (halo == 1 ? taps : (halo == 2 ? taps * d->kchunks : 1))};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(halo ? g.kh * bn : bn)};
+    const bool resident = (halo == 1 && d->n_tiles_n == 1);       // resident B is loaded tap by tap
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)((halo && !resident) ? g.kh * bn : bn)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&d->tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -881,12 +953,24 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
                 "conv_tc: brick %dx%dx%d is not a multiple of the pool window %dx%dx%d", brick[1], brick[2], brick[3],
                 pool[0], pool[1], pool[2]);
   }
-  int rc = pooled ? encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick, pool, pool_dims)
-                  : encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick);
-  if (rc) return rc;
-  rc = encode_out_map(enc, &d->tmap_o1, d->has_out1 ? out1 : out0, d->has_out1 ? out1_ld : g.out_ld, g, max_batch, d->ec,
-                      brick);
-  if (rc) return rc;
+  int rc;
+  if (pair_pool) {
+    // pooled tensor [N, D, H/2, W/2, Cout]; box = Cout channels x (brick_w pairs) x (brick_h / 2) rows
+    WinGeom pg = g;
+    pg.Co = g.Co / 2;
+    const int pbrick[4] = {1, 1, brick[2], brick[3]};
+    const int ppool[3] = {1, 2, 1};
+    rc = encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, pg, max_batch, 64, pbrick, ppool, pool_dims);
+    if (rc) return rc;
+    d->tmap_o1 = d->tmap_o0;
+  } else {
+    rc = pooled ? encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick, pool, pool_dims)
+                : encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick);
+    if (rc) return rc;
+    rc = encode_out_map(enc, &d->tmap_o1, d->has_out1 ? out1 : out0, d->has_out1 ? out1_ld : g.out_ld, g, max_batch, d->ec,
+                        brick);
+    if (rc) return rc;
+  }
 
   // shared memory: [pipeline stages][epilogue staging slots]; 227 KB per CTA minus static + alignment slack
   size_t a_stage = (size_t)TC_BM * kc * 2;
@@ -916,6 +1000,7 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   d->stage_bytes = (uint32_t)stage;
   size_t slot = (size_t)TC_BM * d->ec * 2 * (d->has_out1 ? 2 : 1);
   if (pooled) slot += (((size_t)TC_BM / (pool[0] * pool[1] * pool[2])) * d->ec * 2 + 1023) & ~(size_t)1023;
+  if (pair_pool) slot = (size_t)(TC_BM / 2) * 64 * 2;           // only the pooled [64 rows][64 ch] tile is staged
   // staging slots per epilogue group (two groups): as many as fit (<= 4) while the load pipeline
   // keeps >= 4 stages (3 for the widest tiles); a TMA store only releases its slot once it has
   // read it, so more slots = more stores in flight
@@ -981,6 +1066,7 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   a.a_stage = d.a_stage; a.stage_bytes = d.stage_bytes;
   a.halo = d.halo; a.b_resident = d.b_resident; a.b_region = d.b_region;
   a.pool_d = d.pool[0]; a.pool_h = d.pool[1]; a.pool_w = d.pool[2]; a.pool_zero = d.pool_zero;
+  a.pair_pool = d.pair_pool;
   a.stage_region = d.stage_region;
   a.nslots = d.nslots; a.slot_bytes = d.slot_bytes;
   a.ep = ep;

@@ -591,6 +591,9 @@ preprocess_kernel(const uint8_t* __restrict__ src, TO* __restrict__ out, long lo
 // outside the row) x C channels, tightly packed (index j*C + c) and zero-padded to 16 channels
 // -> [n,T,H,W,16] bf16 (32 B per pixel).  The 3 kw taps of a 3x3x3 stem conv then are one
 // contiguous, aligned K=16 chunk per pixel.
+// NB = 3: per output pixel w, neighbours w-1..w+1.  NB = 4 ("pair" mode, pair-packed stem): the
+// output element is the pixel pair p = (2p, 2p+1) carrying pixels 2p-1..2p+2; a.Wo = number of pairs.
+template <int NB>
 __global__ void __launch_bounds__(256)
 preprocess_unroll_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, long long total,
                          PreArgs a) {
@@ -604,10 +607,11 @@ preprocess_unroll_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restr
 #pragma unroll
   for (int c = 0; c < 16; ++c) v[c] = __float2bfloat16_rn(0.f);
   const long long row = ((nn * a.T + (d + a.t0)) * a.H + (h + a.h0)) * a.W + a.w0;
+  const int wlim = (NB == 4) ? (a.W - a.w0) : a.Wo;         // pixels available in the (cropped) row
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const int ws = w - 1 + j;
-    if (ws >= 0 && ws < a.Wo) {
+  for (int j = 0; j < NB; ++j) {
+    const int ws = (NB == 4 ? 2 * w : w) - 1 + j;
+    if (ws >= 0 && ws < wlim) {
       const uint8_t* s = src + (row + ws) * a.C;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -687,9 +691,10 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
     return CSE_OK;
   }
   if (unroll_w > 0) {
-    CSE_REQUIRE(unroll_w == 3 && out_dt == CSE_BF16 && out_ld == 16 && C <= 4 && wpitch <= 0,
-                "preprocess: unroll_w supports k=3, bf16, out_ld=16, C<=4");
-    CSE_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + To <= T && h0 + Ho <= H && w0 + Wo <= W,
+    CSE_REQUIRE((unroll_w == 3 || unroll_w == 4) && out_dt == CSE_BF16 && out_ld == 16 && C * unroll_w <= 16 && wpitch <= 0,
+                "preprocess: unroll_w supports 3 (pixel) / 4 (pixel pair), bf16, out_ld=16, C*unroll_w<=16");
+    CSE_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + To <= T && h0 + Ho <= H &&
+                    w0 + (unroll_w == 4 ? 2 * Wo - 1 : Wo) <= W,
                 "preprocess: crop outside clip");
     PreArgs a;
     a.T = T; a.H = H; a.W = W; a.C = C; a.t0 = t0; a.h0 = h0; a.w0 = w0;
@@ -700,7 +705,10 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
     }
     const long long total = (long long)n * To * Ho * Wo;
     if (total == 0) return CSE_OK;
-    preprocess_unroll_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
+    if (unroll_w == 4)
+      preprocess_unroll_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
+    else
+      preprocess_unroll_kernel<3><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
     CSE_CUDA(cudaGetLastError());
     return CSE_OK;
   }

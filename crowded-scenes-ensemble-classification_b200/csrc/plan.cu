@@ -157,7 +157,8 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
       continue;
     }
     if (o.kind == CSE_OP_CONV3D && o.pool_k[0] > 0) {
-      const int32_t pd[4] = {o.pool_dims[0], o.pool_dims[1], o.pool_dims[2], o.out_dims[3]};
+      const int32_t pd[4] = {o.pool_dims[0], o.pool_dims[1], o.pool_dims[2],
+                             o.tc_pair_pool ? o.out_dims[3] / 2 : o.out_dims[3]};
       if ((rc = check_span(p, o.out0_off, tensor_span(nb, pd, o.out_ld), o.out_dtype, "pooled out0", false))) return rc;
       CSE_REQUIRE(o.engine == CSE_ENGINE_TCGEN05, "op %zu: fused pooling needs the tcgen05 engine", i);
     } else if ((rc = check_span(p, o.out0_off, tensor_span(nb, o.out_dims, o.out_ld, o.kind == CSE_OP_PREPROCESS ? o.out_wpitch : 0),
@@ -169,7 +170,10 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
       int dt = (o.kind == CSE_OP_CONV3D) ? o.out_dtype : o.in_dtype;
       if ((rc = check_span(p, o.in1_off, tensor_span(nb, d, o.in1_ld), dt, "in1", false))) return rc;
     }
-    const int co = o.out_dims[3];
+    const int co = (o.kind == CSE_OP_CONV3D && o.tc_pair_pool) ? o.out_dims[3] / 2 : o.out_dims[3];
+    if (o.kind == CSE_OP_CONV3D && o.tc_pair_pool)
+      CSE_REQUIRE(o.scale0_off < 0 && o.in1_off < 0 && o.out1_off < 0 && o.pool_k[0] == 1 && o.pool_k[1] == 2 && o.pool_k[2] == 1,
+                  "op %zu: pair-pool stem takes bias (+ReLU) only and pool (1,2,1) in the pair view", i);
     if ((rc = check_span(p, o.scale0_off, co, CSE_F32, "scale0", true))) return rc;
     if ((rc = check_span(p, o.shift0_off, co, CSE_F32, "shift0", true))) return rc;
     if ((rc = check_span(p, o.scale1_off, co, CSE_F32, "scale1", true))) return rc;
@@ -186,7 +190,7 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
         if ((rc = check_span(p, o.w_off, ktot * rows, CSE_BF16, "tc weights", true))) return rc;
         rc = conv_tc_build(&po.tc, p->ws + o.in0_off, p->wts + o.w_off, p->ws + o.out0_off,
                            o.out1_off >= 0 ? p->ws + o.out1_off : nullptr, o.out1_ld, nb, g, o.kc, o.bn, o.brick,
-                           o.tc_halo, o.pool_k, o.pool_dims, o.pool_zero);
+                           o.tc_halo, o.pool_k, o.pool_dims, o.pool_zero, o.tc_pair_pool);
         if (rc) return rc;
         po.has_tc = true;
       } else {

@@ -95,6 +95,7 @@ class DevOp:
     bn: int = 0
     brick: Tuple[int, int, int, int] = (0, 0, 0, 0)
     halo: int = 0
+    pair_pool: int = 0
     pool_k: Tuple[int, int, int] = (0, 0, 0)
     pool_zero: int = 0
     conv_out_dims: Optional[Tuple[int, int, int]] = None   # conv's own output dims when a pool is fused
@@ -144,7 +145,8 @@ class Plan:
                 s.in_wpitch = i0.wpitch
             else:
                 s.in0_off = -1
-            s.out_dims[:] = tuple(op.conv_out_dims or o0.dims) + (o0.C,)
+            s.out_dims[:] = tuple(op.conv_out_dims or o0.dims) + (o0.C * (2 if op.pair_pool else 1),)
+            s.tc_pair_pool = op.pair_pool
             s.out_ld, s.out_dtype, s.out0_off = o0.ld, o0.dtype, o0.byte_off()
             if op.pool_k[0] > 0:
                 s.pool_k[:] = op.pool_k
@@ -337,8 +339,9 @@ class Lowerer:
                  max_batch: int = 8, tc: bool = True, tc_strided: bool = True,
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
                  stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True,
-                 balance_n: bool = True):
+                 balance_n: bool = True, pair_pool: bool = True):
         self.keep_all = keep_all
+        self.pair_pool = pair_pool
         self.balance_n = balance_n
         self.s2d_stem = s2d_stem
         self.fuse_pool = fuse_pool and precision == "bf16" and tc
@@ -484,6 +487,16 @@ class Lowerer:
             # Either materialised by the pre-processing kernel ([.., W, 16]: 3 pixels x C channels
             # tightly packed, K = 16 per (fd,fh) tap) or read through an overlapping-stride TMA view of
             # the W-padded [.., W+4, 8] tensor (3 + 1 zero-weighted 8-channel pixels, K = 32 per tap).
+            if self.stem_unroll and self._pair_pool_ok(first, (t, h, w, c)):
+                # pair-packed stem: one element per pixel PAIR (2p, 2p+1) carrying pixels 2p-1..2p+2
+                b = self.new_buf(node.name, (t, h, w // 2), 16, self.act)
+                out = TRef(b, 0, c, 16, (t, h, w // 2), self.act, 0, 0, 4)
+                mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
+                scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
+                self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
+                                src_dims=(t, h, w, c), pre_mean=mean, pre_scale=scale, layers=(node.name,)))
+                self.val[node.name] = out
+                return
             if self.stem_unroll:
                 b = self.new_buf(node.name, (t, h, w), 16, self.act)
                 out = TRef(b, 0, c, 16, (t, h, w), self.act, 0, 0, 3)
@@ -637,6 +650,9 @@ class Lowerer:
         if x.s2d:
             self._s2d_stem_conv(node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops)
             return
+        if x.unroll_w == 4:
+            self._pair_pool_stem(node, x, kernel, bias, relu, final, layers, out_dims, flops)
+            return
         if x.wpitch or x.unroll_w or self._tc_ok(x, kernel.shape[-1], node.attrs["s"], self.act, None):
             fp = self._fusable_pool(final, out_dims)
             if fp is not None and final not in self.place:
@@ -692,6 +708,59 @@ class Lowerer:
             raise RuntimeError("packed stem must lower to the tcgen05 engine")
         for l in layers:
             self.val[l] = op.out0
+            self.done.add(l)
+
+    def _pair_pool_ok(self, conv: Node, in_shape) -> bool:
+        """C3D-style stem: Conv3D 3x3x3 'same' + bias (+ReLU) on a C<=4 clip whose only consumer is a
+        MaxPooling3D (1,2,2)/(1,2,2) 'valid' (train.py:1230-1233)."""
+        t, h, w, c = in_shape
+        if not (self.pair_pool and self.fuse_pool and self.stem_halo and 4 * c <= 16 and w % 2 == 0 and h % 2 == 0):
+            return False
+        if conv.attrs["filters"] != 64 or not conv.attrs["use_bias"] or conv.name in self.place:
+            return False
+        final = conv.name
+        if conv.attrs["activation"] not in (None, "relu", "linear"):
+            return False
+        if conv.attrs["activation"] != "relu":
+            nxt = self.sole_consumer(final, "relu")
+            if nxt is not None:
+                final = nxt.name
+        if final in self.place:
+            return False
+        mp = self.sole_consumer(final, "maxpool")
+        return (mp is not None and mp.attrs["padding"] == "valid" and tuple(mp.attrs["k"]) == (1, 2, 2)
+                and tuple(mp.attrs["s"]) == (1, 2, 2) and mp.name not in self.place)
+
+    def _pair_pool_stem(self, node, x, kernel, bias, relu, final, layers, out_dims, flops):
+        """C3D conv1 + pool1 (train.py:1230-1233) as ONE tcgen05 op on the pair-unrolled clip: GEMM row =
+        the pixel pair (2p, 2p+1), N = 2 x 64 output channels, K = 9 (kd,kh) taps x 16 (4 neighbouring
+        pixels x C channels); the 3 kw taps of the left pixel read neighbours 0..2, those of the right
+        pixel neighbours 1..3.  The (1,2,2) max-pool is done in registers by the epilogue."""
+        kd, kh, kw, ci, co = kernel.shape
+        assert (kd, kh, kw) == (3, 3, 3) and co == 64 and 4 * ci <= 16
+        mp = self.sole_consumer(final, "maxpool")
+        t, h, wp = x.dims
+        k2 = np.zeros((3, 3, 1, 16, 2 * co), np.float32)
+        for px in range(2):
+            for fw in range(3):
+                k2[:, :, 0, (px + fw) * ci:(px + fw + 1) * ci, px * co:(px + 1) * co] = kernel[:, :, fw, :, :]
+        pooled_dims = tuple(mp.out_shape[:3])
+        assert pooled_dims == (t, h // 2, wp)
+        out0 = self.out_ref(mp.name, pooled_dims, co, self.act)
+        if out0.ld % 8 or out0.coff % 8:
+            raise RuntimeError("pair-pool stem output must be 16-byte aligned")
+        view = TRef(x.buf, 0, 16, 16, x.dims, x.dtype)
+        op = DevOp(rt.OP_CONV3D, node.name, view, None, out0, k=(3, 3, 1), s=(1, 1, 1), pad=(1, 1, 0), relu0=int(relu),
+                   layers=tuple(layers) + (mp.name,), flops=flops)
+        op.engine, op.w_dtype, op.kc, op.bn, op.halo, op.pair_pool = rt.ENGINE_TCGEN05, rt.BF16, 16, 2 * co, 1, 1
+        op.pool_k, op.pool_zero, op.conv_out_dims = (1, 2, 1), 0, (t, h, wp)
+        bricks = [(1, 1, 128 // bw, bw) for bw in (8, 16)]
+        op.brick = min(bricks, key=lambda b: (-(-h // b[2]) * -(-wp // b[3]), b[3]))
+        op.w_blob = self.blob(pack_tc_weights_halo(k2, 16, 2 * co, 1))
+        op.shift0 = self.fblob(bias.astype(np.float32))
+        self.emit(op)
+        for l in op.layers:
+            self.val[l] = out0
             self.done.add(l)
 
     def _s2d_stem_conv(self, node, x, kernel, bias, chain_bn, relu, final, layers, out_dims, flops):

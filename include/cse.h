@@ -84,13 +84,18 @@ typedef struct cse_op {
   int32_t out_wpitch;        /* PREPROCESS: output row pitch in pixels (0 = W); pad columns are written as zeros */
   int32_t out_wpad;          /* PREPROCESS: zero columns on the left of every output row */
   int32_t pre_unroll_w;      /* PREPROCESS: 3 = every output pixel carries its neighbours w-1,w,w+1 (zero outside
-                                the row), C channels each, packed j*C+c and zero-padded to out_ld = 16 (packed stem) */
+                                the row), C channels each, packed j*C+c and zero-padded to out_ld = 16 (packed stem);
+                                4 = every output element is a pixel PAIR p carrying pixels 2p-1 .. 2p+2 (out W = W/2) */
   int32_t pool_k[3];         /* TCGEN05: fused MaxPooling3D window (= stride, 'valid'); 0 = none.  out0 is then the
                                 pooled tensor [n, pool_dims, Cout]; out_dims stay the conv's own output dims */
   int32_t pool_dims[3];      /* D,H,W of the pooled output */
   int32_t pool_zero;         /* 1 = positions beyond the conv output count as 0 (ZeroPadding3D in front of the pool) */
   int32_t tc_halo;           /* TCGEN05: 1 = (kd,kh)-halo'd A brick, weights packed [n_tile][tap][bn][kc] (packed stem);
                                 2 = kh-halo'd A brick, one stage per (fd, chunk), weights [n_tile][fd][chunk][fh][bn][kc] */
+  int32_t tc_pair_pool;      /* TCGEN05 pair-packed stem (C3D conv1 + pool1, train.py:1230-1233): in0 = pair-unrolled clip
+                                [n,T,H,W/2,16], GEMM row = 2 neighbouring output pixels, out_dims = D,H,W/2,2*Cout, weights
+                                [2*Cout][taps*16]; MaxPooling3D (1,2,2) is done in registers, pool_k = (1,2,1) in this
+                                view, out0 = pooled [n, pool_dims, Cout]; bias (+ReLU) epilogue only */
   int32_t pre_s2d;           /* PREPROCESS: 1 = 2x2 space-to-depth over (H,W) for the stride-2 7x7x7 stems: out_dims =
                                 T, ceil(H/2), ceil(W/2); cell channel (ph*2+pw)*C + c, zero-padded to out_ld = 8/16 */
   int64_t in0_off, in1_off;  /* workspace byte offsets (-1 = none); in1 = residual for CONV3D, 2nd addend for ADD */

@@ -204,6 +204,55 @@ def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb, halo):
     assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
 
 
+PAIR_POOL = [((4, 16, 16), 3, True), ((3, 12, 40), 3, True), ((5, 8, 24), 2, False), ((2, 34, 18), 3, True),
+             ((3, 16, 112), 4, True)]
+
+
+@pytest.mark.parametrize("dhw,c,relu", PAIR_POOL)
+def test_conv_tcgen05_pair_pool_stem(dhw, c, relu):
+    """C3D conv1 + pool1 (train.py:1230-1233) as one op: pair-unrolled clip, GEMM row = 2 output pixels
+    (N = 128), MaxPooling3D (1,2,2) in registers (max over the pair's column halves, shuffle with the
+    row partner).  Ragged tiles in H and W, C = 2/3/4, with and without ReLU (signed outputs)."""
+    def build(g):
+        x = g.input(dhw + (c,), name="in")
+        x = g.conv3d(x, 64, (3, 3, 3), (1, 1, 1), "same", True, "relu" if relu else None, name="c")
+        g.maxpool(x, (1, 2, 2), (1, 2, 2), "valid", name="p")
+    g, w, m = make_member(build, "bf16", 3, scale=[1 / 64.0] * c, mean=[128.0] * c)
+    assert len(m.plan.ops) == 2
+    op = m.plan.ops[1]
+    assert op.engine == rt.ENGINE_TCGEN05 and op.pair_pool == 1 and op.bn == 128 and op.halo == 1
+    xs = clips(21, 3, dhw + (c,))
+    run(m, [xs])
+    xin = torch.as_tensor((xs.astype(np.float64) - 128.0) / 64.0, dtype=T64)      # exact in bf16
+    kern, bias = w["c"]
+    y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (1, 1, 1), "same")
+    if relu:
+        y = O.relu(y)
+    exp = O.maxpool3d(bf16_round(y.numpy()), (1, 2, 2), (1, 2, 2), "valid").numpy()
+    got = m.read_tensor(m.plan.tensors["p"], 3)
+    assert got.shape == exp.shape
+    err = np.abs(got - exp).max() / np.abs(exp).max()
+    assert err <= 2.0 ** -7, "rel err %g brick=%s" % (err, op.brick)
+
+
+def test_pair_pool_stem_falls_back_on_odd_width():
+    def build(g):
+        x = g.input((4, 10, 15, 3), name="in")
+        x = g.conv3d(x, 64, (3, 3, 3), (1, 1, 1), "same", True, "relu", name="c")
+        g.maxpool(x, (1, 2, 2), (1, 2, 2), "valid", name="p")
+    g, w, m = make_member(build, "bf16", 2, scale=[1 / 64.0] * 3, mean=[128.0] * 3)
+    op = [o for o in m.plan.ops if o.name == "c"][0]
+    assert op.pair_pool == 0 and op.engine == rt.ENGINE_TCGEN05
+    xs = clips(22, 2, (4, 10, 15, 3))
+    run(m, [xs])
+    xin = torch.as_tensor((xs.astype(np.float64) - 128.0) / 64.0, dtype=T64)
+    kern, bias = w["c"]
+    y = O.relu(O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (1, 1, 1), "same"))
+    exp = O.maxpool3d(bf16_round(y.numpy()), (1, 2, 2), (1, 2, 2), "valid").numpy()
+    got = m.read_tensor(m.plan.tensors["p"], 2)
+    assert np.abs(got - exp).max() / np.abs(exp).max() <= 2.0 ** -7
+
+
 POOL_FUSED = [  # (in dhw, cin, cout, pool k, zeropad, nb)
     ((4, 8, 8), 64, 128, (2, 2, 2), False, 2),
     ((4, 16, 16), 64, 64, (1, 2, 2), False, 2),
