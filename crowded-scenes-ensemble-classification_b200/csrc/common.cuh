@@ -83,6 +83,10 @@ struct ConvTcDesc {            // built once at plan finalize
   uint32_t slot_bytes;
   bool has_out1;
   int pair_pool;               // pair-packed stem with the (1,2,2) max-pool done in registers
+  int twin_ok;                 // twin-tile layout available (two M tiles share every B stage)
+  uint32_t tw_stage_bytes, tw_stage_region;
+  int tw_stages, tw_nslots;
+  size_t tw_smem_bytes;
   int halo;                    // (kd,kh)-halo'd A brick: one pipeline stage per tile
   int b_resident;              // halo + single N tile: weights stay in smem for the CTA's lifetime
   int pool[3], pool_dims[3], pool_zero;   // fused MaxPooling3D (window == stride) and its output dims

@@ -20,6 +20,8 @@
 // Replaces the cuDNN FP32 Conv3D the reference reaches through Keras/TF
 // (train.py:653-658, 1230-1258, 1294-1298 ...), with the fused bias / BatchNormalization /
 // ReLU / residual-add / second BN-ReLU output / channel-offset (concat) write epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cse {
@@ -172,6 +174,7 @@ struct ConvTcArgs {
   uint32_t slot_bytes;             // bytes of one staging slot (full tile [+ out1 tile] [+ pooled tile])
   int pool_d, pool_h, pool_w;      // fused MaxPooling3D window (= stride); 0 = no pooling
   int pool_zero;                   // rows outside the conv output count as 0 (ZeroPadding3D before the pool)
+  int twin;                        // twin-tile mode: two M tiles share every B stage (4 TMEM accumulators of bn <= 128 columns)
   int pair_pool;                   // pair-packed stem: GEMM row = 2 output pixels (N = 2*Cout), (1,2,2) max-pool in registers
   int step1[5], step2[5];          // gridDim.x and 2*gridDim.x as mixed-radix digits (nt, tw, th, td, tn)
   Epilogue ep;
@@ -262,8 +265,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr uint32_t STG_BYTES = TC_BM * EC * 2;       // one staged [128][EC] bf16 tile
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // barriers: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty  (byte offsets 0/64/128/144)
-  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 5];   // [20] = resident-B full barrier (byte 160)
+  // barriers: [0,8) full, [8,16) empty, [16,20) tmem_full, [20,24) tmem_empty  (byte offsets 0/64/128/160)
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 9];   // tmem_full x4 (byte 128), tmem_empty x4 (160), resident-B full (192)
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_par[2][4][256];                   // per epilogue group: scale0, shift0, scale1, shift1
 
@@ -281,11 +284,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(bar_base + 8u * s, 1);
       mbar_init(bar_base + 64u + 8u * s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(bar_base + 128u + 8u * b, 1);
-      mbar_init(bar_base + 144u + 8u * b, 128);
+      mbar_init(bar_base + 160u + 8u * b, 128);
     }
-    mbar_init(bar_base + 160u, 1);
+    mbar_init(bar_base + 192u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -316,14 +319,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t phase = 0;
     if (a.b_resident) {
       // the whole (single N tile) weight matrix stays in shared memory for the CTA's lifetime
-      const uint32_t bb = bar_base + 160u;
+      const uint32_t bb = bar_base + 192u;
       mbar_expect_tx_p(leader, bb, a.b_bytes);
       const uint32_t b_tap = (uint32_t)a.bn * ROW_BYTES;        // resident B: one box per (fd,fh) tap
       for (int t = 0; t < a.kd * a.kh; ++t)
         tma_load_2d(leader, smem_base + a.b_region + t * b_tap, &tmap_b, bb, 0, t * a.bn);
     }
+    if (a.twin) {
+      // twin-tile mode (single N tile): the CTA's tiles 2j and 2j+1 run in lock-step; every stage
+      // holds both A tiles and ONE B tile, which halves the weight traffic per MMA
+      TileIter t0, t1;
+      t0.init(a, blockIdx.x);
+      t1.init(a, blockIdx.x + gridDim.x);
+      for (; t0.tile < a.num_tiles; t0.advance(a, a.step2, 2 * gridDim.x), t1.advance(a, a.step2, 2 * gridDim.x)) {
+        const bool two = t1.tile < a.num_tiles;
+        const int iw0 = t0.tw * a.b_w * a.sw - a.pw, ih0 = t0.th * a.b_h * a.sh - a.ph, id0 = t0.td * a.b_d * a.sd - a.pd;
+        const int iw1 = t1.tw * a.b_w * a.sw - a.pw, ih1 = t1.th * a.b_h * a.sh - a.ph, id1 = t1.td * a.b_d * a.sd - a.pd;
+        const int n0 = t0.tn * a.b_n, n1 = t1.tn * a.b_n;
+        int kcoord = 0;
+        for (int fd = 0; fd < a.kd; ++fd)
+          for (int fh = 0; fh < a.kh; ++fh)
+            for (int fw = 0; fw < a.kw; ++fw)
+              for (int ch = 0; ch < a.kchunks; ++ch, kcoord += KC) {
+                mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);
+                const uint32_t fb = bar_base + 8u * stage;
+                mbar_expect_tx_p(leader, fb, (two ? 2u : 1u) * a.a_bytes + a.b_bytes);
+                const uint32_t sa = smem_base + stage * stage_bytes;
+                tma_load_5d(leader, sa, &tmap_a, fb, ch * KC, iw0 + fw, ih0 + fh, id0 + fd, n0);
+                if (two) tma_load_5d(leader, sa + A_STAGE, &tmap_a, fb, ch * KC, iw1 + fw, ih1 + fh, id1 + fd, n1);
+                tma_load_2d(leader, sa + 2u * A_STAGE, &tmap_b, fb, kcoord, 0);
+                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+              }
+      }
+    }
     TileIter ti;
-    for (ti.init(a, blockIdx.x); ti.tile < a.num_tiles; ti.advance(a, a.step1, gridDim.x)) {
+    for (ti.init(a, a.twin ? a.num_tiles : blockIdx.x); ti.tile < a.num_tiles; ti.advance(a, a.step1, gridDim.x)) {
       const int nt = ti.nt;
       const int iw0 = ti.tw * a.b_w * a.sw - a.pw;
       const int ih0 = ti.th * a.b_h * a.sh - a.ph;
@@ -388,12 +418,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     int buf = 0;
     if (a.b_resident) {
-      mbar_wait(bar_base + 160u, 0u);
+      mbar_wait(bar_base + 192u, 0u);
       tc_fence_after();
     }
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    if (a.twin) {
+      uint32_t eph[2] = {0u, 0u};                 // tmem_empty phase per buffer pair
+      int pp = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += 2 * gridDim.x) {
+        const bool two = tile + (int)gridDim.x < a.num_tiles;
+        const uint32_t b0 = (uint32_t)(pp * 2), b1 = b0 + 1u;
+        const uint32_t ep_ = pp ? eph[1] : eph[0];
+        mbar_wait(bar_base + 160u + 8u * b0, ep_ ^ 1u);
+        mbar_wait(bar_base + 160u + 8u * b1, ep_ ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = b0 * 128u, d1 = b1 * 128u;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(bar_base + 8u * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+          const uint64_t ad1 = desc_hi | (uint64_t)(((sa + A_STAGE) >> 4) & 0x3FFF);
+          const uint64_t bd = desc_hi | (uint64_t)(((sa + 2u * A_STAGE) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)
+            tc_mma_bf16(leader, d0, ad0 + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          if (two) {
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k)
+              tc_mma_bf16(leader, d1, ad1 + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(leader, bar_base + 64u + 8u * stage);
+          if (ks == ksteps - 1) {
+            tc_commit(leader, bar_base + 128u + 8u * b0);
+            if (two) tc_commit(leader, bar_base + 128u + 8u * b1);
+          }
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (pp) eph[1] ^= 1u; else eph[0] ^= 1u;
+        pp ^= 1;
+      }
+    }
+    for (int tile = a.twin ? a.num_tiles : blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const uint32_t aph = buf ? acc_phase1 : acc_phase0;
-      mbar_wait(bar_base + 128u + 16u + 8u * buf, aph ^ 1u);             // tmem_empty[buf]
+      mbar_wait(bar_base + 160u + 8u * buf, aph ^ 1u);                   // tmem_empty[buf]
       tc_fence_after();
       const uint32_t d_tmem = (uint32_t)buf * 256u;                       // TMEM base is 0 (asserted)
       if (a.halo == 2) {
@@ -528,12 +595,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       pre(0, pv_r2_0, pv_cd_0); pre(1, pv_r2_1, pv_cd_1); pre(2, pv_r2_2, pv_cd_2); pre(3, pv_r2_3, pv_cd_3);
     }
     const uint32_t bar_id = 1u + (uint32_t)grp;
-    const int buf = grp;
-    uint32_t acc_phase = 0u;
+    // normal mode: group g owns accumulator g (256 columns each).  twin mode: four 128-column
+    // accumulators; group g drains tile g of every tile pair, alternating between buffer g and 2+g.
+    uint32_t acc_phases[2] = {0u, 0u};
+    int pair_parity = 0;
     int slot = 0;
     int last_nt = -1;
     TileIter ti;
     for (ti.init(a, blockIdx.x + grp * gridDim.x); ti.tile < a.num_tiles; ti.advance(a, a.step2, 2 * gridDim.x)) {
+      const int buf = a.twin ? (pair_parity * 2 + grp) : grp;
+      const uint32_t acc_phase = pair_parity ? acc_phases[1] : acc_phases[0];
+      const uint32_t buf_col = a.twin ? (uint32_t)buf * 128u : (uint32_t)buf * 256u;
+      if (pair_parity) acc_phases[1] ^= 1u; else acc_phases[0] ^= 1u;
+      if (a.twin) pair_parity ^= 1;
       const int nt = ti.nt;
       const int ow0 = ti.tw * a.b_w, oh0 = ti.th * a.b_h, od0 = ti.td * a.b_d, on0 = ti.tn * a.b_n;
       const int col_base = nt * a.bn;
@@ -561,7 +635,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
       mbar_wait(bar_base + 128u + 8u * buf, acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 256u;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + buf_col;
       if (EC == 64 && a.pair_pool) {
         // Pair-packed stem + MaxPooling3D (1,2,2): row = (h, pixel pair), columns [0,64) = left pixel,
         // [64,128) = right pixel.  max over the pair in registers, + bias, (ReLU) -> bf16, max with the
@@ -587,7 +661,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_wait_ld();
           if (q == 3) {
             tc_fence_before();
-            mbar_arrive(bar_base + 144u + 8u * buf);
+            mbar_arrive(bar_base + 160u + 8u * buf);
           }
           uint32_t pk[8];
 #pragma unroll
@@ -621,7 +695,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (++slot == a.nslots) slot = 0;
-        acc_phase ^= 1u;
         continue;
       }
       for (int c0 = 0; c0 < a.bn; c0 += EC) {
@@ -642,7 +715,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp
           // before the math / staging / store of this last chunk
           tc_fence_before();
-          mbar_arrive(bar_base + 144u + 8u * buf);
+          mbar_arrive(bar_base + 160u + 8u * buf);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         const uint32_t s0 = my_stg + (uint32_t)slot * slot_bytes + (uint32_t)row * (EC * 2);
@@ -795,7 +868,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if (++slot == a.nslots) slot = 0;
       }
-      acc_phase ^= 1u;
     }
     if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -1005,43 +1077,65 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   // keeps >= 4 stages (3 for the widest tiles); a TMA store only releases its slot once it has
   // read it, so more slots = more stores in flight
   d->slot_bytes = (uint32_t)slot;
-  const int want_stages = (stage >= 48 * 1024) ? 3 : 4;
+  auto layout = [&](size_t stage_sz, int* out_stages, int* out_nslots, size_t* out_staging) -> bool {
+    const int want_stages = (stage_sz >= 48 * 1024) ? 3 : 4;
+    int stages = 0, nslots = 0;
+    size_t staging = 0;
+    for (int ns = 4; ns >= 1; --ns) {
+      staging = slot * ns * 2;
+      if (staging + resident + 2 * stage_sz > 214 * 1024) continue;
+      stages = (int)((214 * 1024 - staging - resident) / stage_sz);
+      nslots = ns;
+      if (stages >= want_stages) break;
+    }
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    *out_stages = stages; *out_nslots = nslots; *out_staging = staging;
+    return stages >= 2;
+  };
   int stages = 0;
   size_t staging = 0;
-  for (int ns = 4; ns >= 1; --ns) {
-    staging = slot * ns * 2;
-    if (staging + resident + 2 * stage > 214 * 1024) continue;
-    stages = (int)((214 * 1024 - staging - resident) / stage);
-    d->nslots = ns;
-    if (stages >= want_stages) break;
-  }
-  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  CSE_REQUIRE(stages >= 2, "conv_tc: tile too large for shared memory");
+  CSE_REQUIRE(layout(stage, &stages, &d->nslots, &staging), "conv_tc: tile too large for shared memory");
   d->stages = stages;
   d->b_region = (uint32_t)(stage * stages);
   d->stage_region = (uint32_t)(stage * stages + resident);
+  // twin-tile layout (two A tiles + one B tile per stage): usable when there is a single N tile of
+  // <= 128 columns (four accumulators fit in TMEM) on the generic (non-halo) path
+  d->twin_ok = 0;
+  if (halo == 0 && !pair_pool && d->n_tiles_n == 1 && bn <= 128) {
+    const size_t tstage = 2 * a_stage + b_stage;
+    int tst = 0, tns = 0;
+    size_t tstaging = 0;
+    if (layout(tstage, &tst, &tns, &tstaging) && tst >= 3) {
+      d->twin_ok = 1;
+      d->tw_stage_bytes = (uint32_t)tstage;
+      d->tw_stages = tst;
+      d->tw_nslots = tns;
+      d->tw_stage_region = (uint32_t)(tstage * tst);
+      d->tw_smem_bytes = tstage * tst + tstaging + 1024;
+    }
+  }
   d->smem_bytes = stage * stages + resident + staging + 1024;   // + alignment slack
   return CSE_OK;
 }
 
 template <int KC, int EC>
-static int launch_tc_t(const ConvTcDesc& d, const ConvTcArgs& args, int grid, cudaStream_t st) {
+static int launch_tc_t(const ConvTcDesc& d, const ConvTcArgs& args, int grid, size_t smem_bytes, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     CSE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<KC, EC><<<grid, TC_THREADS, d.smem_bytes, st>>>(d.tmap_a, d.tmap_b, d.tmap_o0, d.tmap_o1, args);
+  conv_tc_kernel<KC, EC><<<grid, TC_THREADS, smem_bytes, st>>>(d.tmap_a, d.tmap_b, d.tmap_o0, d.tmap_o1, args);
   CSE_CUDA(cudaGetLastError());
   return CSE_OK;
 }
 
 template <int KC>
-static int launch_tc_kc(const ConvTcDesc& d, const ConvTcArgs& a, int grid, cudaStream_t st) {
+static int launch_tc_kc(const ConvTcDesc& d, const ConvTcArgs& a, int grid, size_t smem_bytes, cudaStream_t st) {
   switch (d.ec) {
-    case 64: return launch_tc_t<KC, 64>(d, a, grid, st);
-    case 32: return launch_tc_t<KC, 32>(d, a, grid, st);
-    default: return launch_tc_t<KC, 16>(d, a, grid, st);
+    case 64: return launch_tc_t<KC, 64>(d, a, grid, smem_bytes, st);
+    case 32: return launch_tc_t<KC, 32>(d, a, grid, smem_bytes, st);
+    default: return launch_tc_t<KC, 16>(d, a, grid, smem_bytes, st);
   }
 }
 
@@ -1071,6 +1165,18 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   a.nslots = d.nslots; a.slot_bytes = d.slot_bytes;
   a.ep = ep;
   int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
+  size_t smem_bytes = d.smem_bytes;
+  a.twin = 0;
+  int twin_min = 2 * sm_count;
+  if (const char* e = getenv("CSE_TWIN_MIN_TILES")) twin_min = atoi(e);      // tests force the twin path on small shapes
+  if (d.twin_ok && twin_min > 0 && a.num_tiles >= twin_min) {
+    // enough tiles to keep every SM busy with tile pairs
+    a.twin = 1;
+    a.stages = d.tw_stages; a.stage_bytes = d.tw_stage_bytes; a.stage_region = d.tw_stage_region; a.nslots = d.tw_nslots;
+    smem_bytes = d.tw_smem_bytes;
+    const int pairs = (a.num_tiles + 1) / 2;
+    grid = pairs < sm_count ? pairs : sm_count;
+  }
   {
     const int radix[4] = {a.n_tiles_n, a.tiles_w, a.tiles_h, a.tiles_d};
     for (int which = 0; which < 2; ++which) {
@@ -1081,9 +1187,9 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
     }
   }
   switch (d.kc) {
-    case 64: return launch_tc_kc<64>(d, a, grid, st);
-    case 32: return launch_tc_kc<32>(d, a, grid, st);
-    default: return launch_tc_kc<16>(d, a, grid, st);
+    case 64: return launch_tc_kc<64>(d, a, grid, smem_bytes, st);
+    case 32: return launch_tc_kc<32>(d, a, grid, smem_bytes, st);
+    default: return launch_tc_kc<16>(d, a, grid, smem_bytes, st);
   }
 }
 

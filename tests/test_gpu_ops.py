@@ -150,6 +150,53 @@ def test_conv_tcgen05_vs_oracle(dhw, cin, cout, k, nb):
     assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
 
 
+TWIN_CASES = [((4, 8, 8), 64, 128, (3, 3, 3), 2), ((5, 9, 9), 192, 64, (1, 1, 1), 2), ((3, 6, 6), 16, 48, (3, 3, 3), 3),
+              ((4, 14, 14), 32, 96, (3, 3, 3), 1), ((2, 5, 5), 480, 24, (1, 1, 1), 3)]
+
+
+@pytest.mark.parametrize("dhw,cin,cout,k,nb", TWIN_CASES)
+def test_conv_tcgen05_twin_tiles(dhw, cin, cout, k, nb, monkeypatch):
+    """Twin-tile mode (two M tiles share every weight stage, four TMEM accumulators), forced on small
+    shapes so that even and odd tile counts, several tiles per CTA and the residual / second-output
+    epilogue all run through it."""
+    monkeypatch.setenv("CSE_TWIN_MIN_TILES", "2")
+
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, cin, (1, 1, 1), (1, 1, 1), "same", True, "relu", name="pre")
+        x = g.conv3d(x, cout, k, (1, 1, 1), "same", True, None, name="c")
+        x = g.bn(x, scale=True, name="b")
+        g.relu(x, name="r")
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * 3, mean=[128.0] * 3)
+    op = [o for o in m.plan.ops if o.name == "c"][0]
+    assert op.engine == rt.ENGINE_TCGEN05 and op.bn <= 128
+    xs = clips(4, nb, dhw + (3,))
+    run(m, [xs])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], nb), dtype=T64)
+    kern, bias = w["c"]
+    y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (1, 1, 1), "same")
+    y = O.relu(O.batchnorm(y, *[torch.as_tensor(a, dtype=T64) for a in w["b"]]))
+    got = m.read_tensor(m.plan.tensors["r"], nb)
+    err = np.abs(got - y.numpy()).max() / max(np.abs(y.numpy()).max(), 1e-6)
+    assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
+
+
+def test_twin_tiles_whole_r3d_matches_default(monkeypatch):
+    """R3D_18 (residual + second-output epilogues, strided convs) with the twin path forced everywhere
+    it is legal gives bit-identical logits to the default tiling: same products, same per-tile
+    accumulation order."""
+    shape = (16, 64, 64, 3)
+    g = G.build_model_graph("R3D_18", shape, 11)
+    w = synthetic_weights(g, seed=5, nontrivial=True)
+    x = torch.from_numpy(clips(30, 3, shape)).cuda()
+    monkeypatch.setenv("CSE_TWIN_MIN_TILES", "0")
+    base, _ = Member(g, w, precision="bf16", max_batch=3).forward_device([x])
+    base = base.cpu().numpy()
+    monkeypatch.setenv("CSE_TWIN_MIN_TILES", "2")
+    twin, _ = Member(g, w, precision="bf16", max_batch=3).forward_device([x])
+    assert np.array_equal(base, twin.cpu().numpy())
+
+
 @pytest.mark.parametrize("unroll", [True, False])
 @pytest.mark.parametrize("dhw,c,cout,nb", [((4, 16, 16), 3, 64, 2), ((3, 9, 13), 3, 24, 3), ((5, 8, 8), 2, 64, 2)])
 def test_conv_tcgen05_packed_stem(dhw, c, cout, nb, unroll):
