@@ -268,8 +268,19 @@ int cse_plan_run_range(cse_plan* p, const uint8_t* d_rgb_u8, const uint8_t* d_fl
 
 int cse_plan_run(cse_plan* p, const uint8_t* d_rgb_u8, const uint8_t* d_flow_u8, int n, float* d_logits,
                  float* d_probs, void* stream) {
+  return cse_plan_run_from(p, d_rgb_u8, d_flow_u8, n, 0, d_logits, d_probs, stream);
+}
+
+int cse_plan_num_input_ops(const cse_plan* p) {
+  int k = 0;
+  if (p) while (k < (int)p->ops.size() && p->ops[k].op.kind == CSE_OP_PREPROCESS) ++k;
+  return k;
+}
+
+int cse_plan_run_from(cse_plan* p, const uint8_t* d_rgb_u8, const uint8_t* d_flow_u8, int n, int first_op,
+                      float* d_logits, float* d_probs, void* stream) {
   CSE_REQUIRE(p != nullptr, "plan_run: NULL plan");
-  int rc = cse_plan_run_range(p, d_rgb_u8, d_flow_u8, n, 0, (int)p->ops.size(), stream);
+  int rc = cse_plan_run_range(p, d_rgb_u8, d_flow_u8, n, first_op, (int)p->ops.size(), stream);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = (size_t)n * p->nb_classes * sizeof(float);

@@ -29,6 +29,11 @@ class DeviceEnsemble:
         self.micro_batch = int(micro_batch) if micro_batch else min(self.max_batch, 128)
         self.members: List[Member] = []
         shared = None
+        # all members share one workspace and one lowering, hence the offset of the pre-processed
+        # clip tensor: it is written once per micro-batch by the first member and kept alive
+        self.share_input = bool(lower_kw.pop("share_input", True)) and len(weight_sets) > 1
+        if self.share_input:
+            lower_kw = dict(lower_kw, persist_input=True)
         for w in weight_sets:
             m = Member(graph, w, precision=precision, max_batch=self.micro_batch, device=device,
                        workspace=shared, **lower_kw)
@@ -63,7 +68,8 @@ class DeviceEnsemble:
         for i in range(0, n, mb):
             chunk = [x[i:i + mb] for x in inputs_u8]
             for j, m in enumerate(self.members):
-                m.forward_device(chunk, self.logits[j, i:i + mb], self.probs[j, i:i + mb])
+                m.forward_device(chunk, self.logits[j, i:i + mb], self.probs[j, i:i + mb],
+                                 skip_input_ops=self.share_input and j > 0)
                 launches += m.launches              # kernels only (the two D2D copies of logits / probs are memcpys)
         self.last_launches = launches
         return n
@@ -95,12 +101,17 @@ class DeviceEnsemble:
         mb = self.micro_batch
         plan = self.members[0].plan
         acc = [0.0] * len(plan.ops)
+        n_input_ops = 0
+        while n_input_ops < len(plan.ops) and plan.ops[n_input_ops].kind == rt.OP_PREPROCESS:
+            n_input_ops += 1
         for it in range(iters + 1):
             evs = []
             for i in range(0, n, mb):
                 chunk = [x[i:i + mb] for x in inputs_u8]
-                for m in self.members:
+                for j, m in enumerate(self.members):
                     for k in range(len(plan.ops)):
+                        if self.share_input and j > 0 and k < n_input_ops:
+                            continue            # pre-processed clips are shared with member 0
                         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         a.record(stream)
                         m.run_ops(chunk, k, k + 1)
@@ -176,6 +187,50 @@ class HeteroEnsemble:
     def predict_host(self, host_group_inputs):
         dev = [[h.to(self.device, non_blocking=True) for h in inputs] for inputs in host_group_inputs]
         return self.predict_device(dev).cpu().numpy()
+
+    def stream_host(self, batches):
+        """Pipelined host path: `batches` yields pinned uint8 host inputs (group_inputs layout); the
+        H2D copy of batch i+1 runs on a copy stream while batch i computes (two device buffer sets).
+        Yields the int32 prediction tensor (device) of every batch, in order; the caller reads it back."""
+        torch = self.torch
+        comp = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._dev_bufs = [None, None]
+        copy = self._copy_stream
+        ready = [None, None]
+        free = [None, None]
+
+        def upload(k, batch):
+            if self._dev_bufs[k] is None or any(d.shape != h.shape for ds, hs in zip(self._dev_bufs[k], batch)
+                                                for d, h in zip(ds, hs)):
+                self._dev_bufs[k] = [[torch.empty(h.shape, dtype=torch.uint8, device=self.device) for h in hs]
+                                     for hs in batch]
+            with torch.cuda.stream(copy):
+                if free[k] is not None:
+                    copy.wait_event(free[k])         # the compute that read this buffer set has finished
+                for ds, hs in zip(self._dev_bufs[k], batch):
+                    for d, h in zip(ds, hs):
+                        d.copy_(h, non_blocking=True)
+                ready[k] = torch.cuda.Event()
+                ready[k].record(copy)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        k = 0
+        if nxt is not None:
+            upload(0, nxt)
+        while nxt is not None:
+            cur_k = k
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(cur_k ^ 1, nxt)
+            comp.wait_event(ready[cur_k])
+            pred = self.predict_device(self._dev_bufs[cur_k])
+            free[cur_k] = torch.cuda.Event()
+            free[cur_k].record(comp)
+            yield pred
+            k ^= 1
 
     def profile_ops(self, group_inputs, iters: int = 2):
         out = []

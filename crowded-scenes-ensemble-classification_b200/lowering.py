@@ -339,8 +339,9 @@ class Lowerer:
                  max_batch: int = 8, tc: bool = True, tc_strided: bool = True,
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
                  stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True,
-                 balance_n: bool = True, pair_pool: bool = True):
+                 balance_n: bool = True, pair_pool: bool = True, persist_input: bool = False):
         self.keep_all = keep_all
+        self.persist_input = persist_input
         self.pair_pool = pair_pool
         self.balance_n = balance_n
         self.s2d_stem = s2d_stem
@@ -433,6 +434,11 @@ class Lowerer:
         for r in (logits, probs):
             if r is not None:
                 r.buf.last = len(self.ops) + 1
+        if self.persist_input:      # pre-processed clips stay valid for the next member of the ensemble
+            for op in self.ops:
+                if op.kind == rt.OP_PREPROCESS:
+                    op.out0.buf.last = len(self.ops) + 1
+                    op.out0.buf.first = 0
         if self.keep_all:           # tests: every intermediate stays readable after the run
             for b in self.bufs:
                 if b.last >= 0:

@@ -79,7 +79,7 @@ class Member:
         return self.graph.total_flops()
 
     # ---- device-level forward ------------------------------------------------ #
-    def forward_device(self, inputs_u8, logits_out=None, probs_out=None):
+    def forward_device(self, inputs_u8, logits_out=None, probs_out=None, skip_input_ops: bool = False):
         """inputs_u8: list of uint8 CUDA tensors [n,T,H,W,C] (rgb[, flow]); runs on the current
         stream; returns (logits, probs) fp32 CUDA tensors [n, nb_classes]."""
         torch = self.torch
@@ -101,8 +101,11 @@ class Member:
         if probs_out is None:
             probs_out = torch.empty((n, self.nb_classes), dtype=torch.float32, device=self.device)
         flow_ptr = inputs_u8[1].data_ptr() if len(inputs_u8) > 1 else None
-        rt.check(self.lib.cse_plan_run(self.handle, inputs_u8[0].data_ptr(), flow_ptr, n,
-                                       logits_out.data_ptr(), probs_out.data_ptr(), rt.current_stream_ptr()))
+        # skip_input_ops: the pre-processed clips of this batch are already in the (shared) workspace,
+        # written by another member of the same architecture (DeviceEnsemble)
+        first = self.lib.cse_plan_num_input_ops(self.handle) if skip_input_ops else 0
+        rt.check(self.lib.cse_plan_run_from(self.handle, inputs_u8[0].data_ptr(), flow_ptr, n, first,
+                                            logits_out.data_ptr(), probs_out.data_ptr(), rt.current_stream_ptr()))
         self.launches = self.lib.cse_plan_last_launches(self.handle)
         return logits_out, probs_out
 

@@ -19,7 +19,8 @@ OP_PREPROCESS, OP_CONV3D, OP_MAXPOOL3D, OP_AVGPOOL3D, OP_AFFINE, OP_ADD, OP_SOFT
 OP_NAMES = {1: "preprocess", 2: "conv3d", 3: "maxpool3d", 4: "avgpool3d", 5: "affine", 6: "add", 7: "softmax"}
 
 EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_plan_create", "cse_plan_add_op",
-           "cse_plan_finalize", "cse_plan_run", "cse_plan_run_range", "cse_plan_num_ops",
+           "cse_plan_finalize", "cse_plan_run", "cse_plan_run_from", "cse_plan_num_input_ops", "cse_plan_run_range",
+           "cse_plan_num_ops",
            "cse_plan_last_launches", "cse_plan_destroy", "cse_preprocess", "cse_vote", "cse_vote_search"]
 
 
@@ -68,6 +69,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cse_plan_finalize.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i64, i64]
     lib.cse_plan_run.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.cse_plan_run_range.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.cse_plan_run_from.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    lib.cse_plan_num_input_ops.argtypes = [vp]
     lib.cse_plan_num_ops.argtypes = [vp]
     lib.cse_plan_last_launches.argtypes = [vp]
     lib.cse_plan_destroy.argtypes = [vp]

@@ -126,6 +126,13 @@ int  cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes,
  * NULL for single-stream members).  d_logits / d_probs: fp32 [n, nb_classes] (either may be NULL). */
 int  cse_plan_run(cse_plan* p, const uint8_t* d_rgb_u8, const uint8_t* d_flow_u8, int n,
                   float* d_logits, float* d_probs, void* stream);
+/* Same, starting at op `first_op`.  Members of one fold ensemble share the architecture, the
+ * workspace and therefore the pre-processed clip tensor(s): the first member runs the whole plan,
+ * the others start after the cse_plan_num_input_ops() leading PREPROCESS ops (the plans must have
+ * been lowered with persistent input buffers). */
+int  cse_plan_run_from(cse_plan* p, const uint8_t* d_rgb_u8, const uint8_t* d_flow_u8, int n, int first_op,
+                       float* d_logits, float* d_probs, void* stream);
+int  cse_plan_num_input_ops(const cse_plan* p);
 /* Runs ops [first, last) only (per-layer parity tests, profiling). */
 int  cse_plan_run_range(cse_plan* p, const uint8_t* d_rgb_u8, const uint8_t* d_flow_u8, int n,
                         int first, int last, void* stream);

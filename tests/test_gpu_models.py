@@ -126,3 +126,26 @@ def test_bf16_top1_agreement():
     clear = margin > 1e-2
     agree_clear = float((p32.argmax(1) == p16.argmax(1))[clear].mean())
     assert agree_clear >= 0.999, "agreement on clear-margin clips %.4f (overall %.4f)" % (agree_clear, agree)
+
+
+@pytest.mark.parametrize("mt,shape", [("C3D", (16, 48, 48, 3)), ("TWOSTREAM_I3D", (20, 96, 96, 0))])
+def test_ensemble_shared_input_matches_per_member_preprocessing(mt, shape):
+    """DeviceEnsemble pre-processes each micro-batch once (first member) and the other members of the
+    fold start after their PREPROCESS ops: probabilities must be bit-identical to every member
+    running its whole plan, for several micro-batches and a ragged last one."""
+    from cse_b200.ensemble_runtime import DeviceEnsemble
+    g = G.build_model_graph(mt, shape, 11)
+    ws = [synthetic_weights(g, seed=300 + j) for j in range(3)]
+    n = 7
+    xs = [torch.from_numpy(clips(40 + i, n, g.shape(name))).cuda() for i, name in enumerate(g.inputs)]
+    outs = []
+    for share in (True, False):
+        ens = DeviceEnsemble(g, ws, precision="bf16", max_batch=n, micro_batch=3, share_input=share)
+        assert ens.share_input == share
+        ens.forward_members(xs)
+        torch.cuda.synchronize()
+        outs.append(ens.probs[:, :n].cpu().numpy().copy())
+        pred = ens.vote(n).cpu().numpy()
+        del ens
+    assert np.array_equal(outs[0], outs[1])
+    assert pred.shape == (n,)
