@@ -363,6 +363,105 @@ maxpool_bf16_wblock_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* 
   }
 }
 
+// 3x3x3 / stride-1 max pooling (the branch-3 pools of the Inception blocks, train.py:1066-1187), bf16,
+// register-blocked in all three dims: one thread produces a DT x HT x WT block of outputs of one
+// 8-channel vector.  Each input row is loaded once ((WT+2) 16-byte loads, clamped addresses, masked
+// to -inf outside the tensor), reduced along W, folded into the <= 3 output rows that contain it,
+// and each hw-reduced plane into the <= 3 output planes that contain it: 6 loads per output instead
+// of 27 (13.5 with W blocking only).
+template <int DT, int HT, int WT>
+__global__ void __launch_bounds__(128)
+maxpool3s1_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long total,
+                       WinGeom g, int wblocks, int hblocks, int dblocks) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = g.Co / 8;
+  const int c = (int)(idx % cv) * 8; long long t = idx / cv;
+  const int owb = (int)(t % wblocks); t /= wblocks;
+  const int ohb = (int)(t % hblocks); t /= hblocks;
+  const int odb = (int)(t % dblocks); const long long nn = t / dblocks;
+  const int ow0 = owb * WT, oh0 = ohb * HT, od0 = odb * DT;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+  bool wok[WT + 2];
+  long long woff[WT + 2];
+#pragma unroll
+  for (int j = 0; j < WT + 2; ++j) {
+    const int iw = ow0 - g.pw + j;
+    wok[j] = (unsigned)iw < (unsigned)g.Wi;
+    woff[j] = (long long)min(max(iw, 0), g.Wi - 1) * g.in_ld;
+  }
+  uint4 acc[DT][HT][WT];
+#pragma unroll
+  for (int a = 0; a < DT; ++a)
+#pragma unroll
+    for (int b = 0; b < HT; ++b)
+#pragma unroll
+      for (int o = 0; o < WT; ++o) acc[a][b][o] = ninf;
+#pragma unroll
+  for (int pd = 0; pd < DT + 2; ++pd) {
+    const int id = od0 - g.pd + pd;
+    const bool okd = (unsigned)id < (unsigned)g.Di;
+    const int idc = min(max(id, 0), g.Di - 1);
+    uint4 hw[HT][WT];
+#pragma unroll
+    for (int b = 0; b < HT; ++b)
+#pragma unroll
+      for (int o = 0; o < WT; ++o) hw[b][o] = ninf;
+#pragma unroll
+    for (int ph = 0; ph < HT + 2; ++ph) {
+      const int ih = oh0 - g.ph + ph;
+      const bool ok = okd && (unsigned)ih < (unsigned)g.Hi;
+      const int ihc = min(max(ih, 0), g.Hi - 1);
+      const __nv_bfloat16* row = in + (((nn * g.Di + idc) * g.Hi + ihc) * (long long)g.Wi) * g.in_ld + c;
+      uint4 v[WT + 2];
+#pragma unroll
+      for (int j = 0; j < WT + 2; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(row + woff[j]));
+#pragma unroll
+      for (int j = 0; j < WT + 2; ++j) v[j] = (ok && wok[j]) ? v[j] : ninf;
+#pragma unroll
+      for (int o = 0; o < WT; ++o) {
+        const uint4 wm = hmax8(hmax8(v[o], v[o + 1]), v[o + 2]);
+#pragma unroll
+        for (int b = 0; b < HT; ++b)
+          if (ph - b >= 0 && ph - b <= 2) hw[b][o] = hmax8(hw[b][o], wm);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < DT; ++a)
+      if (pd - a >= 0 && pd - a <= 2) {
+#pragma unroll
+        for (int b = 0; b < HT; ++b)
+#pragma unroll
+          for (int o = 0; o < WT; ++o) acc[a][b][o] = hmax8(acc[a][b][o], hw[b][o]);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < DT; ++a) {
+    const int od = od0 + a;
+    if (od >= g.Do) break;
+#pragma unroll
+    for (int b = 0; b < HT; ++b) {
+      const int oh = oh0 + b;
+      if (oh >= g.Ho) break;
+      __nv_bfloat16* orow = out + (((nn * g.Do + od) * g.Ho + oh) * (long long)g.Wo) * g.out_ld + c;
+#pragma unroll
+      for (int o = 0; o < WT; ++o)
+        if (ow0 + o < g.Wo) *reinterpret_cast<uint4*>(orow + (long long)(ow0 + o) * g.out_ld) = acc[a][b][o];
+    }
+  }
+}
+
+static int maxpool3s1(const void* in, void* out, int n, const WinGeom& g, cudaStream_t st) {
+  constexpr int DT = 2, HT = 2, WT = 4;
+  const int wb = ceil_div(g.Wo, WT), hb = ceil_div(g.Ho, HT), db = ceil_div(g.Do, DT);
+  const long long total = (long long)n * db * hb * wb * (g.Co / 8);
+  if (total == 0) return CSE_OK;
+  maxpool3s1_bf16_kernel<DT, HT, WT><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, g, wb, hb, db);
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}
+
 template <int KW, int SW>
 static int maxpool_wblock(bool pad_is_zero, const void* in, void* out, int n, const WinGeom& g, cudaStream_t st) {
   constexpr int WT = 4;
@@ -403,6 +502,9 @@ int launch_pool(int dt, bool is_max, bool pad_is_zero, const void* in, void* out
   }
   if (dt == CSE_BF16) {
     if (is_max && vec_ok(g.Co, g.in_ld, g.out_ld, 8, in, out, 2)) {
+      if (!pad_is_zero && g.kd == 3 && g.kh == 3 && g.kw == 3 && g.sd == 1 && g.sh == 1 && g.sw == 1 &&
+          g.Do == g.Di && g.Ho == g.Hi && g.Wo == g.Wi)
+        return maxpool3s1(in, out, n, g, st);
       if (g.kw == 3 && g.sw == 1) return maxpool_wblock<3, 1>(pad_is_zero, in, out, n, g, st);
       if (g.kw == 3 && g.sw == 2) return maxpool_wblock<3, 2>(pad_is_zero, in, out, n, g, st);
       if (g.kw == 2 && g.sw == 2) return maxpool_wblock<2, 2>(pad_is_zero, in, out, n, g, st);
