@@ -43,9 +43,9 @@ WORKLOADS = {
     "c3d_single_b8": ([("C3D", (16, 112, 112, 3), 1, 8)], 8),                     # configs[0]
     "r3d34_ens": ([("R3D_34", (16, 112, 112, 3), 4, 256)], 256),
     "i3d20_ens": ([("I3D", (20, 224, 224, 3), 4, 128)], 128),                     # reference-true T=20 (train.py:1573)
-    "i3d64_ens": ([("I3D", (64, 224, 224, 3), 4, 32)], 32),                       # configs[2]
+    "i3d64_ens": ([("I3D", (64, 224, 224, 3), 4, 64)], 64),                       # configs[2]
     "twostream20_ens": ([("TWOSTREAM_I3D", (20, 224, 224, 0), 4, 64)], 64),
-    "twostream64_ens": ([("TWOSTREAM_I3D", (64, 224, 224, 0), 4, 16)], 16),       # configs[3]
+    "twostream64_ens": ([("TWOSTREAM_I3D", (64, 224, 224, 0), 4, 32)], 32),       # configs[3]
     "global_hetero": ([("C3D", (16, 112, 112, 3), 4, 256), ("I3D", (64, 224, 224, 3), 4, 32),
                        ("R3D_34", (16, 112, 112, 3), 4, 256)], 256),              # configs[4] (per GPU)
     "global_hetero_t20": ([("C3D", (16, 112, 112, 3), 4, 256), ("I3D", (20, 224, 224, 3), 4, 128),

@@ -218,11 +218,16 @@ def fold_bn(bias, bn_weights, has_gamma, co):
 
 
 def choose_kc(ci: int) -> int:
-    best, best_pad = 64, None
+    """Channels per pipeline stage (64/32/16 -> 128B/64B/32B swizzle).  Every stage costs a barrier
+    round trip and one TMA issue on top of its kc/16 MMAs, so a few zero-padded channels (TMA fills
+    the tail beyond Cin with zeros, the packed weights hold zeros there) beat many thin stages:
+    Cin = 144 runs as 3 x 64 rather than 9 x 16."""
+    best, best_cost = 64, None
     for kc in (64, 32, 16):
-        pad = _round_up(ci, kc)
-        if best_pad is None or pad < best_pad:
-            best, best_pad = kc, pad
+        chunks = -(-ci // kc)
+        cost = chunks * (24 + kc)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = kc, cost
     return best
 
 
