@@ -82,6 +82,7 @@ struct ConvTcDesc {            // built once at plan finalize
   int ec, nslots;              // epilogue chunk width (channels per TMA store) and staging slots
   uint32_t slot_bytes;
   bool has_out1;
+  int out_split, out_jump;     // fused sibling 1x1 convs: channels >= split are stored out_jump further
   int pair_pool;               // pair-packed stem with the (1,2,2) max-pool done in registers
   int twin_ok;                 // twin-tile layout available (two M tiles share every B stage)
   uint32_t tw_stage_bytes, tw_stage_region;
@@ -102,7 +103,7 @@ struct ConvTcDesc {            // built once at plan finalize
 };
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
                   int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
-                  const int pool_dims[3], int pool_zero, int pair_pool);
+                  const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_jump);
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);
 
 }  // namespace cse

@@ -451,7 +451,151 @@ maxpool3s1_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __re
   }
 }
 
+// Plane-sweep variant (Mixed_3b..5c: 28x28, 14x14, 7x7 planes): a CTA owns one clip x one chunk of
+// 8*vpc channels (vpc = 8: a full 128-byte line per pixel) x one strip of hs output rows x one segment of
+// output planes, and walks the input planes of that segment once.  Each plane strip (+ one halo row above
+// and below) goes global -> shared memory with cp.async, three stages deep.  A thread owns NG groups of
+// WT neighbouring pixels of one 8-channel vector: per plane it reads 3 x (WT + 2) vectors from shared
+// memory (a neighbour outside the plane is replaced by the pixel itself, which leaves the maximum
+// unchanged), reduces them along H then W, and keeps the last two hw-reduced planes in registers, so
+// every input element is read from HBM once (halo rows / planes are re-read through L2).
+constexpr int SWEEP_STAGES = 3;
+template <int WT, int NG>
+__global__ void __launch_bounds__(224, 3)
+maxpool3s1_sweep_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, WinGeom g,
+                        int vpc, int nchunks, int hs, int nstrips, int dsegs, int dlen) {
+  extern __shared__ uint4 sweep_smem[];
+  const int rowv = g.Wi * vpc;                       // vectors per plane row of this chunk
+  const int gpr = g.Wi / WT;                         // pixel groups per row
+  int b = blockIdx.x;
+  const int chunk = b % nchunks; b /= nchunks;
+  const int strip = b % nstrips; b /= nstrips;
+  const int seg = b % dsegs;
+  const long long nn = b / dsegs;
+  const int h0 = strip * hs, h1 = min(h0 + hs, g.Hi);
+  const int lo = max(h0 - 1, 0), hi = min(h1 + 1, g.Hi);          // rows loaded: [lo, hi)
+  const int d_lo = seg * dlen, d_hi = min(d_lo + dlen, g.Di);
+  const int ngroups = (h1 - h0) * gpr * vpc;
+  const int stage_v = (hs + 2) * rowv;                // smem row r holds plane row h0 - 1 + r
+  const int cbase = chunk * vpc * 8;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+  // per group: first pixel | channel << 16, its smem index, and 5 flag bits (active, has up / down / left /
+  // right neighbour)
+  uint32_t pc[NG], ci[NG];
+  uint32_t flags = 0;
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    const int gi = threadIdx.x + k * blockDim.x;
+    const int v = gi % vpc, t = gi / vpc;
+    const int wg = t % gpr, hh = t / gpr;
+    const int w0 = wg * WT, h = h0 + hh;
+    const int c = cbase + v * 8;
+    const bool act = gi < ngroups && c < g.Co;
+    pc[k] = act ? ((uint32_t)(h * g.Wi + w0) | ((uint32_t)c << 16)) : 0u;
+    ci[k] = act ? (uint32_t)(((hh + 1) * g.Wi + w0) * vpc + v) : 0u;
+    flags |= ((act ? 1u : 0u) | (h > 0 ? 2u : 0u) | (h < g.Hi - 1 ? 4u : 0u) | (w0 > 0 ? 8u : 0u) |
+              (w0 + WT < g.Wi ? 16u : 0u)) << (5 * k);
+  }
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(sweep_smem);
+  const int nload = (hi - lo) * rowv;
+  auto load_plane = [&](int id, int stage) {          // rows [lo, hi) of plane id -> stage
+    if (id >= 0 && id < g.Di && id <= d_hi) {
+      const __nv_bfloat16* pl = in + ((nn * g.Di + id) * g.Hi + lo) * (long long)g.Wi * g.in_ld + cbase;
+      const uint32_t dst = smem_base + (uint32_t)(stage * stage_v + (lo - (h0 - 1)) * rowv) * 16u;
+      for (int j = threadIdx.x; j < nload; j += blockDim.x) {
+        const int p = j / vpc, v = j - p * vpc;
+        if (cbase + v * 8 < g.Co)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)j * 16u),
+                       "l"(pl + (long long)p * g.in_ld + v * 8) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  uint4 r0[NG][WT], r1[NG][WT];
+#pragma unroll
+  for (int k = 0; k < NG; ++k)
+#pragma unroll
+    for (int o = 0; o < WT; ++o) { r0[k][o] = ninf; r1[k][o] = ninf; }
+  load_plane(d_lo - 1, 0);
+  load_plane(d_lo, 1);
+  int stage = 0;
+  for (int id = d_lo - 1; id <= d_hi; ++id) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();                                   // plane id has landed; everyone is done with plane id - 1
+    load_plane(id + 2, stage == 0 ? SWEEP_STAGES - 1 : stage - 1);
+    const bool valid = id >= 0 && id < g.Di;
+    const uint4* sp = sweep_smem + stage * stage_v;
+    const bool emit = id - 1 >= d_lo && id - 1 < d_hi;
+    __nv_bfloat16* opl = out + (nn * g.Do + (id - 1)) * (long long)g.Hi * g.Wi * g.out_ld;
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      const uint32_t f = flags >> (5 * k);
+      uint4 hw[WT];
+#pragma unroll
+      for (int o = 0; o < WT; ++o) hw[o] = ninf;
+      if (valid && (f & 1u)) {
+        const uint4* q = sp + ci[k];
+        const int ou = (f & 2u) ? -rowv : 0, od = (f & 4u) ? rowv : 0;
+        uint4 col[WT + 2];
+#pragma unroll
+        for (int j = 0; j < WT + 2; ++j) {
+          const int cj = j == 0 ? ((f & 8u) ? -vpc : 0) : (j == WT + 1 ? ((f & 16u) ? WT * vpc : (WT - 1) * vpc) : (j - 1) * vpc);
+          col[j] = hmax8(hmax8(q[ou + cj], q[cj]), q[od + cj]);
+        }
+#pragma unroll
+        for (int o = 0; o < WT; ++o) hw[o] = hmax8(hmax8(col[o], col[o + 1]), col[o + 2]);
+      }
+      if (emit && (f & 1u)) {
+        __nv_bfloat16* op = opl + (long long)(pc[k] & 0xFFFFu) * g.out_ld + (pc[k] >> 16);
+#pragma unroll
+        for (int o = 0; o < WT; ++o)
+          *reinterpret_cast<uint4*>(op + (long long)o * g.out_ld) = hmax8(hmax8(r0[k][o], r1[k][o]), hw[o]);
+      }
+#pragma unroll
+      for (int o = 0; o < WT; ++o) { r0[k][o] = r1[k][o]; r1[k][o] = hw[o]; }
+    }
+    stage = stage == SWEEP_STAGES - 1 ? 0 : stage + 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int WT, int NG>
+static int maxpool3s1_sweep_launch(const void* in, void* out, int n, const WinGeom& g, int vpc, cudaStream_t st) {
+  static bool attr_set = false;
+  // strip height: <= 224 threads x NG groups of WT pixels, equal strips
+  const int per_row = (g.Wi / WT) * vpc;
+  int hs = max(1, min(g.Hi, 224 * NG / per_row));
+  hs = ceil_div(g.Hi, ceil_div(g.Hi, hs));
+  const int threads = ceil_div(ceil_div(hs * per_row, NG), 32) * 32;
+  const size_t smem = (size_t)SWEEP_STAGES * (hs + 2) * g.Wi * vpc * sizeof(uint4);
+  if (threads > 224 || smem > 72 * 1024) return -1;
+  if (!attr_set) {
+    CSE_CUDA(cudaFuncSetAttribute(maxpool3s1_sweep_kernel<WT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  const int nchunks = ceil_div(g.Co / 8, vpc);
+  const int nstrips = ceil_div(g.Hi, hs);
+  // segments of >= 8 output planes, as many as it takes to give every SM a few CTAs
+  int dsegs = 1;
+  while (dsegs * 2 * 8 <= g.Di && (long long)n * nchunks * nstrips * dsegs < 8 * 148) dsegs *= 2;
+  const int dlen = ceil_div(g.Di, dsegs);
+  dsegs = ceil_div(g.Di, dlen);
+  maxpool3s1_sweep_kernel<WT, NG><<<(unsigned)(n * nchunks * nstrips * dsegs), threads, smem, st>>>(
+      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, g, vpc, nchunks, hs, nstrips, dsegs, dlen);
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}
+
 static int maxpool3s1(const void* in, void* out, int n, const WinGeom& g, cudaStream_t st) {
+  const int vpc = min(8, g.Co / 8);
+  if (n > 0 && g.Hi * g.Wi <= 65535 && g.Co <= 65528 &&
+      (long long)g.Hi * g.Wi * max(g.in_ld, g.out_ld) < (1ll << 31)) {
+    int rc;
+    if (g.Wi % 4 == 0) rc = maxpool3s1_sweep_launch<4, 1>(in, out, n, g, vpc, st);
+    else if (g.Wi % 2 == 0) rc = maxpool3s1_sweep_launch<2, 2>(in, out, n, g, vpc, st);
+    else rc = maxpool3s1_sweep_launch<1, 4>(in, out, n, g, vpc, st);
+    if (rc >= 0) return rc;                           // -1: the plane strip does not fit -> register-blocked kernel
+  }
   constexpr int DT = 2, HT = 2, WT = 4;
   const int wb = ceil_div(g.Wo, WT), hb = ceil_div(g.Ho, HT), db = ceil_div(g.Do, DT);
   const long long total = (long long)n * db * hb * wb * (g.Co / 8);

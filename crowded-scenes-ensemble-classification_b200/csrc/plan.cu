@@ -161,8 +161,13 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
                              o.tc_pair_pool ? o.out_dims[3] / 2 : o.out_dims[3]};
       if ((rc = check_span(p, o.out0_off, tensor_span(nb, pd, o.out_ld), o.out_dtype, "pooled out0", false))) return rc;
       CSE_REQUIRE(o.engine == CSE_ENGINE_TCGEN05, "op %zu: fused pooling needs the tcgen05 engine", i);
-    } else if ((rc = check_span(p, o.out0_off, tensor_span(nb, o.out_dims, o.out_ld, o.kind == CSE_OP_PREPROCESS ? o.out_wpitch : 0),
+    } else if ((rc = check_span(p, o.out0_off,
+                                tensor_span(nb, o.out_dims, o.out_ld, o.kind == CSE_OP_PREPROCESS ? o.out_wpitch : 0) +
+                                    ((o.kind == CSE_OP_CONV3D && o.out_split > 0) ? o.out_jump : 0),
                                 o.out_dtype, "out0", false))) return rc;
+    if (o.kind == CSE_OP_CONV3D && o.out_split > 0)
+      CSE_REQUIRE(o.engine == CSE_ENGINE_TCGEN05 && o.out_dims[3] + o.out_jump <= o.out_ld,
+                  "op %zu: split output needs the tcgen05 engine and Cout + jump <= out_ld", i);
     if (o.out1_off >= 0 &&
         (rc = check_span(p, o.out1_off, tensor_span(nb, o.out_dims, o.out1_ld), o.out_dtype, "out1", false))) return rc;
     if (o.in1_off >= 0) {
@@ -190,7 +195,7 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
         if ((rc = check_span(p, o.w_off, ktot * rows, CSE_BF16, "tc weights", true))) return rc;
         rc = conv_tc_build(&po.tc, p->ws + o.in0_off, p->wts + o.w_off, p->ws + o.out0_off,
                            o.out1_off >= 0 ? p->ws + o.out1_off : nullptr, o.out1_ld, nb, g, o.kc, o.bn, o.brick,
-                           o.tc_halo, o.pool_k, o.pool_dims, o.pool_zero, o.tc_pair_pool);
+                           o.tc_halo, o.pool_k, o.pool_dims, o.pool_zero, o.tc_pair_pool, o.out_split, o.out_jump);
         if (rc) return rc;
         po.has_tc = true;
       } else {

@@ -96,6 +96,8 @@ class DevOp:
     brick: Tuple[int, int, int, int] = (0, 0, 0, 0)
     halo: int = 0
     pair_pool: int = 0
+    out_split: int = 0            # fused sibling 1x1x1 convs: channels >= out_split land out_jump further
+    out_jump: int = 0
     pool_k: Tuple[int, int, int] = (0, 0, 0)
     pool_zero: int = 0
     conv_out_dims: Optional[Tuple[int, int, int]] = None   # conv's own output dims when a pool is fused
@@ -147,6 +149,7 @@ class Plan:
                 s.in0_off = -1
             s.out_dims[:] = tuple(op.conv_out_dims or o0.dims) + (o0.C * (2 if op.pair_pool else 1),)
             s.tc_pair_pool = op.pair_pool
+            s.out_split, s.out_jump = op.out_split, op.out_jump
             s.out_ld, s.out_dtype, s.out0_off = o0.ld, o0.dtype, o0.byte_off()
             if op.pool_k[0] > 0:
                 s.pool_k[:] = op.pool_k
@@ -344,8 +347,10 @@ class Lowerer:
                  max_batch: int = 8, tc: bool = True, tc_strided: bool = True,
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
                  stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True,
-                 balance_n: bool = True, pair_pool: bool = True, persist_input: bool = False):
+                 balance_n: bool = True, pair_pool: bool = True, persist_input: bool = False,
+                 fuse_siblings: bool = True):
         self.keep_all = keep_all
+        self.fuse_siblings = fuse_siblings
         self.persist_input = persist_input
         self.pair_pool = pair_pool
         self.balance_n = balance_n
@@ -635,12 +640,8 @@ class Lowerer:
             return None
         return k, tuple(mp.out_shape[:3]), zero, names + [mp.name]
 
-    def _conv3d(self, node: Node):
-        g = self.g
-        x = self.val[node.inputs[0]]
-        ws = self.w[node.name]
-        kernel = ws[0]
-        bias = ws[1] if node.attrs["use_bias"] else None
+    def _conv_chain(self, node: Node):
+        """Conv3D (+ BatchNormalization) (+ ReLU) chain folded into one op -> (chain_bn, relu, final, layers)."""
         layers = [node.name]
         final = node.name
         relu = node.attrs["activation"] == "relu"
@@ -655,6 +656,93 @@ class Lowerer:
             relu = True
             layers.append(nxt.name)
             final = nxt.name
+        return chain_bn, relu, final, layers
+
+    def _fused_siblings(self, node: Node) -> bool:
+        """Horizontal fusion of the 1x1x1 convs that read the same tensor (branch 0, 1a, 2a of an Inception
+        block, train.py:1048-1193): one GEMM with N = sum of their filters, so the block input is read
+        once instead of three times.  Branch 0 lands in its slice of the concat buffer; the 1a / 2a
+        activations land in scratch channels appended behind the concat channels of the same buffer
+        (ld = concat channels + scratch), where the 3x3x3 convs read them as channel slices."""
+        if not (self.use_tc and self.fuse_siblings):
+            return False
+
+        def is_pw(n):
+            return (n.op == "conv3d" and tuple(n.attrs["k"]) == (1, 1, 1) and tuple(n.attrs["s"]) == (1, 1, 1)
+                    and n.name not in self.done)
+        if not is_pw(node):
+            return False
+        src = node.inputs[0]
+        x = self.val[src]
+        sibs = [self.g.nodes[c] for c in self.consumers[src] if is_pw(self.g.nodes[c])]
+        if len(sibs) < 2 or node.name not in [n.name for n in sibs]:
+            return False
+        chains = [self._conv_chain(n) for n in sibs]
+        placed = [i for i, ch in enumerate(chains) if ch[2] in self.place]
+        if len(placed) != 1 or len({ch[1] for ch in chains}) != 1:
+            return False
+        order = placed + [i for i in range(len(sibs)) if i != placed[0]]
+        sibs, chains = [sibs[i] for i in order], [chains[i] for i in order]
+        cos = [n.attrs["filters"] for n in sibs]
+        cname, coff = self.place[chains[0][2]]
+        if coff != 0 or cname in self.concat_ref or cos[0] % 16 or any(c % 8 for c in cos):
+            return False
+        co = sum(cos)
+        if not self._tc_ok(x, co, (1, 1, 1), self.act, None):
+            return False
+        out_dims = tuple(node.out_shape[:3])
+        ctot = self.g.shape(cname)[-1]
+        ld = ctot + co - cos[0]
+        buf = self.new_buf(cname, out_dims, ld, self.act)
+        self.concat_ref[cname] = TRef(buf, 0, ctot, ld, out_dims, self.act)
+        kernel = np.concatenate([self.w[n.name][0] for n in sibs], axis=-1)
+        scales, shifts = [], []
+        for n, ch, c in zip(sibs, chains, cos):
+            bias = self.w[n.name][1] if n.attrs["use_bias"] else None
+            sc, sh = fold_bn(bias, ch[0][0] if ch[0] else None, ch[0][1] if ch[0] else False, c)
+            scales.append(np.ones(c, np.float32) if sc is None else sc)
+            shifts.append(np.zeros(c, np.float32) if sh is None else sh)
+        fl = self.g.conv_dense_flops()
+        layers = tuple(l for ch in chains for l in ch[3])
+        op = DevOp(rt.OP_CONV3D, "+".join(n.name for n in sibs), x, None, TRef(buf, 0, co, ld, out_dims, self.act),
+                   k=(1, 1, 1), s=(1, 1, 1), pad=(0, 0, 0), relu0=int(chains[0][1]), layers=layers,
+                   flops=sum(fl[n.name] for n in sibs))
+        op.scale0, op.shift0 = self.fblob(np.concatenate(scales)), self.fblob(np.concatenate(shifts))
+        op.out_split, op.out_jump = cos[0], ctot - cos[0]
+        kc = choose_kc(x.C)
+        op.brick = choose_brick(self.nb, *out_dims)
+        m_tiles = (-(-self.nb // op.brick[0]) * -(-out_dims[0] // op.brick[1]) * -(-out_dims[1] // op.brick[2])
+                   * -(-out_dims[2] // op.brick[3]))
+        bn, n_tiles = choose_bn(co, m_tiles if self.balance_n else 0)
+        # a TMA store chunk (64 / 32 / 16 channels) must divide both the N tile and the split: widen the
+        # tile to the next multiple of 64 or 32 when that costs < 15 % padded columns (wider stores win)
+        for gran in (64, 32):
+            wide = _round_up(bn, gran)
+            if cos[0] % gran == 0 and wide <= 256 and wide * n_tiles <= 1.15 * co:
+                bn = wide
+                break
+        op.engine, op.w_dtype, op.kc, op.bn = rt.ENGINE_TCGEN05, rt.BF16, kc, bn
+        op.w_blob = self.blob(pack_tc_weights(kernel, kc, bn, n_tiles))
+        self.emit(op)
+        off = 0
+        for i, (ch, c) in enumerate(zip(chains, cos)):
+            ref = TRef(buf, 0 if i == 0 else ctot + off, c, ld, out_dims, self.act)
+            if i > 0:
+                off += c
+            for l in ch[3]:
+                self.val[l] = ref
+                self.done.add(l)
+        return True
+
+    def _conv3d(self, node: Node):
+        g = self.g
+        if self._fused_siblings(node):
+            return
+        x = self.val[node.inputs[0]]
+        ws = self.w[node.name]
+        kernel = ws[0]
+        bias = ws[1] if node.attrs["use_bias"] else None
+        chain_bn, relu, final, layers = self._conv_chain(node)
         out_dims = node.out_shape[:3]
         flops = g.conv_dense_flops()[node.name]
         pool = None

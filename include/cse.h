@@ -96,6 +96,10 @@ typedef struct cse_op {
                                 [n,T,H,W/2,16], GEMM row = 2 neighbouring output pixels, out_dims = D,H,W/2,2*Cout, weights
                                 [2*Cout][taps*16]; MaxPooling3D (1,2,2) is done in registers, pool_k = (1,2,1) in this
                                 view, out0 = pooled [n, pool_dims, Cout]; bias (+ReLU) epilogue only */
+  int32_t out_split, out_jump;/* TCGEN05: > 0 = horizontally fused sibling 1x1x1 convs of an Inception block
+                                (train.py:1048-1193): output channels [0, out_split) are stored at out0's channel offset
+                                (branch 0, inside the concat buffer), channels >= out_split out_jump channels further
+                                (the branch-1a / 2a activations, kept in scratch channels behind the concat) */
   int32_t pre_s2d;           /* PREPROCESS: 1 = 2x2 space-to-depth over (H,W) for the stride-2 7x7x7 stems: out_dims =
                                 T, ceil(H/2), ceil(W/2); cell channel (ph*2+pw)*C + c, zero-padded to out_ld = 8/16 */
   int64_t in0_off, in1_off;  /* workspace byte offsets (-1 = none); in1 = residual for CONV3D, 2nd addend for ADD */

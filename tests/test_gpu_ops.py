@@ -150,6 +150,64 @@ def test_conv_tcgen05_vs_oracle(dhw, cin, cout, k, nb):
     assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
 
 
+SIBLING_CASES = [((4, 14, 14), 64, (32, 48, 16, 24, 8, 16), 3),      # split 32 -> 64-wide chunks shrink to 32
+                 ((3, 9, 11), 40, (112, 24, 32, 8, 16, 8), 2),      # split 112 -> 16-wide chunks, ragged bricks
+                 ((2, 7, 7), 256, (256, 160, 64, 32, 32, 16), 5)]   # two N tiles, split on a tile boundary or not
+
+
+@pytest.mark.parametrize("dhw,cin,f,nb", SIBLING_CASES)
+def test_conv_tcgen05_fused_siblings(dhw, cin, f, nb):
+    """Inception block (train.py:1048-1064): the three 1x1x1 convs reading the block input run as ONE
+    tcgen05 GEMM whose output columns are split between the concat slice (branch 0) and scratch
+    channels behind it (1a, 2a); every branch and the concat must match the oracle."""
+    from cse_b200.graph import _conv3d_bn
+    k1, k3, s1 = (1, 1, 1), (3, 3, 3), (1, 1, 1)
+
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, cin, k1, s1, "same", True, "relu", name="pre")
+        b0 = _conv3d_bn(g, x, f[0], k1, s1, "b0")
+        b1 = _conv3d_bn(g, x, f[1], k1, s1, "b1a")
+        b1 = _conv3d_bn(g, b1, f[2], k3, s1, "b1b")
+        b2 = _conv3d_bn(g, x, f[3], k1, s1, "b2a")
+        b2 = _conv3d_bn(g, b2, f[4], k3, s1, "b2b")
+        b3 = g.maxpool(x, k3, s1, "same", name="b3a")
+        b3 = _conv3d_bn(g, b3, f[5], k1, s1, "b3b")
+        g.concat([b0, b1, b2, b3], name="cat")
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * 3, mean=[128.0] * 3)
+    fused = [o for o in m.plan.ops if o.out_split > 0]
+    assert len(fused) == 1 and fused[0].out_split == f[0] and fused[0].engine == rt.ENGINE_TCGEN05
+    assert fused[0].out0.C == f[0] + f[1] + f[3]
+    run(m, [clips(9, nb, dhw + (3,))])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], nb), dtype=T64)
+
+    def cbr(x, name, k):
+        y = O.conv3d(x, bf16_round(w[name + "_conv"][0]), None, s1, "same")
+        return O.relu(O.batchnorm(y, None, *[torch.as_tensor(a, dtype=T64) for a in w[name + "_bn"]]))
+    exp = {"b0": cbr(xin, "b0", k1), "b1a": cbr(xin, "b1a", k1), "b2a": cbr(xin, "b2a", k1)}
+    for name, e in exp.items():
+        got = m.read_tensor(m.plan.tensors[name], nb)
+        e = e.numpy()
+        err = np.abs(got - e).max() / max(np.abs(e).max(), 1e-6)
+        assert err <= 2.0 ** -7, "%s rel err %g" % (name, err)
+    # downstream: the 3x3x3 convs read the scratch slices, the concat holds all four branches
+    a1 = torch.as_tensor(m.read_tensor(m.plan.tensors["b1a"], nb), dtype=T64)
+    a2 = torch.as_tensor(m.read_tensor(m.plan.tensors["b2a"], nb), dtype=T64)
+    p3 = O.maxpool3d(xin, k3, s1, "same")
+    assert np.array_equal(m.read_tensor(m.plan.tensors["b3a"], nb), p3.numpy().astype(np.float32))
+    cat = np.concatenate([m.read_tensor(m.plan.tensors["b0"], nb), cbr(a1, "b1b", k3).numpy(),
+                          cbr(a2, "b2b", k3).numpy(), cbr(p3, "b3b", k1).numpy()], axis=-1)
+    got = m.read_tensor(m.plan.tensors["cat"], nb)
+    assert got.shape == cat.shape
+    err = np.abs(got - cat).max() / np.abs(cat).max()
+    assert err <= 2.0 ** -7, "concat rel err %g" % err
+    # and the unfused lowering gives bit-identical activations (same MMA order per output column)
+    g2, w2, m2 = make_member(build, "bf16", nb, scale=[1 / 64.0] * 3, mean=[128.0] * 3, fuse_siblings=False)
+    assert not [o for o in m2.plan.ops if o.out_split > 0]
+    run(m2, [clips(9, nb, dhw + (3,))])
+    assert np.array_equal(m2.read_tensor(m2.plan.tensors["cat"], nb), got)
+
+
 TWIN_CASES = [((4, 8, 8), 64, 128, (3, 3, 3), 2), ((5, 9, 9), 192, 64, (1, 1, 1), 2), ((3, 6, 6), 16, 48, (3, 3, 3), 3),
               ((4, 14, 14), 32, 96, (3, 3, 3), 1), ((2, 5, 5), 480, 24, (1, 1, 1), 3)]
 
@@ -411,6 +469,27 @@ def test_maxpool_exact(k, s, pad, precision):
     exp = O.maxpool3d(xin, k, s, pad).numpy()
     got = m.read_tensor(m.plan.tensors["p"], 2)
     assert np.array_equal(got, exp.astype(np.float32))       # max is exact in any precision
+
+
+@pytest.mark.parametrize("dhw,c,nb", [((9, 28, 28), 48, 2),      # 2 vectors / pixel, 4 items / thread
+                                      ((33, 28, 28), 16, 1),     # split into D segments (halo planes re-read)
+                                      ((20, 14, 14), 40, 3),     # 4 vectors / pixel, ragged last channel chunk
+                                      ((8, 7, 7), 72, 2),        # 8 vectors / pixel
+                                      ((1, 5, 3), 8, 2),         # single plane
+                                      ((2, 40, 40), 8, 1),       # 1 vector / pixel, one 40-row strip
+                                      ((5, 30, 30), 64, 1),      # 28 + 2 rows -> strips of 7/8 rows with halo rows
+                                      ((2, 3, 230), 64, 1)])     # row too long for shared memory -> register-blocked kernel
+def test_maxpool3s1_plane_sweep_exact(dhw, c, nb):
+    """3x3x3 / stride-1 'same' max-pool (Inception branch 3, train.py:1066): plane-sweep kernel, signed inputs."""
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, c, (1, 1, 1), (1, 1, 1), "same", True, None, name="pre")
+        g.maxpool(x, (3, 3, 3), (1, 1, 1), "same", name="p")
+    g, w, m = make_member(build, "bf16", nb, tc=False, scale=[1 / 64.0] * 3, mean=[128.0] * 3)
+    run(m, [clips(16, nb, dhw + (3,))])
+    xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], nb), dtype=T64)
+    exp = O.maxpool3d(xin, (3, 3, 3), (1, 1, 1), "same").numpy()
+    assert np.array_equal(m.read_tensor(m.plan.tensors["p"], nb), exp.astype(np.float32))
 
 
 def test_zeropad_maxpool_and_avgpool():
