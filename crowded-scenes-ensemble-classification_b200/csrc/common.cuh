@@ -78,11 +78,11 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
 
 // tcgen05 engine
 struct ConvTcDesc {            // built once at plan finalize
-  CUtensorMap tmap_a, tmap_b, tmap_o0, tmap_o1;
+  CUtensorMap tmap_a, tmap_b, tmap_o0, tmap_o1, tmap_o2;
   int ec, nslots;              // epilogue chunk width (channels per TMA store) and staging slots
   uint32_t slot_bytes;
   bool has_out1;
-  int out_split, out_jump;     // fused sibling 1x1 convs: channels >= split are stored out_jump further
+  int out_split, out_split2;   // fused sibling 1x1 convs: columns >= split go to out1, columns >= split2 to out2
   int pair_pool;               // pair-packed stem with the (1,2,2) max-pool done in registers
   int twin_ok;                 // twin-tile layout available (two M tiles share every B stage)
   uint32_t tw_stage_bytes, tw_stage_region;
@@ -103,7 +103,7 @@ struct ConvTcDesc {            // built once at plan finalize
 };
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
                   int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
-                  const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_jump);
+                  const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_split2, void* out2, int out2_ld);
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);
 
 }  // namespace cse

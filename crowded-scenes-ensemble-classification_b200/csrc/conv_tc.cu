@@ -174,7 +174,7 @@ struct ConvTcArgs {
   uint32_t slot_bytes;             // bytes of one staging slot (full tile [+ out1 tile] [+ pooled tile])
   int pool_d, pool_h, pool_w;      // fused MaxPooling3D window (= stride); 0 = no pooling
   int pool_zero;                   // rows outside the conv output count as 0 (ZeroPadding3D before the pool)
-  int out_split, out_jump;         // output channels >= out_split are stored out_jump channels further (fused sibling 1x1 convs)
+  int out_split, out_split2;       // fused sibling 1x1 convs: columns >= out_split go to tmap_o1, columns >= out_split2 to tmap_o2
   int twin;                        // twin-tile mode: two M tiles share every B stage (4 TMEM accumulators of bn <= 128 columns)
   int pair_pool;                   // pair-packed stem: GEMM row = 2 output pixels (N = 2*Cout), (1,2,2) max-pool in registers
   int step1[5], step2[5];          // gridDim.x and 2*gridDim.x as mixed-radix digits (nt, tw, th, td, tn)
@@ -259,6 +259,7 @@ template <int KC, int EC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1,
+               const __grid_constant__ CUtensorMap tmap_o2,
                const ConvTcArgs a) {
   constexpr uint32_t ROW_BYTES = KC * 2;
   constexpr uint32_t SBO = 8 * ROW_BYTES;
@@ -858,12 +859,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (store_thread) {
           const uint32_t src = my_stg + (uint32_t)slot * slot_bytes;
           if (col_base + c0 < a.Co) {
-            const int dcol = col_base + c0 + ((a.out_split > 0 && col_base + c0 >= a.out_split) ? a.out_jump : 0);
+            const int col = col_base + c0;
             if (pooled) {
-              tma_store_5d(&tmap_o0, src + pool_stg_off, dcol, ow0 / a.pool_w, oh0 / a.pool_h, od0 / a.pool_d, on0);
+              tma_store_5d(&tmap_o0, src + pool_stg_off, col, ow0 / a.pool_w, oh0 / a.pool_h, od0 / a.pool_d, on0);
+            } else if (a.out_split > 0 && col >= a.out_split) {
+              if (a.out_split2 > 0 && col >= a.out_split2) tma_store_5d(&tmap_o2, src, col - a.out_split2, ow0, oh0, od0, on0);
+              else tma_store_5d(&tmap_o1, src, col - a.out_split, ow0, oh0, od0, on0);
             } else {
-              tma_store_5d(&tmap_o0, src, dcol, ow0, oh0, od0, on0);
-              if (has_out1) tma_store_5d(&tmap_o1, src + STG_BYTES, col_base + c0, ow0, oh0, od0, on0);
+              tma_store_5d(&tmap_o0, src, col, ow0, oh0, od0, on0);
+              if (has_out1) tma_store_5d(&tmap_o1, src + STG_BYTES, col, ow0, oh0, od0, on0);
             }
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -930,7 +934,7 @@ static int encode_out_map(PFN_encodeTiled enc, CUtensorMap* m, void* out, int ld
 
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
                   int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
-                  const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_jump) {
+                  const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_split2, void* out2, int out2_ld) {
   CSE_REQUIRE(kc == 16 || kc == 32 || kc == 64, "conv_tc: kc=%d must be 16/32/64", kc);
   CSE_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "conv_tc: bn=%d must be a multiple of 16 in [16,256]", bn);
   CSE_REQUIRE(g.Ci % 8 == 0 && g.in_ld % 8 == 0, "conv_tc: Cin=%d / ld=%d must be multiples of 8", g.Ci, g.in_ld);
@@ -954,16 +958,19 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   d->tiles_h = ceil_div(g.Ho, brick[2]);
   d->tiles_w = ceil_div(g.Wo, brick[3]);
   d->ec = (bn % 64 == 0) ? 64 : (bn % 32 == 0 ? 32 : 16);
-  d->out_split = out_split; d->out_jump = out_split > 0 ? out_jump : 0;
+  d->out_split = out_split; d->out_split2 = out_split > 0 ? out_split2 : 0;
   if (out_split > 0) {
-    // fused sibling 1x1 convs: channels [0, split) go to the concat slice, the rest out_jump further
-    // (scratch channels behind the concat); a store chunk must not straddle the split
-    CSE_REQUIRE(out_split % 16 == 0 && out_split < g.Co && out_jump >= 0 && out_jump % 8 == 0 && out1 == nullptr &&
+    // fused sibling 1x1 convs: columns [0, split) -> out0, [split, split2 or Co) -> out1, [split2, Co) -> out2; a store
+    // chunk must not straddle a split
+    CSE_REQUIRE(out_split % 16 == 0 && out_split < g.Co && out1 != nullptr && ((uintptr_t)out1 % 16) == 0 && out1_ld % 8 == 0 &&
                     !(pool && pool[0] > 0) && !pair_pool,
-                "conv_tc: bad output split %d (+%d) for Cout=%d", out_split, out_jump, g.Co);
-    while (out_split % d->ec) d->ec /= 2;
+                "conv_tc: bad output split %d for Cout=%d", out_split, g.Co);
+    CSE_REQUIRE(out_split2 == 0 || (out_split2 % 16 == 0 && out_split2 > out_split && out_split2 < g.Co && out2 != nullptr &&
+                                    ((uintptr_t)out2 % 16) == 0 && out2_ld % 8 == 0),
+                "conv_tc: bad second output split %d (first %d, Cout=%d)", out_split2, out_split, g.Co);
+    while (out_split % d->ec || out_split2 % d->ec) d->ec /= 2;
   }
-  d->has_out1 = out1 != nullptr;
+  d->has_out1 = out1 != nullptr && out_split == 0;
   d->halo = halo;
   d->pair_pool = pair_pool;
   if (pair_pool) {
@@ -1046,15 +1053,26 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
     rc = encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, pg, max_batch, 64, pbrick, ppool, pool_dims);
     if (rc) return rc;
     d->tmap_o1 = d->tmap_o0;
-  } else {
+    d->tmap_o2 = d->tmap_o0;
+  } else if (out_split > 0) {
     WinGeom og = g;
-    og.Co = g.Co + d->out_jump;            // the jumped range ends out_jump channels further
+    og.Co = out_split;
+    if ((rc = encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, og, max_batch, d->ec, brick))) return rc;
+    og.Co = (d->out_split2 > 0 ? d->out_split2 : g.Co) - out_split;
+    if ((rc = encode_out_map(enc, &d->tmap_o1, out1, out1_ld, og, max_batch, d->ec, brick))) return rc;
+    d->tmap_o2 = d->tmap_o1;
+    if (d->out_split2 > 0) {
+      og.Co = g.Co - d->out_split2;
+      if ((rc = encode_out_map(enc, &d->tmap_o2, out2, out2_ld, og, max_batch, d->ec, brick))) return rc;
+    }
+  } else {
     rc = pooled ? encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick, pool, pool_dims)
-                : encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, og, max_batch, d->ec, brick);
+                : encode_out_map(enc, &d->tmap_o0, out0, g.out_ld, g, max_batch, d->ec, brick);
     if (rc) return rc;
     rc = encode_out_map(enc, &d->tmap_o1, d->has_out1 ? out1 : out0, d->has_out1 ? out1_ld : g.out_ld, g, max_batch, d->ec,
                         brick);
     if (rc) return rc;
+    d->tmap_o2 = d->tmap_o0;
   }
 
   // shared memory: [pipeline stages][epilogue staging slots]; 227 KB per CTA minus static + alignment slack
@@ -1138,7 +1156,7 @@ static int launch_tc_t(const ConvTcDesc& d, const ConvTcArgs& args, int grid, si
     CSE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<KC, EC><<<grid, TC_THREADS, smem_bytes, st>>>(d.tmap_a, d.tmap_b, d.tmap_o0, d.tmap_o1, args);
+  conv_tc_kernel<KC, EC><<<grid, TC_THREADS, smem_bytes, st>>>(d.tmap_a, d.tmap_b, d.tmap_o0, d.tmap_o1, d.tmap_o2, args);
   CSE_CUDA(cudaGetLastError());
   return CSE_OK;
 }
@@ -1174,7 +1192,7 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   a.halo = d.halo; a.b_resident = d.b_resident; a.b_region = d.b_region;
   a.pool_d = d.pool[0]; a.pool_h = d.pool[1]; a.pool_w = d.pool[2]; a.pool_zero = d.pool_zero;
   a.pair_pool = d.pair_pool;
-  a.out_split = d.out_split; a.out_jump = d.out_jump;
+  a.out_split = d.out_split; a.out_split2 = d.out_split2;
   a.stage_region = d.stage_region;
   a.nslots = d.nslots; a.slot_bytes = d.slot_bytes;
   a.ep = ep;

@@ -161,15 +161,25 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
                              o.tc_pair_pool ? o.out_dims[3] / 2 : o.out_dims[3]};
       if ((rc = check_span(p, o.out0_off, tensor_span(nb, pd, o.out_ld), o.out_dtype, "pooled out0", false))) return rc;
       CSE_REQUIRE(o.engine == CSE_ENGINE_TCGEN05, "op %zu: fused pooling needs the tcgen05 engine", i);
-    } else if ((rc = check_span(p, o.out0_off,
-                                tensor_span(nb, o.out_dims, o.out_ld, o.kind == CSE_OP_PREPROCESS ? o.out_wpitch : 0) +
-                                    ((o.kind == CSE_OP_CONV3D && o.out_split > 0) ? o.out_jump : 0),
-                                o.out_dtype, "out0", false))) return rc;
-    if (o.kind == CSE_OP_CONV3D && o.out_split > 0)
-      CSE_REQUIRE(o.engine == CSE_ENGINE_TCGEN05 && o.out_dims[3] + o.out_jump <= o.out_ld,
-                  "op %zu: split output needs the tcgen05 engine and Cout + jump <= out_ld", i);
-    if (o.out1_off >= 0 &&
-        (rc = check_span(p, o.out1_off, tensor_span(nb, o.out_dims, o.out1_ld), o.out_dtype, "out1", false))) return rc;
+    } else if (o.kind == CSE_OP_CONV3D && o.out_split > 0) {
+      // fused sibling convs: three column ranges, three tensors
+      CSE_REQUIRE(o.engine == CSE_ENGINE_TCGEN05 && o.out_split < o.out_dims[3] && o.out1_off >= 0 &&
+                      (o.out_split2 == 0 || (o.out_split2 > o.out_split && o.out_split2 < o.out_dims[3] && o.out2_off >= 0)),
+                  "op %zu: split output needs the tcgen05 engine and out1 (/ out2) tensors", i);
+      const int end1 = o.out_split2 > 0 ? o.out_split2 : o.out_dims[3];
+      const int32_t d0[4] = {o.out_dims[0], o.out_dims[1], o.out_dims[2], o.out_split};
+      const int32_t d1[4] = {o.out_dims[0], o.out_dims[1], o.out_dims[2], end1 - o.out_split};
+      const int32_t d2[4] = {o.out_dims[0], o.out_dims[1], o.out_dims[2], o.out_dims[3] - end1};
+      if ((rc = check_span(p, o.out0_off, tensor_span(nb, d0, o.out_ld), o.out_dtype, "out0 (split)", false))) return rc;
+      if ((rc = check_span(p, o.out1_off, tensor_span(nb, d1, o.out1_ld), o.out_dtype, "out1 (split)", false))) return rc;
+      if (o.out_split2 > 0 &&
+          (rc = check_span(p, o.out2_off, tensor_span(nb, d2, o.out2_ld), o.out_dtype, "out2 (split)", false))) return rc;
+    } else {
+      if ((rc = check_span(p, o.out0_off, tensor_span(nb, o.out_dims, o.out_ld, o.kind == CSE_OP_PREPROCESS ? o.out_wpitch : 0),
+                           o.out_dtype, "out0", false))) return rc;
+      if (o.out1_off >= 0 &&
+          (rc = check_span(p, o.out1_off, tensor_span(nb, o.out_dims, o.out1_ld), o.out_dtype, "out1", false))) return rc;
+    }
     if (o.in1_off >= 0) {
       const int32_t* d = (o.kind == CSE_OP_CONV3D) ? o.out_dims : o.in_dims;
       int dt = (o.kind == CSE_OP_CONV3D) ? o.out_dtype : o.in_dtype;
@@ -195,7 +205,8 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
         if ((rc = check_span(p, o.w_off, ktot * rows, CSE_BF16, "tc weights", true))) return rc;
         rc = conv_tc_build(&po.tc, p->ws + o.in0_off, p->wts + o.w_off, p->ws + o.out0_off,
                            o.out1_off >= 0 ? p->ws + o.out1_off : nullptr, o.out1_ld, nb, g, o.kc, o.bn, o.brick,
-                           o.tc_halo, o.pool_k, o.pool_dims, o.pool_zero, o.tc_pair_pool, o.out_split, o.out_jump);
+                           o.tc_halo, o.pool_k, o.pool_dims, o.pool_zero, o.tc_pair_pool, o.out_split, o.out_split2,
+                           o.out_split2 > 0 ? p->ws + o.out2_off : nullptr, o.out2_ld);
         if (rc) return rc;
         po.has_tc = true;
       } else {
@@ -228,7 +239,7 @@ static int run_op(cse_plan* p, PlanOp& po, const uint8_t* rgb, const uint8_t* fl
       ep.scale0 = wtf(o.scale0_off); ep.shift0 = wtf(o.shift0_off);
       ep.scale1 = wtf(o.scale1_off); ep.shift1 = wtf(o.shift1_off);
       ep.res = wsp(o.in1_off); ep.res_ld = o.in1_ld;
-      ep.out0 = wsp(o.out0_off); ep.out1 = wsp(o.out1_off); ep.out1_ld = o.out1_ld;
+      ep.out0 = wsp(o.out0_off); ep.out1 = o.out_split > 0 ? nullptr : wsp(o.out1_off); ep.out1_ld = o.out1_ld;
       ep.relu0 = o.relu0; ep.relu1 = o.relu1;
       if (po.has_tc) return launch_conv_tc(po.tc, n, ep, p->sm_count, st);
       return launch_conv_direct(o.in_dtype, o.w_dtype, o.out_dtype, wsp(o.in0_off), wt + o.w_off, n, geom_of(o), ep, st);

@@ -96,8 +96,9 @@ class DevOp:
     brick: Tuple[int, int, int, int] = (0, 0, 0, 0)
     halo: int = 0
     pair_pool: int = 0
-    out_split: int = 0            # fused sibling 1x1x1 convs: channels >= out_split land out_jump further
-    out_jump: int = 0
+    out_split: int = 0            # fused sibling 1x1x1 convs: columns >= out_split go to out1, >= out_split2 to out2
+    out_split2: int = 0
+    out2: Optional[TRef] = None
     pool_k: Tuple[int, int, int] = (0, 0, 0)
     pool_zero: int = 0
     conv_out_dims: Optional[Tuple[int, int, int]] = None   # conv's own output dims when a pool is fused
@@ -149,7 +150,7 @@ class Plan:
                 s.in0_off = -1
             s.out_dims[:] = tuple(op.conv_out_dims or o0.dims) + (o0.C * (2 if op.pair_pool else 1),)
             s.tc_pair_pool = op.pair_pool
-            s.out_split, s.out_jump = op.out_split, op.out_jump
+            s.out_split, s.out_split2 = op.out_split, op.out_split2
             s.out_ld, s.out_dtype, s.out0_off = o0.ld, o0.dtype, o0.byte_off()
             if op.pool_k[0] > 0:
                 s.pool_k[:] = op.pool_k
@@ -165,6 +166,10 @@ class Plan:
                 s.out1_ld, s.out1_off = op.out1.ld, op.out1.byte_off()
             else:
                 s.out1_off = -1
+            if op.out2 is not None:
+                s.out2_ld, s.out2_off = op.out2.ld, op.out2.byte_off()
+            else:
+                s.out2_off = -1
             s.k[:], s.s[:], s.pad[:] = op.k, op.s, op.pad
             s.relu0, s.relu1, s.pad_is_zero, s.ext_input = op.relu0, op.relu1, op.pad_is_zero, op.ext_input
             s.crop[:] = op.crop
@@ -437,7 +442,7 @@ class Lowerer:
         logits, probs = self.val.get("__logits__"), self.val.get("__probs__")
         # liveness
         for idx, op in enumerate(self.ops):
-            for r in (op.in0, op.in1, op.out0, op.out1):
+            for r in (op.in0, op.in1, op.out0, op.out1, op.out2):
                 if r is not None:
                     r.buf.first = min(r.buf.first, idx)
                     r.buf.last = max(r.buf.last, idx)
@@ -661,9 +666,9 @@ class Lowerer:
     def _fused_siblings(self, node: Node) -> bool:
         """Horizontal fusion of the 1x1x1 convs that read the same tensor (branch 0, 1a, 2a of an Inception
         block, train.py:1048-1193): one GEMM with N = sum of their filters, so the block input is read
-        once instead of three times.  Branch 0 lands in its slice of the concat buffer; the 1a / 2a
-        activations land in scratch channels appended behind the concat channels of the same buffer
-        (ld = concat channels + scratch), where the 3x3x3 convs read them as channel slices."""
+        once instead of three times.  The epilogue stores each column range through its own TMA map:
+        branch 0 into its slice of the concat buffer, the 1a / 2a activations into dense buffers of
+        their own (the 3x3x3 convs that follow re-read them 27 times, so they must stay contiguous)."""
         if not (self.use_tc and self.fuse_siblings):
             return False
 
@@ -679,22 +684,22 @@ class Lowerer:
             return False
         chains = [self._conv_chain(n) for n in sibs]
         placed = [i for i, ch in enumerate(chains) if ch[2] in self.place]
-        if len(placed) != 1 or len({ch[1] for ch in chains}) != 1:
+        if len(placed) != 1 or len(sibs) > 3 or len({ch[1] for ch in chains}) != 1:
             return False
         order = placed + [i for i in range(len(sibs)) if i != placed[0]]
         sibs, chains = [sibs[i] for i in order], [chains[i] for i in order]
         cos = [n.attrs["filters"] for n in sibs]
-        cname, coff = self.place[chains[0][2]]
-        if coff != 0 or cname in self.concat_ref or cos[0] % 16 or any(c % 8 for c in cos):
+        if cos[0] % 16 or (len(cos) == 3 and cos[1] % 16) or any(c % 8 for c in cos):
+            return False
+        if any(ch[2] in self.place for ch in chains[1:]):
             return False
         co = sum(cos)
         if not self._tc_ok(x, co, (1, 1, 1), self.act, None):
             return False
         out_dims = tuple(node.out_shape[:3])
-        ctot = self.g.shape(cname)[-1]
-        ld = ctot + co - cos[0]
-        buf = self.new_buf(cname, out_dims, ld, self.act)
-        self.concat_ref[cname] = TRef(buf, 0, ctot, ld, out_dims, self.act)
+        outs = [self.out_ref(ch[2], out_dims, c, self.act) for ch, c in zip(chains, cos)]
+        if any(o.ld % 8 or o.coff % 8 for o in outs):
+            return False
         kernel = np.concatenate([self.w[n.name][0] for n in sibs], axis=-1)
         scales, shifts = [], []
         for n, ch, c in zip(sibs, chains, cos):
@@ -704,31 +709,31 @@ class Lowerer:
             shifts.append(np.zeros(c, np.float32) if sh is None else sh)
         fl = self.g.conv_dense_flops()
         layers = tuple(l for ch in chains for l in ch[3])
-        op = DevOp(rt.OP_CONV3D, "+".join(n.name for n in sibs), x, None, TRef(buf, 0, co, ld, out_dims, self.act),
-                   k=(1, 1, 1), s=(1, 1, 1), pad=(0, 0, 0), relu0=int(chains[0][1]), layers=layers,
-                   flops=sum(fl[n.name] for n in sibs))
+        o0 = outs[0]
+        op = DevOp(rt.OP_CONV3D, "+".join(n.name for n in sibs), x, None,
+                   TRef(o0.buf, o0.coff, co, o0.ld, out_dims, self.act), outs[1], k=(1, 1, 1), s=(1, 1, 1), pad=(0, 0, 0),
+                   relu0=int(chains[0][1]), layers=layers, flops=sum(fl[n.name] for n in sibs))
         op.scale0, op.shift0 = self.fblob(np.concatenate(scales)), self.fblob(np.concatenate(shifts))
-        op.out_split, op.out_jump = cos[0], ctot - cos[0]
+        op.out_split = cos[0]
+        if len(cos) == 3:
+            op.out_split2, op.out2 = cos[0] + cos[1], outs[2]
         kc = choose_kc(x.C)
         op.brick = choose_brick(self.nb, *out_dims)
         m_tiles = (-(-self.nb // op.brick[0]) * -(-out_dims[0] // op.brick[1]) * -(-out_dims[1] // op.brick[2])
                    * -(-out_dims[2] // op.brick[3]))
         bn, n_tiles = choose_bn(co, m_tiles if self.balance_n else 0)
-        # a TMA store chunk (64 / 32 / 16 channels) must divide both the N tile and the split: widen the
+        # a TMA store chunk (64 / 32 / 16 channels) must divide the N tile and both splits: widen the
         # tile to the next multiple of 64 or 32 when that costs < 15 % padded columns (wider stores win)
         for gran in (64, 32):
             wide = _round_up(bn, gran)
-            if cos[0] % gran == 0 and wide <= 256 and wide * n_tiles <= 1.15 * co:
+            if (op.out_split % gran == 0 and op.out_split2 % gran == 0 and wide <= 256
+                    and wide * n_tiles <= 1.15 * co):
                 bn = wide
                 break
         op.engine, op.w_dtype, op.kc, op.bn = rt.ENGINE_TCGEN05, rt.BF16, kc, bn
         op.w_blob = self.blob(pack_tc_weights(kernel, kc, bn, n_tiles))
         self.emit(op)
-        off = 0
-        for i, (ch, c) in enumerate(zip(chains, cos)):
-            ref = TRef(buf, 0 if i == 0 else ctot + off, c, ld, out_dims, self.act)
-            if i > 0:
-                off += c
+        for ch, ref in zip(chains, outs):
             for l in ch[3]:
                 self.val[l] = ref
                 self.done.add(l)

@@ -37,8 +37,8 @@ class CseOp(C.Structure):
         ("kc", C.c_int32), ("bn", C.c_int32), ("brick", C.c_int32 * 4),
         ("pre_mean", C.c_float * 4), ("pre_scale", C.c_float * 4),
         ("in_wpitch", C.c_int32), ("out_wpitch", C.c_int32), ("out_wpad", C.c_int32), ("pre_unroll_w", C.c_int32), ("pool_k", C.c_int32 * 3), ("pool_dims", C.c_int32 * 3), ("pool_zero", C.c_int32),
-        ("tc_halo", C.c_int32), ("tc_pair_pool", C.c_int32), ("out_split", C.c_int32), ("out_jump", C.c_int32), ("pre_s2d", C.c_int32),
-        ("in0_off", C.c_int64), ("in1_off", C.c_int64), ("out0_off", C.c_int64), ("out1_off", C.c_int64),
+        ("tc_halo", C.c_int32), ("tc_pair_pool", C.c_int32), ("out_split", C.c_int32), ("out_split2", C.c_int32), ("out2_ld", C.c_int32), ("pre_s2d", C.c_int32),
+        ("in0_off", C.c_int64), ("in1_off", C.c_int64), ("out0_off", C.c_int64), ("out1_off", C.c_int64), ("out2_off", C.c_int64),
         ("w_off", C.c_int64), ("scale0_off", C.c_int64), ("shift0_off", C.c_int64),
         ("scale1_off", C.c_int64), ("shift1_off", C.c_int64),
     ]

@@ -96,14 +96,18 @@ typedef struct cse_op {
                                 [n,T,H,W/2,16], GEMM row = 2 neighbouring output pixels, out_dims = D,H,W/2,2*Cout, weights
                                 [2*Cout][taps*16]; MaxPooling3D (1,2,2) is done in registers, pool_k = (1,2,1) in this
                                 view, out0 = pooled [n, pool_dims, Cout]; bias (+ReLU) epilogue only */
-  int32_t out_split, out_jump;/* TCGEN05: > 0 = horizontally fused sibling 1x1x1 convs of an Inception block
-                                (train.py:1048-1193): output channels [0, out_split) are stored at out0's channel offset
-                                (branch 0, inside the concat buffer), channels >= out_split out_jump channels further
-                                (the branch-1a / 2a activations, kept in scratch channels behind the concat) */
+  int32_t out_split, out_split2, out2_ld;
+                             /* TCGEN05: out_split > 0 = horizontally fused sibling 1x1x1 convs of an Inception block
+                                (train.py:1048-1193), one GEMM whose output columns go to up to three tensors: columns
+                                [0, out_split) -> out0 (branch 0, a channel slice of the concat buffer); columns
+                                [out_split, out_split2 or Cout) -> the tensor at out1_off / out1_ld (branch 1a), starting at
+                                its channel 0; columns [out_split2, Cout) -> the tensor at out2_off / out2_ld (branch 2a)
+                                when out_split2 > 0.  One epilogue (scale0 / shift0 / relu0) for all columns; out1 is
+                                then NOT a second epilogue output */
   int32_t pre_s2d;           /* PREPROCESS: 1 = 2x2 space-to-depth over (H,W) for the stride-2 7x7x7 stems: out_dims =
                                 T, ceil(H/2), ceil(W/2); cell channel (ph*2+pw)*C + c, zero-padded to out_ld = 8/16 */
   int64_t in0_off, in1_off;  /* workspace byte offsets (-1 = none); in1 = residual for CONV3D, 2nd addend for ADD */
-  int64_t out0_off, out1_off;
+  int64_t out0_off, out1_off, out2_off;
   int64_t w_off;             /* weight-arena byte offsets (-1 = none) */
   int64_t scale0_off, shift0_off;   /* fp32 [Cout]: y = acc*scale0 + shift0 (+ in1); out0 = relu0?(y) */
   int64_t scale1_off, shift1_off;   /* fp32 [Cout]: out1 = relu1?(y*scale1 + shift1) */

@@ -151,15 +151,15 @@ def test_conv_tcgen05_vs_oracle(dhw, cin, cout, k, nb):
 
 
 SIBLING_CASES = [((4, 14, 14), 64, (32, 48, 16, 24, 8, 16), 3),      # split 32 -> 64-wide chunks shrink to 32
-                 ((3, 9, 11), 40, (112, 24, 32, 8, 16, 8), 2),      # split 112 -> 16-wide chunks, ragged bricks
+                 ((3, 9, 11), 40, (112, 48, 32, 8, 16, 8), 2),      # split 112 -> 16-wide chunks, ragged bricks
                  ((2, 7, 7), 256, (256, 160, 64, 32, 32, 16), 5)]   # two N tiles, split on a tile boundary or not
 
 
 @pytest.mark.parametrize("dhw,cin,f,nb", SIBLING_CASES)
 def test_conv_tcgen05_fused_siblings(dhw, cin, f, nb):
     """Inception block (train.py:1048-1064): the three 1x1x1 convs reading the block input run as ONE
-    tcgen05 GEMM whose output columns are split between the concat slice (branch 0) and scratch
-    channels behind it (1a, 2a); every branch and the concat must match the oracle."""
+    tcgen05 GEMM whose output columns are stored to three tensors (branch 0 into its concat slice, 1a and
+    2a into dense buffers of their own); every branch and the concat must match the oracle."""
     from cse_b200.graph import _conv3d_bn
     k1, k3, s1 = (1, 1, 1), (3, 3, 3), (1, 1, 1)
 
