@@ -53,33 +53,56 @@ def _resize(frame: np.ndarray, width: int, height: int) -> np.ndarray:
     return cv2.resize(frame, (width, height))
 
 
-def load_rgb_clip(path: str, t: int, h: int, w: int) -> np.ndarray:
-    """-> uint8 [T,H,W,3] BGR (get_onestream_videoclip, train.py:245-291)."""
+def _gray(frame: np.ndarray) -> np.ndarray:
+    """opticalflow_TVL1_retriever (train.py:334-357): every decoded flow frame goes through BGR2GRAY."""
+    if frame.ndim == 2:
+        return frame
+    import cv2
+    return cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
+
+
+def decode_frames(path: str, gray: bool = False) -> List[np.ndarray]:
+    """All frames of a video (OpenCV) or of a pre-decoded ``.npy`` [F,H,W(,C)] uint8 array."""
     path = path.strip()
-    if path.endswith(".npy"):
-        clip = np.load(path)
-        frames = select_frames(list(clip), t)
-    else:
-        frames = select_frames(_read_video(path), t)
-    out = np.asarray([_resize(f, w, h) for f in frames], dtype=np.uint8)
-    if out.shape != (t, h, w, 3):
-        raise ValueError("clip %s decodes to %r, expected %r" % (path, out.shape, (t, h, w, 3)))
+    frames = list(np.load(path)) if path.endswith(".npy") else _read_video(path)
+    return [_gray(f) for f in frames] if gray else frames
+
+
+def _assemble(frames: List[np.ndarray], t: int, h: int, w: int, device=None):
+    """select_frames + resize -> uint8 [T,H,W(,C)].  device=None: on the CPU with cv2 (the reference's
+    own path); otherwise the selected frames are uploaded once and resized by cse_assemble_clip
+    (bit-identical output, csrc/ingest.cu) and the clip stays on the GPU."""
+    sel = select_frames(frames, t)
+    if device is None:
+        return np.asarray([_resize(f, w, h) for f in sel], dtype=np.uint8)
+    from . import runtime as rt
+    torch = rt.require_cuda()
+    if len(sel) < t:
+        raise ValueError("video has %d frames, select_frames keeps %d < %d" % (len(frames), len(sel), t))
+    src = torch.from_numpy(np.ascontiguousarray(np.asarray(sel, dtype=np.uint8))).to(device)
+    with torch.cuda.device(src.device):
+        return rt.assemble_clip(src, t, h, w)
+
+
+def load_rgb_clip(path: str, t: int, h: int, w: int, device=None):
+    """-> uint8 [T,H,W,3] BGR (get_onestream_videoclip, train.py:245-291); numpy, or a CUDA tensor
+    when `device` is given."""
+    out = _assemble(decode_frames(path), t, h, w, device)
+    if tuple(out.shape) != (t, h, w, 3):
+        raise ValueError("clip %s decodes to %r, expected %r" % (path, tuple(out.shape), (t, h, w, 3)))
     return out
 
 
-def load_flow_clip(xpath: str, ypath: str, t: int, h: int, w: int) -> np.ndarray:
-    """-> uint8 [T,H,W,2] from two gray flow videos (TV-L1, train.py:196-221)."""
-    chans = []
-    for p in (xpath.strip(), ypath.strip()):
-        if p.endswith(".npy"):
-            frames = list(np.load(p))
-        else:
-            frames = [f[..., 0] if f.ndim == 3 else f for f in _read_video(p)]
-        frames = select_frames(frames, t)
-        chans.append(np.asarray([_resize(f, w, h) for f in frames], dtype=np.uint8))
-    out = np.stack(chans, axis=-1)
-    if out.shape != (t, h, w, 2):
-        raise ValueError("flow clip decodes to %r, expected %r" % (out.shape, (t, h, w, 2)))
+def load_flow_clip(xpath: str, ypath: str, t: int, h: int, w: int, device=None):
+    """-> uint8 [T,H,W,2] from two gray flow videos (TV-L1, train.py:196-221, 334-357)."""
+    chans = [_assemble(decode_frames(p, gray=True), t, h, w, device) for p in (xpath, ypath)]
+    if device is None:
+        out = np.stack(chans, axis=-1)
+    else:
+        import torch
+        out = torch.stack(chans, dim=-1).contiguous()
+    if tuple(out.shape) != (t, h, w, 2):
+        raise ValueError("flow clip decodes to %r, expected %r" % (tuple(out.shape), (t, h, w, 2)))
     return out
 
 
@@ -88,7 +111,10 @@ class ClipSequence:
 
     def __init__(self, video_data, model_type, input_shape, num_classes, batch_size=1,
                  optical_flow_status="TVL1_precomputed", augmentation_status="non_augmented",
-                 augmentation_frequency=0, shuffle=False):
+                 augmentation_frequency=0, shuffle=False, device=None):
+        """device: None = clips are assembled on the CPU and returned as numpy arrays (the reference's
+        behaviour); a CUDA device = frames are resized on that GPU and x is returned as uint8 CUDA
+        tensors, which Member.predict / predict_generator take directly."""
         if shuffle or augmentation_status != "non_augmented":
             raise ValueError("evaluation clips are ordered and non-augmented")
         if model_type == "TWOSTREAM_I3D" and optical_flow_status != "TVL1_precomputed":
@@ -98,6 +124,7 @@ class ClipSequence:
         self.input_shape = tuple(input_shape)
         self.num_classes = num_classes
         self.batch_size = int(batch_size)
+        self.device = device
         self.n = int(video_data.count().iloc[0]) if hasattr(video_data.count(), "iloc") else int(video_data.count()[0])
 
     def __len__(self):
@@ -110,9 +137,14 @@ class ClipSequence:
         labels = np.asarray([vd["class"].values[i] for i in idx], dtype=int)
         onehot = np.zeros((len(labels), self.num_classes), np.float32)
         onehot[np.arange(len(labels)), labels % self.num_classes] = 1.0
-        rgb = np.stack([load_rgb_clip(vd["rgbclips_path"].values[i], t, h, w) for i in idx])
+        if self.device is None:
+            stack = np.stack
+        else:
+            import torch
+            stack = torch.stack
+        rgb = stack([load_rgb_clip(vd["rgbclips_path"].values[i], t, h, w, self.device) for i in idx])
         if self.model_type == "TWOSTREAM_I3D":
-            flow = np.stack([load_flow_clip(vd["x_axis_flowclips_path"].values[i],
-                                            vd["y_axis_flowclips_path"].values[i], t, h, w) for i in idx])
+            flow = stack([load_flow_clip(vd["x_axis_flowclips_path"].values[i],
+                                         vd["y_axis_flowclips_path"].values[i], t, h, w, self.device) for i in idx])
             return [rgb, flow], onehot
         return rgb, onehot

@@ -306,6 +306,15 @@ def _gather_rows(local: np.ndarray, n: int, dist, rank: int, world: int) -> np.n
     return np.concatenate([o[:, :s].cpu().numpy() for o, s in zip(out, sizes)], axis=1)
 
 
+def _clip_device():
+    """Where clips are assembled (select_frames + resize): on the GPU that runs the members
+    (cse_assemble_clip, bit-identical to cv2.resize) unless CSE_CPU_RESIZE=1 asks for the cv2 path."""
+    if os.environ.get("CSE_CPU_RESIZE", "0") == "1":
+        return None
+    import torch
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _load_members(model_type, member_paths, input_shape, nb_classes, batch):
     """All members of one test fold on this GPU, sharing one activation workspace."""
     from .ensemble_runtime import DeviceEnsemble
@@ -330,8 +339,9 @@ def _predict_members(ens, generator, n_clips, dist_state, chunk):
         if not pend:
             return
         ninp = len(pend[0])
-        xs = [np.concatenate([p[j] for p in pend]) for j in range(ninp)]
-        dev = [torch.from_numpy(np.ascontiguousarray(x)).to(ens.device) for x in xs]
+        dev = [torch.cat([p[j] for p in pend]).to(ens.device).contiguous() if torch.is_tensor(pend[0][j])
+               else torch.from_numpy(np.ascontiguousarray(np.concatenate([p[j] for p in pend]))).to(ens.device)
+               for j in range(ninp)]
         n = ens.forward_members(dev)
         out[:, pos:pos + n] = ens.probs[:, :n].cpu().numpy()
         pos += n
@@ -345,7 +355,7 @@ def _predict_members(ens, generator, n_clips, dist_state, chunk):
         keep = [i for i in range(xs[0].shape[0]) if mine[0] <= lo + i <= mine[-1]]
         if not keep:
             continue
-        xs = [np.asarray(v)[keep] for v in xs]
+        xs = [v[keep] if torch.is_tensor(v) else np.asarray(v)[keep] for v in xs]
         while xs[0].shape[0]:
             take = min(chunk - pend_n, xs[0].shape[0])
             pend.append([v[:take] for v in xs])
@@ -381,7 +391,7 @@ def store_probabilities(trained_models_folder, results_folder, involved_sets, ba
         sample_input = zoo.define_input(model_type)
         generator = ClipSequence(data, model_type, sample_input.shape, nb_classes, batch_size=1,
                                  optical_flow_status=optical_flow_status, augmentation_status="non_augmented",
-                                 augmentation_frequency=0, shuffle=False)
+                                 augmentation_frequency=0, shuffle=False, device=_clip_device())
         val_folds_indices = [i for i in test_folds_indices if i != test_index]
         member_paths = [os.path.join(data_folder, models_name + "_split_test" + str(test_index) + "_val" +
                                      str(v) + "_weights.hdf5") for v in val_folds_indices]

@@ -133,7 +133,11 @@ class Member:
 
     # ---- host-level API -------------------------------------------------------- #
     @staticmethod
-    def _as_u8(x) -> np.ndarray:
+    def _as_u8(x):
+        if hasattr(x, "is_cuda"):              # torch tensor: clips assembled on the GPU (clips.ClipSequence(device=...))
+            if not (x.is_cuda and str(x.dtype) == "torch.uint8"):
+                raise ValueError("tensor clips must be uint8 CUDA tensors")
+            return x.contiguous()
         a = np.asarray(x)
         if a.dtype == np.uint8:
             return np.ascontiguousarray(a)
@@ -152,7 +156,8 @@ class Member:
         logits = np.empty((n, self.nb_classes), np.float32)
         with torch.cuda.device(self.device):
             for i in range(0, n, bs):
-                dev = [torch.from_numpy(v[i:i + bs]).to(self.device, non_blocking=False) for v in xs]
+                dev = [v[i:i + bs].to(self.device).contiguous() if hasattr(v, "is_cuda")
+                       else torch.from_numpy(v[i:i + bs]).to(self.device, non_blocking=False) for v in xs]
                 lg, pr = self.forward_device(dev)
                 probs[i:i + bs] = pr.cpu().numpy()
                 logits[i:i + bs] = lg.cpu().numpy()
@@ -173,7 +178,8 @@ class Member:
             if not pend:
                 return
             ninp = len(pend[0])
-            cat = [np.concatenate([p[j] for p in pend], axis=0) for j in range(ninp)]
+            cat = [self.torch.cat([p[j] for p in pend], dim=0) if hasattr(pend[0][j], "is_cuda")
+                   else np.concatenate([p[j] for p in pend], axis=0) for j in range(ninp)]
             outs.append(self.predict(cat if ninp > 1 else cat[0]))
             pend.clear()
 

@@ -21,7 +21,8 @@ OP_NAMES = {1: "preprocess", 2: "conv3d", 3: "maxpool3d", 4: "avgpool3d", 5: "af
 EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_plan_create", "cse_plan_add_op",
            "cse_plan_finalize", "cse_plan_run", "cse_plan_run_from", "cse_plan_num_input_ops", "cse_plan_run_range",
            "cse_plan_num_ops",
-           "cse_plan_last_launches", "cse_plan_destroy", "cse_preprocess", "cse_vote", "cse_vote_search"]
+           "cse_plan_last_launches", "cse_plan_destroy", "cse_preprocess", "cse_vote", "cse_vote_search",
+           "cse_assemble_clip"]
 
 
 class CseOp(C.Structure):
@@ -79,6 +80,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), vp, i32, i32, vp]
     lib.cse_vote.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.cse_vote_search.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.cse_assemble_clip.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.cse_abi_version() != 1:
@@ -168,3 +170,20 @@ def vote_search(probs_f64, weight_matrix, labels):
                               labels.contiguous().data_ptr(), w, m, n, c, correct.data_ptr(),
                               current_stream_ptr()))
     return correct
+
+
+def assemble_clip(frames_u8, t: int, h: int, w: int, out=None):
+    """Decoded frames of one video, uint8 device tensor [n_frames, Hs, Ws(, C)] -> uint8 [T, H, W(, C)]:
+    select_frames + cv2.resize (train.py:132-145, 286), bit-exact with OpenCV's 8-bit INTER_LINEAR."""
+    torch = require_cuda()
+    lib = load_library()
+    assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+    assert frames_u8.dim() in (3, 4)
+    n, hs, ws = frames_u8.shape[:3]
+    c = frames_u8.shape[3] if frames_u8.dim() == 4 else 1
+    shape = (t, h, w) + ((c,) if frames_u8.dim() == 4 else ())
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=frames_u8.device)
+    assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == shape
+    check(lib.cse_assemble_clip(frames_u8.data_ptr(), n, hs, ws, c, out.data_ptr(), t, h, w, current_stream_ptr()))
+    return out

@@ -171,6 +171,14 @@ int  cse_vote_search(const double* d_probs /*[M,N,C]*/, const double* d_weights 
                      const int32_t* d_labels /*[N]*/, int W, int M, int N, int C,
                      int32_t* d_correct, void* stream);
 
+/* ---- clip assembly: replaces select_frames + cv2.resize of get_onestream_videoclip / get_twostream_videoclip ---- */
+/* (train.py:132-145, 279-291, 196-221).  d_frames: the decoded frames of one video, uint8
+ * [n_frames, Hs, Ws, C] (BGR, or gray flow frames), C <= 4.  Keeps frames t*step, t < T, step = max(1, n_frames / T)
+ * and resizes each to H x W exactly like OpenCV's INTER_LINEAR on CV_8U (11-bit fixed point): d_clip uint8 [T, H, W, C]
+ * is bit-identical to the reference's CPU result.  Fails when select_frames would keep fewer than T frames. */
+int  cse_assemble_clip(const uint8_t* d_frames, int n_frames, int Hs, int Ws, int C,
+                       uint8_t* d_clip, int T, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

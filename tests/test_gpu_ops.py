@@ -569,3 +569,47 @@ def test_vote_search_counts():
                          torch.from_numpy(labels).cuda()).cpu().numpy()
     exp = np.array([(OV.ensemble_predictions(p, wm[i]) == labels).sum() for i in range(wn)])
     assert np.array_equal(got, exp)
+
+
+# --------------------------------------------------------------------------- clip assembly
+def test_assemble_clip_bit_exact_vs_oracle_and_cv2():
+    """cse_assemble_clip (select_frames + cv2.resize INTER_LINEAR on uint8, train.py:132-145, 286) vs the
+    numpy restatement (itself pinned against cv2 in tests/test_oracle_resize.py): bit-exact."""
+    from oracle import resize as R
+    rng = np.random.default_rng(21)
+    cases = [(37, 90, 122, 3, 16, 112, 112), (16, 360, 640, 3, 16, 112, 112), (70, 120, 160, 3, 64, 224, 224),
+             (25, 48, 64, 1, 20, 224, 224), (9, 33, 17, 2, 4, 7, 150), (5, 1, 1, 4, 5, 3, 3), (40, 224, 224, 3, 20, 224, 224),
+             (33, 448, 448, 3, 16, 224, 224), (7, 50, 300, 3, 7, 131, 9)]
+    for (n, hs, ws, c, t, h, w) in cases:
+        frames = rng.integers(0, 256, (n, hs, ws, c) if c > 1 else (n, hs, ws), dtype=np.uint8)
+        got = rt.assemble_clip(torch.from_numpy(frames).cuda(), t, h, w).cpu().numpy()
+        exp = R.assemble_clip(list(frames), t, h, w)
+        assert got.shape == exp.shape and np.array_equal(got, exp), (n, hs, ws, c, t, h, w)
+    with pytest.raises(rt.CseError):          # select_frames would keep 3 < 16 frames
+        rt.assemble_clip(torch.zeros((3, 8, 8, 3), dtype=torch.uint8).cuda(), 16, 8, 8)
+
+
+def test_assemble_clip_equals_reference_golden_and_feeds_predict():
+    """The committed videos, decoded on the host, assembled on the GPU == the reference's own
+    get_onestream_videoclip / get_twostream_videoclip outputs (tests/golden/clips_golden.npz)."""
+    import hashlib
+    import os
+    from cse_b200 import clips
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(gold, "clips_golden.npz"))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for tag in ("small", "up", "c3d", "i3d"):
+        t, h, w = (int(v) for v in g["shape_" + tag])
+        rgb = clips.load_rgb_clip(os.path.join(gold, "clip_rgb.avi"), t, h, w, device=dev)
+        flow = clips.load_flow_clip(os.path.join(gold, "clip_flow_x.avi"), os.path.join(gold, "clip_flow_y.avi"), t, h, w,
+                                    device=dev)
+        assert rgb.is_cuda and flow.is_cuda
+        for arr, key in ((rgb, "sha_rgb_"), (flow, "sha_flow_")):
+            digest = np.frombuffer(hashlib.sha256(arr.cpu().numpy().tobytes()).digest(), np.uint8)
+            assert np.array_equal(digest, g[key + tag]), (tag, key)
+    # a GPU-assembled clip goes straight into Member.predict and gives the same probabilities as the numpy clip
+    m = Member(G.build_model_graph("C3D", (16, 112, 112, 3), 11), synthetic_weights(G.build_model_graph("C3D", (16, 112, 112, 3), 11), seed=3),
+               precision="bf16", max_batch=2)
+    clip_dev = clips.load_rgb_clip(os.path.join(gold, "clip_rgb.avi"), 16, 112, 112, device=dev)[None]
+    clip_np = clips.load_rgb_clip(os.path.join(gold, "clip_rgb.avi"), 16, 112, 112)[None]
+    assert np.array_equal(m.predict(clip_dev), m.predict(clip_np))
