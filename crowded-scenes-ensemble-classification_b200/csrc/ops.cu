@@ -839,7 +839,7 @@ preprocess_kernel(const uint8_t* __restrict__ src, TO* __restrict__ out, long lo
 // contiguous, aligned K=16 chunk per pixel.
 // NB = 3: per output pixel w, neighbours w-1..w+1.  NB = 4 ("pair" mode, pair-packed stem): the
 // output element is the pixel pair p = (2p, 2p+1) carrying pixels 2p-1..2p+2; a.Wo = number of pairs.
-template <int NB>
+template <int NB, int C>
 __global__ void __launch_bounds__(256)
 preprocess_unroll_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, long long total,
                          PreArgs a) {
@@ -858,10 +858,9 @@ preprocess_unroll_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restr
   for (int j = 0; j < NB; ++j) {
     const int ws = (NB == 4 ? 2 * w : w) - 1 + j;
     if (ws >= 0 && ws < wlim) {
-      const uint8_t* s = src + (row + ws) * a.C;
+      const uint8_t* s = src + (row + ws) * C;        // C is a template constant: v[] stays in registers
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < a.C) v[j * a.C + c] = __float2bfloat16_rn(((float)s[c] - a.mean[c]) * a.scale[c]);
+      for (int c = 0; c < C; ++c) v[j * C + c] = __float2bfloat16_rn(((float)__ldg(s + c) - a.mean[c]) * a.scale[c]);
     }
   }
   uint4* o = reinterpret_cast<uint4*>(out + idx * 16);
@@ -874,7 +873,7 @@ preprocess_unroll_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restr
 // x C channels, packed (ph*2+pw)*C + c and zero-padded to out_ld (8 or 16) channels; pixels outside
 // the frame and the wpad / right pad columns of the row are zeros.  A stride-2 window of 7 (+1
 // zero-weighted) input columns then is 4 neighbouring cells = one contiguous K chunk per pixel.
-template <int CL>
+template <int CL, int C>
 __global__ void __launch_bounds__(256)
 preprocess_s2d_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, long long total,
                       PreArgs a) {
@@ -893,15 +892,15 @@ preprocess_s2d_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict
     for (int ph = 0; ph < 2; ++ph) {
       const int hs = 2 * h2 + ph;
       if (hs >= a.H) continue;
-      const uint8_t* row = src + (((nn * a.T + d) * a.H + hs) * a.W) * a.C;
+      const uint8_t* row = src + (((nn * a.T + d) * a.H + hs) * a.W) * C;
 #pragma unroll
       for (int pw = 0; pw < 2; ++pw) {
         const int ws = 2 * w2 + pw;
         if (ws >= a.W) continue;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < a.C && (ph * 2 + pw) * a.C + c < CL)
-            v[(ph * 2 + pw) * a.C + c] = __float2bfloat16_rn(((float)row[ws * a.C + c] - a.mean[c]) * a.scale[c]);
+        for (int c = 0; c < C; ++c)
+          if ((ph * 2 + pw) * C + c < CL)
+            v[(ph * 2 + pw) * C + c] = __float2bfloat16_rn(((float)__ldg(row + ws * C + c) - a.mean[c]) * a.scale[c]);
       }
     }
   }
@@ -931,13 +930,19 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
     const long long total = (long long)n * To * Ho * wpitch;
     if (total == 0) return CSE_OK;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (out_ld == 16) preprocess_s2d_kernel<16><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
-    else preprocess_s2d_kernel<8><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
+#define S2D_CASE(CL_, C_) preprocess_s2d_kernel<CL_, C_><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a)
+    if (out_ld == 16) {
+      switch (C) { case 1: S2D_CASE(16, 1); break; case 2: S2D_CASE(16, 2); break; case 3: S2D_CASE(16, 3); break; default: S2D_CASE(16, 4); }
+    } else {
+      switch (C) { case 1: S2D_CASE(8, 1); break; default: S2D_CASE(8, 2); }
+    }
+#undef S2D_CASE
     CSE_CUDA(cudaGetLastError());
     return CSE_OK;
   }
   if (unroll_w > 0) {
-    CSE_REQUIRE((unroll_w == 3 || unroll_w == 4) && out_dt == CSE_BF16 && out_ld == 16 && C * unroll_w <= 16 && wpitch <= 0,
+    CSE_REQUIRE((unroll_w == 3 || unroll_w == 4) && out_dt == CSE_BF16 && out_ld == 16 && C >= 1 && C <= 4 && C * unroll_w <= 16 &&
+                    wpitch <= 0,
                 "preprocess: unroll_w supports 3 (pixel) / 4 (pixel pair), bf16, out_ld=16, C*unroll_w<=16");
     CSE_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + To <= T && h0 + Ho <= H &&
                     w0 + (unroll_w == 4 ? 2 * Wo - 1 : Wo) <= W,
@@ -951,10 +956,14 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
     }
     const long long total = (long long)n * To * Ho * Wo;
     if (total == 0) return CSE_OK;
-    if (unroll_w == 4)
-      preprocess_unroll_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
-    else
-      preprocess_unroll_kernel<3><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a);
+#define UNR_CASE(NB_, C_) \
+  preprocess_unroll_kernel<NB_, C_><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a)
+    if (unroll_w == 4) {
+      switch (C) { case 1: UNR_CASE(4, 1); break; case 2: UNR_CASE(4, 2); break; case 3: UNR_CASE(4, 3); break; default: UNR_CASE(4, 4); }
+    } else {
+      switch (C) { case 1: UNR_CASE(3, 1); break; case 2: UNR_CASE(3, 2); break; case 3: UNR_CASE(3, 3); break; default: UNR_CASE(3, 4); }
+    }
+#undef UNR_CASE
     CSE_CUDA(cudaGetLastError());
     return CSE_OK;
   }
