@@ -326,6 +326,17 @@ def run_ours(args):
             with open(args.profile_out, "w") as f:
                 json.dump({"workload": args.workload, "batch": batch, "members": members, "micro_batch": ens.micro_batch,
                            "ops": prof}, f, indent=1)
+        # HBM-bound kernels of the path (pre-processing, pooling): algorithmic bytes / CUDA-event time
+        hbm = {}
+        for p_ in prof:
+            if p_.get("bytes", 0) > 0 and p_["ms"] > 0:
+                k_ = hbm.setdefault(p_["kind"], {"bytes": 0.0, "ms": 0.0, "launch_groups": 0})
+                k_["bytes"] += p_["bytes"]; k_["ms"] += p_["ms"]; k_["launch_groups"] += 1
+        roofline["hbm_kernels"] = [{"kind": k_, "ops": v_["launch_groups"], "ms": round(v_["ms"], 3),
+                                    "achieved_gbs": round(v_["bytes"] / (v_["ms"] / 1e3) / 1e9, 1),
+                                    "peak_gbs": peaks["hbm_gbs"],
+                                    "frac": round(v_["bytes"] / (v_["ms"] / 1e3) / 1e9 / peaks["hbm_gbs"], 3)}
+                                   for k_, v_ in sorted(hbm.items())]
         top = sorted(prof, key=lambda p: -p["ms"])[:6]
         roofline["top_ops"] = [{"op": p["name"], "engine": p["engine"], "ms": round(p["ms"], 3),
                                 "tflops": round(p["flops"] / (p["ms"] / 1e3) / 1e12, 1) if p["ms"] > 0 else 0}

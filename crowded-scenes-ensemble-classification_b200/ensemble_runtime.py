@@ -125,9 +125,28 @@ class DeviceEnsemble:
         out = []
         eng = {0: "", 1: "direct", 2: "tcgen05"}
         for k, op in enumerate(plan.ops):
+            shared = self.share_input and k < n_input_ops
             out.append({"name": op.name, "kind": rt.OP_NAMES[op.kind], "engine": eng[op.engine],
-                        "ms": acc[k] / iters, "flops": op.flops * n * self.M})
+                        "ms": acc[k] / iters, "flops": op.flops * n * self.M,
+                        "bytes": _algorithmic_bytes(op) * n * (1 if shared else self.M)})
         return out
+
+
+def _algorithmic_bytes(op) -> float:
+    """Algorithmic HBM bytes per clip of the HBM-bound ops: preprocess = uint8 clip read +
+    layout bytes written; pool / affine / add = (input + output elements) x element size.  0 for convs
+    (they are reported against the tensor roofline)."""
+    def elems(r):
+        return float(np.prod(r.dims)) * r.C
+    if op.kind == rt.OP_PREPROCESS:
+        t, h, w, c = op.src_dims
+        o = op.out0
+        return float(t * h * w * c) + float(o.dims[0] * o.dims[1] * (o.wpitch or o.dims[2]) * o.ld * o.esize)
+    if op.kind in (rt.OP_MAXPOOL3D, rt.OP_AVGPOOL3D, rt.OP_AFFINE):
+        return elems(op.in0) * op.in0.esize + elems(op.out0) * op.out0.esize
+    if op.kind == rt.OP_ADD:
+        return (elems(op.in0) + elems(op.in1)) * op.in0.esize + elems(op.out0) * op.out0.esize
+    return 0.0
 
 
 class HeteroEnsemble:
