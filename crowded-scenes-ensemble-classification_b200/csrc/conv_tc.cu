@@ -104,16 +104,65 @@ __device__ __forceinline__ void tc_commit(uint32_t pred, uint32_t bar) {
                "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(pred)
                : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t pred, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(pred)
-      : "memory");
+// NK consecutive K=16 MMAs of one pipeline stage chunk in ONE asm block: the descriptors only differ in their
+// 14-bit start address (+2 per 32-byte K step), so they are rebuilt from a 32-bit low word and the constant
+// high word inside the block.  The MMA warp then spends ~3 instructions per MMA instead of ~12 (64-bit adds,
+// vector->uniform moves and predicate votes per call), which matters for N = 64 tiles (32-48 cycles each).
+#define CSE_MMA_STEP                                                        \
+  "add.u32 al, al, 2;\n\tadd.u32 bl, bl, 2;\n\t"                           \
+  "mov.b64 da, {al, %3};\n\tmov.b64 db, {bl, %3};\n\t"                     \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+template <int NK>
+__device__ __forceinline__ void tc_mma_k(uint32_t pred, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi32,
+                                         uint32_t idesc, uint32_t accumulate_first) {
+  static_assert(NK == 1 || NK == 2 || NK == 4, "K steps per stage chunk");
+#define CSE_MMA_HEAD                                                        \
+  "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"   \
+  "setp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\tsetp.eq.b32 t, %6, %6;\n\t" \
+  "mov.b32 al, %1;\n\tmov.b32 bl, %2;\n\t"                                 \
+  "mov.b64 da, {al, %3};\n\tmov.b64 db, {bl, %3};\n\t"                     \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+  if (NK == 1)
+    asm volatile(CSE_MMA_HEAD "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi32), "r"(idesc), "r"(accumulate_first), "r"(pred) : "memory");
+  else if (NK == 2)
+    asm volatile(CSE_MMA_HEAD CSE_MMA_STEP "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi32), "r"(idesc), "r"(accumulate_first), "r"(pred) : "memory");
+  else
+    asm volatile(CSE_MMA_HEAD CSE_MMA_STEP CSE_MMA_STEP CSE_MMA_STEP "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi32), "r"(idesc), "r"(accumulate_first), "r"(pred) : "memory");
+#undef CSE_MMA_HEAD
 }
+// Four taps x NK K-steps (the kh taps of an h-halo stage: tap t reads A at a_lo + t*a_step, B at b_lo + t*b_step)
+// in one asm block: 4*NK back-to-back MMAs with one operand set-up.
+#define CSE_MMA_TAP(FIRST_PRED)                                                   \
+  "mov.b32 al, ab;\n\tmov.b32 bl, bb;\n\t"                                       \
+  "mov.b64 da, {al, %3};\n\tmov.b64 db, {bl, %3};\n\t"                           \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, " FIRST_PRED ";\n\t"
+#define CSE_MMA_NEXT_TAP "add.u32 ab, ab, %7;\n\tadd.u32 bb, bb, %8;\n\t"
+template <int NK>
+__device__ __forceinline__ void tc_mma_taps4(uint32_t pred, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi32,
+                                             uint32_t idesc, uint32_t accumulate_first, uint32_t a_step, uint32_t b_step) {
+  static_assert(NK == 1 || NK == 2 || NK == 4, "K steps per stage chunk");
+#define CSE_MMA_HEAD4                                                             \
+  "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl, ab, bb;\n\t" \
+  "setp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\tsetp.eq.b32 t, %6, %6;\n\t"     \
+  "mov.b32 ab, %1;\n\tmov.b32 bb, %2;\n\t"
+#define CSE_MMA_ARGS ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi32), "r"(idesc), "r"(accumulate_first), "r"(pred), "r"(a_step), "r"(b_step) : "memory"
+  if (NK == 1)
+    asm volatile(CSE_MMA_HEAD4 CSE_MMA_TAP("p") CSE_MMA_NEXT_TAP CSE_MMA_TAP("t") CSE_MMA_NEXT_TAP CSE_MMA_TAP("t")
+                 CSE_MMA_NEXT_TAP CSE_MMA_TAP("t") "}" CSE_MMA_ARGS);
+  else if (NK == 2)
+    asm volatile(CSE_MMA_HEAD4 CSE_MMA_TAP("p") CSE_MMA_STEP CSE_MMA_NEXT_TAP CSE_MMA_TAP("t") CSE_MMA_STEP CSE_MMA_NEXT_TAP
+                 CSE_MMA_TAP("t") CSE_MMA_STEP CSE_MMA_NEXT_TAP CSE_MMA_TAP("t") CSE_MMA_STEP "}" CSE_MMA_ARGS);
+  else
+    asm volatile(CSE_MMA_HEAD4 CSE_MMA_TAP("p") CSE_MMA_STEP CSE_MMA_STEP CSE_MMA_STEP CSE_MMA_NEXT_TAP
+                 CSE_MMA_TAP("t") CSE_MMA_STEP CSE_MMA_STEP CSE_MMA_STEP CSE_MMA_NEXT_TAP
+                 CSE_MMA_TAP("t") CSE_MMA_STEP CSE_MMA_STEP CSE_MMA_STEP CSE_MMA_NEXT_TAP
+                 CSE_MMA_TAP("t") CSE_MMA_STEP CSE_MMA_STEP CSE_MMA_STEP "}" CSE_MMA_ARGS);
+#undef CSE_MMA_ARGS
+#undef CSE_MMA_HEAD4
+}
+#undef CSE_MMA_NEXT_TAP
+#undef CSE_MMA_TAP
+#undef CSE_MMA_STEP
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -175,6 +224,12 @@ struct ConvTcArgs {
   int pool_d, pool_h, pool_w;      // fused MaxPooling3D window (= stride); 0 = no pooling
   int pool_zero;                   // rows outside the conv output count as 0 (ZeroPadding3D before the pool)
   int out_split, out_split2;       // fused sibling 1x1 convs: columns >= out_split go to tmap_o1, columns >= out_split2 to tmap_o2
+  int bshare;                      // h-halo mode: groups of `bshare` M tiles share every weight stage (B ring of b_slots slots)
+  int b_slots;
+  uint32_t b_stage;                // bshare: bytes of one slot of the B ring (1024-aligned); the ring starts at b_region
+  int nbuf;                        // TMEM accumulators in flight (2 / 4 twin / 2*bshare), acc_cols columns apart
+  uint32_t acc_cols;
+  int stepG[5];                    // bshare * gridDim.x as mixed-radix digits
   int twin;                        // twin-tile mode: two M tiles share every B stage (4 TMEM accumulators of bn <= 128 columns)
   int pair_pool;                   // pair-packed stem: GEMM row = 2 output pixels (N = 2*Cout), (1,2,2) max-pool in registers
   int step1[5], step2[5];          // gridDim.x and 2*gridDim.x as mixed-radix digits (nt, tw, th, td, tn)
@@ -268,7 +323,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // barriers: [0,8) full, [8,16) empty, [16,20) tmem_full, [20,24) tmem_empty  (byte offsets 0/64/128/160)
-  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 9];   // tmem_full x4 (byte 128), tmem_empty x4 (160), resident-B full (192)
+  // byte offsets: full[8] 0, empty[8] 64, tmem_full[8] 128, tmem_empty[8] 192, resident-B full 256,
+  // shared-B ring full[3] 264, empty[3] 288
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 16 + 1 + 6];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_par[2][4][256];                   // per epilogue group: scale0, shift0, scale1, shift1
 
@@ -286,11 +343,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(bar_base + 8u * s, 1);
       mbar_init(bar_base + 64u + 8u * s, 1);
     }
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 8; ++b) {
       mbar_init(bar_base + 128u + 8u * b, 1);
-      mbar_init(bar_base + 160u + 8u * b, 128);
+      mbar_init(bar_base + 192u + 8u * b, 128);
     }
-    mbar_init(bar_base + 192u, 1);
+    mbar_init(bar_base + 256u, 1);
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(bar_base + 264u + 8u * b, 1);
+      mbar_init(bar_base + 288u + 8u * b, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -321,7 +382,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t phase = 0;
     if (a.b_resident) {
       // the whole (single N tile) weight matrix stays in shared memory for the CTA's lifetime
-      const uint32_t bb = bar_base + 192u;
+      const uint32_t bb = bar_base + 256u;
       mbar_expect_tx_p(leader, bb, a.b_bytes);
       const uint32_t b_tap = (uint32_t)a.bn * ROW_BYTES;        // resident B: one box per (fd,fh) tap
       for (int t = 0; t < a.kd * a.kh; ++t)
@@ -354,8 +415,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
       }
     }
+    if (a.bshare) {
+      // shared-B h-halo mode (7x7x7/2 stems, single N tile): the CTA's tiles run in groups of G; per
+      // (fd, chunk) ONE weight block is loaded into the B ring and used by the G tiles' A boxes, so
+      // the weights are streamed from L2 once per G tiles instead of once per tile
+      const int G = a.bshare;
+      TileIter tg[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tg[j].init(a, blockIdx.x + j * gridDim.x);
+      int bs = 0;
+      uint32_t bphase = 0;
+      while (tg[0].tile < a.num_tiles) {
+        for (int fd = 0; fd < a.kd; ++fd)
+          for (int ch = 0; ch < a.kchunks; ++ch) {
+            mbar_wait(bar_base + 288u + 8u * bs, bphase ^ 1u);
+            const uint32_t bf = bar_base + 264u + 8u * bs;
+            mbar_expect_tx_p(leader, bf, a.b_bytes);
+            tma_load_2d(leader, smem_base + a.b_region + (uint32_t)bs * a.b_stage, &tmap_b, bf, 0,
+                        (fd * a.kchunks + ch) * a.kh * a.bn);
+            if (++bs == a.b_slots) { bs = 0; bphase ^= 1u; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < G && tg[j].tile < a.num_tiles) {
+                const int iw0 = tg[j].tw * a.b_w * a.sw - a.pw, ih0 = tg[j].th * a.b_h * a.sh - a.ph;
+                const int id0 = tg[j].td * a.b_d * a.sd - a.pd, n0 = tg[j].tn * a.b_n;
+                mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);
+                const uint32_t fb = bar_base + 8u * stage;
+                mbar_expect_tx_p(leader, fb, a.a_bytes);
+                tma_load_5d(leader, smem_base + stage * stage_bytes, &tmap_a, fb, ch * KC, iw0, ih0, id0 + fd, n0);
+                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+              }
+            }
+          }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tg[j].advance(a, a.stepG, G * gridDim.x);
+      }
+    }
     TileIter ti;
-    for (ti.init(a, a.twin ? a.num_tiles : blockIdx.x); ti.tile < a.num_tiles; ti.advance(a, a.step1, gridDim.x)) {
+    for (ti.init(a, (a.twin || a.bshare) ? a.num_tiles : blockIdx.x); ti.tile < a.num_tiles; ti.advance(a, a.step1, gridDim.x)) {
       const int nt = ti.nt;
       const int iw0 = ti.tw * a.b_w * a.sw - a.pw;
       const int ih0 = ti.th * a.b_h * a.sh - a.ph;
@@ -414,13 +511,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) |
                            ((uint32_t)(TC_BM >> 4) << 24);
     // descriptor template: everything but the 14-bit start address
-    const uint64_t desc_hi = make_smem_desc(0, SBO, LAYOUT);
+    const uint32_t desc_hi32 = (uint32_t)(make_smem_desc(0, SBO, LAYOUT) >> 32);
+    auto dlo = [](uint32_t saddr) -> uint32_t { return ((saddr >> 4) & 0x3FFFu) | 0x10000u; };   // start address + LBO = 1
     int stage = 0;
     uint32_t phase = 0;
     uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     int buf = 0;
     if (a.b_resident) {
-      mbar_wait(bar_base + 192u, 0u);
+      mbar_wait(bar_base + 256u, 0u);
       tc_fence_after();
     }
     if (a.twin) {
@@ -430,25 +528,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool two = tile + (int)gridDim.x < a.num_tiles;
         const uint32_t b0 = (uint32_t)(pp * 2), b1 = b0 + 1u;
         const uint32_t ep_ = pp ? eph[1] : eph[0];
-        mbar_wait(bar_base + 160u + 8u * b0, ep_ ^ 1u);
-        mbar_wait(bar_base + 160u + 8u * b1, ep_ ^ 1u);
+        mbar_wait(bar_base + 192u + 8u * b0, ep_ ^ 1u);
+        mbar_wait(bar_base + 192u + 8u * b1, ep_ ^ 1u);
         tc_fence_after();
         const uint32_t d0 = b0 * 128u, d1 = b1 * 128u;
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(bar_base + 8u * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
-          const uint64_t ad1 = desc_hi | (uint64_t)(((sa + A_STAGE) >> 4) & 0x3FFF);
-          const uint64_t bd = desc_hi | (uint64_t)(((sa + 2u * A_STAGE) >> 4) & 0x3FFF);
-#pragma unroll
-          for (int k = 0; k < KC / 16; ++k)
-            tc_mma_bf16(leader, d0, ad0 + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ks > 0 || k > 0) ? 1u : 0u);
-          if (two) {
-#pragma unroll
-            for (int k = 0; k < KC / 16; ++k)
-              tc_mma_bf16(leader, d1, ad1 + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ks > 0 || k > 0) ? 1u : 0u);
-          }
+          const uint32_t bl = dlo(sa + 2u * A_STAGE);
+          tc_mma_k<KC / 16>(leader, d0, dlo(sa), bl, desc_hi32, idesc, ks > 0 ? 1u : 0u);
+          if (two) tc_mma_k<KC / 16>(leader, d1, dlo(sa + A_STAGE), bl, desc_hi32, idesc, ks > 0 ? 1u : 0u);
           tc_commit(leader, bar_base + 64u + 8u * stage);
           if (ks == ksteps - 1) {
             tc_commit(leader, bar_base + 128u + 8u * b0);
@@ -460,9 +550,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         pp ^= 1;
       }
     }
-    for (int tile = a.twin ? a.num_tiles : blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    if (a.bshare) {
+      const int G = a.bshare;
+      const int nst = a.kd * a.kchunks;
+      const uint32_t a_fh = ((uint32_t)a.b_w * ROW_BYTES) >> 4;          // one brick row of pixels
+      const uint32_t b_tap = ((uint32_t)a.bn * ROW_BYTES) >> 4;
+      const uint32_t bmask = (uint32_t)a.nbuf - 1u;
+      int bs = 0;
+      uint32_t bphase = 0;
+      uint32_t i0 = 0;                             // sequence index of the group's first tile in this CTA
+      for (int tile0 = blockIdx.x; tile0 < a.num_tiles; tile0 += G * (int)gridDim.x, i0 += (uint32_t)G) {
+        int nvalid = 0;
+        for (int j = 0; j < G; ++j)
+          if (tile0 + j * (int)gridDim.x < a.num_tiles) nvalid = j + 1;
+        for (int j = 0; j < nvalid; ++j) {
+          const uint32_t i = i0 + (uint32_t)j;
+          mbar_wait(bar_base + 192u + 8u * (i & bmask), ((i / (uint32_t)a.nbuf) & 1u) ^ 1u);
+        }
+        tc_fence_after();
+        for (int st = 0; st < nst; ++st) {
+          mbar_wait(bar_base + 264u + 8u * bs, bphase);
+          tc_fence_after();
+          const uint32_t sb = smem_base + a.b_region + (uint32_t)bs * a.b_stage;
+          const uint32_t bl0 = dlo(sb);
+          for (int j = 0; j < nvalid; ++j) {
+            const uint32_t bj = (i0 + (uint32_t)j) & bmask;
+            const uint32_t d_tmem = bj * a.acc_cols;
+            mbar_wait(bar_base + 8u * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint32_t al0 = dlo(sa);
+            if (a.kh == 4) {
+              tc_mma_taps4<KC / 16>(leader, d_tmem, al0, bl0, desc_hi32, idesc, st > 0 ? 1u : 0u, a_fh, b_tap);
+            } else {
+              for (int fh = 0; fh < a.kh; ++fh)
+                tc_mma_k<KC / 16>(leader, d_tmem, al0 + (uint32_t)fh * a_fh, bl0 + (uint32_t)fh * b_tap, desc_hi32, idesc,
+                                  (st > 0 || fh > 0) ? 1u : 0u);
+            }
+            tc_commit(leader, bar_base + 64u + 8u * stage);
+            if (st == nst - 1) tc_commit(leader, bar_base + 128u + 8u * bj);
+            if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+          }
+          tc_commit(leader, bar_base + 288u + 8u * bs);
+          if (++bs == a.b_slots) { bs = 0; bphase ^= 1u; }
+        }
+      }
+    }
+    for (int tile = (a.twin || a.bshare) ? a.num_tiles : blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const uint32_t aph = buf ? acc_phase1 : acc_phase0;
-      mbar_wait(bar_base + 160u + 8u * buf, aph ^ 1u);                   // tmem_empty[buf]
+      mbar_wait(bar_base + 192u + 8u * buf, aph ^ 1u);                   // tmem_empty[buf]
       tc_fence_after();
       const uint32_t d_tmem = (uint32_t)buf * 256u;                       // TMEM base is 0 (asserted)
       if (a.halo == 2) {
@@ -474,14 +610,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(bar_base + 8u * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
-          const uint64_t bd0 = desc_hi | (uint64_t)(((sa + A_STAGE) >> 4) & 0x3FFF);
-          for (int fh = 0; fh < a.kh; ++fh) {
-            const uint64_t ad = ad0 + (uint64_t)(fh * a_fh);
-            const uint64_t bd = bd0 + (uint64_t)(fh * b_tap);
-#pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              tc_mma_bf16(leader, d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, acc);
+          const uint32_t al0 = dlo(sa), bl0 = dlo(sa + A_STAGE);
+          if (a.kh == 4) {
+            tc_mma_taps4<KC / 16>(leader, d_tmem, al0, bl0, desc_hi32, idesc, acc, a_fh, b_tap);
+            acc = 1u;
+          } else {
+            for (int fh = 0; fh < a.kh; ++fh) {
+              tc_mma_k<KC / 16>(leader, d_tmem, al0 + (uint32_t)fh * a_fh, bl0 + (uint32_t)fh * b_tap, desc_hi32, idesc, acc);
               acc = 1u;
             }
           }
@@ -497,21 +632,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(bar_base + 8u * stage, phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * stage_bytes;
-        const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
         const uint32_t sb = a.b_resident ? (smem_base + a.b_region) : (sa + A_STAGE);
-        const uint64_t bd0 = desc_hi | (uint64_t)((sb >> 4) & 0x3FFF);
+        const uint32_t al0 = dlo(sa), bl0 = dlo(sb);
         const uint32_t a_fh = ((uint32_t)a.b_w * ROW_BYTES) >> 4;                       // one brick row of pixels
         const uint32_t a_fd = ((uint32_t)(a.b_h + a.kh - 1) * a.b_w * ROW_BYTES) >> 4;  // one halo plane
         const uint32_t b_tap = ((uint32_t)a.bn * ROW_BYTES) >> 4;
         uint32_t tap = 0;
         for (int fd = 0; fd < a.kd; ++fd)
-          for (int fh = 0; fh < a.kh; ++fh, ++tap) {
-            const uint64_t ad = ad0 + (uint64_t)(fd * a_fd + fh * a_fh);
-            const uint64_t bd = bd0 + (uint64_t)(tap * b_tap);
-#pragma unroll
-            for (int k = 0; k < KC / 16; ++k)
-              tc_mma_bf16(leader, d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (tap > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int fh = 0; fh < a.kh; ++fh, ++tap)
+            tc_mma_k<KC / 16>(leader, d_tmem, al0 + (uint32_t)fd * a_fd + (uint32_t)fh * a_fh, bl0 + tap * b_tap, desc_hi32, idesc,
+                              tap > 0 ? 1u : 0u);
         tc_commit(leader, bar_base + 64u + 8u * stage);
         tc_commit(leader, bar_base + 128u + 8u * buf);
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
@@ -523,11 +653,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(bar_base + 8u * stage, phase);                           // full[stage]
         tc_fence_after();
         const uint32_t sa = smem_base + stage * stage_bytes;
-        const uint64_t ad = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
-        const uint64_t bd = desc_hi | (uint64_t)(((sa + A_STAGE) >> 4) & 0x3FFF);
-#pragma unroll
-        for (int k = 0; k < KC / 16; ++k)
-          tc_mma_bf16(leader, d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+        tc_mma_k<KC / 16>(leader, d_tmem, dlo(sa), dlo(sa + A_STAGE), desc_hi32, idesc, ks > 0 ? 1u : 0u);
         tc_commit(leader, bar_base + 64u + 8u * stage);                    // frees the smem stage when the MMAs retire
         if (ks == ksteps - 1) tc_commit(leader, bar_base + 128u + 8u * buf);   // tmem_full[buf]
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
@@ -597,19 +723,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       pre(0, pv_r2_0, pv_cd_0); pre(1, pv_r2_1, pv_cd_1); pre(2, pv_r2_2, pv_cd_2); pre(3, pv_r2_3, pv_cd_3);
     }
     const uint32_t bar_id = 1u + (uint32_t)grp;
-    // normal mode: group g owns accumulator g (256 columns each).  twin mode: four 128-column
-    // accumulators; group g drains tile g of every tile pair, alternating between buffer g and 2+g.
-    uint32_t acc_phases[2] = {0u, 0u};
-    int pair_parity = 0;
+    // The CTA's i-th tile (i = grp, grp + 2, ...) lives in accumulator i % nbuf, acc_cols columns apart:
+    // normal mode 2 x 256 columns (group g owns buffer g), twin mode 4 x 128, shared-B mode 2G x 512/(2G).
+    uint32_t seq = (uint32_t)grp;
+    const uint32_t bmask = (uint32_t)a.nbuf - 1u;
     int slot = 0;
     int last_nt = -1;
     TileIter ti;
     for (ti.init(a, blockIdx.x + grp * gridDim.x); ti.tile < a.num_tiles; ti.advance(a, a.step2, 2 * gridDim.x)) {
-      const int buf = a.twin ? (pair_parity * 2 + grp) : grp;
-      const uint32_t acc_phase = pair_parity ? acc_phases[1] : acc_phases[0];
-      const uint32_t buf_col = a.twin ? (uint32_t)buf * 128u : (uint32_t)buf * 256u;
-      if (pair_parity) acc_phases[1] ^= 1u; else acc_phases[0] ^= 1u;
-      if (a.twin) pair_parity ^= 1;
+      const int buf = (int)(seq & bmask);
+      const uint32_t acc_phase = (seq / (uint32_t)a.nbuf) & 1u;
+      const uint32_t buf_col = (uint32_t)buf * a.acc_cols;
+      seq += 2u;
       const int nt = ti.nt;
       const int ow0 = ti.tw * a.b_w, oh0 = ti.th * a.b_h, od0 = ti.td * a.b_d, on0 = ti.tn * a.b_n;
       const int col_base = nt * a.bn;
@@ -663,7 +788,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_wait_ld();
           if (q == 3) {
             tc_fence_before();
-            mbar_arrive(bar_base + 160u + 8u * buf);
+            mbar_arrive(bar_base + 192u + 8u * buf);
           }
           uint32_t pk[8];
 #pragma unroll
@@ -717,7 +842,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp
           // before the math / staging / store of this last chunk
           tc_fence_before();
-          mbar_arrive(bar_base + 160u + 8u * buf);
+          mbar_arrive(bar_base + 192u + 8u * buf);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         const uint32_t s0 = my_stg + (uint32_t)slot * slot_bytes + (uint32_t)row * (EC * 2);
@@ -1145,6 +1270,28 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
       d->tw_smem_bytes = tstage * tst + tstaging + 1024;
     }
   }
+  // shared-B layout for the h-halo mode (single N tile): an A ring of `bs_stages` haloed boxes, a B ring of
+  // two weight blocks each used by G consecutive tiles of the CTA, 2G accumulators of 512/(2G) TMEM columns
+  d->bs_group = 0;
+  if (halo == 2 && d->n_tiles_n == 1 && bn <= 128 && kc <= 32) {
+    // (kc = 64 stems are bound by the MMA operand reads, not by the weight stream: measured slower there)
+    const int G = bn <= 64 ? 4 : 2;
+    for (int nb_ = 3; nb_ >= 2 && !d->bs_group; --nb_)
+      for (int ns = 2; ns >= 1 && !d->bs_group; --ns) {
+        const size_t stg = slot * ns * 2;
+        if (stg + nb_ * b_stage + (size_t)(G + 2) * a_stage > 214 * 1024) continue;
+        int st = (int)((214 * 1024 - stg - nb_ * b_stage) / a_stage);
+        if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
+        d->bs_group = G;
+        d->bs_slots = nb_;
+        d->bs_stages = st;
+        d->bs_nslots = ns;
+        d->bs_b_region = (uint32_t)(a_stage * st);
+        d->bs_b_stage = (uint32_t)b_stage;
+        d->bs_stage_region = (uint32_t)(a_stage * st + nb_ * b_stage);
+        d->bs_smem_bytes = a_stage * st + nb_ * b_stage + stg + 1024;
+      }
+  }
   d->smem_bytes = stage * stages + resident + staging + 1024;   // + alignment slack
   return CSE_OK;
 }
@@ -1199,11 +1346,22 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
   size_t smem_bytes = d.smem_bytes;
   a.twin = 0;
+  a.bshare = 0; a.b_slots = 2; a.b_stage = 0; a.nbuf = 2; a.acc_cols = 256;
+  int bs_min = 8 * sm_count;
+  if (const char* e = getenv("CSE_BSHARE_MIN_TILES")) bs_min = atoi(e);      // tests force the shared-B path on small shapes
+  if (d.bs_group && bs_min > 0 && a.num_tiles >= bs_min) {
+    a.bshare = d.bs_group; a.b_slots = d.bs_slots;
+    a.nbuf = 2 * d.bs_group; a.acc_cols = 512u / (uint32_t)a.nbuf;
+    a.stages = d.bs_stages; a.stage_bytes = d.a_stage; a.b_region = d.bs_b_region; a.b_stage = d.bs_b_stage;
+    a.stage_region = d.bs_stage_region; a.nslots = d.bs_nslots;
+    smem_bytes = d.bs_smem_bytes;
+  }
   int twin_min = 2 * sm_count;
   if (const char* e = getenv("CSE_TWIN_MIN_TILES")) twin_min = atoi(e);      // tests force the twin path on small shapes
   if (d.twin_ok && twin_min > 0 && a.num_tiles >= twin_min) {
     // enough tiles to keep every SM busy with tile pairs
     a.twin = 1;
+    a.nbuf = 4; a.acc_cols = 128;
     a.stages = d.tw_stages; a.stage_bytes = d.tw_stage_bytes; a.stage_region = d.tw_stage_region; a.nslots = d.tw_nslots;
     smem_bytes = d.tw_smem_bytes;
     const int pairs = (a.num_tiles + 1) / 2;
@@ -1211,9 +1369,9 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   }
   {
     const int radix[4] = {a.n_tiles_n, a.tiles_w, a.tiles_h, a.tiles_d};
-    for (int which = 0; which < 2; ++which) {
-      int v = grid * (which + 1);
-      int* st = which ? a.step2 : a.step1;
+    for (int which = 0; which < 3; ++which) {
+      int v = grid * (which == 2 ? (a.bshare ? a.bshare : 1) : which + 1);
+      int* st = which == 2 ? a.stepG : (which ? a.step2 : a.step1);
       for (int i = 0; i < 4; ++i) { st[i] = v % radix[i]; v /= radix[i]; }
       st[4] = v;
     }

@@ -309,6 +309,35 @@ def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb, halo):
     assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
 
 
+@pytest.mark.parametrize("dhw,c,cout,nb", S2D_STEM + [((16, 48, 48), 2, 64, 5), ((10, 30, 44), 1, 32, 3), ((12, 40, 40), 2, 128, 2)])
+def test_conv_tcgen05_s2d_stem_shared_weights(dhw, c, cout, nb, monkeypatch):
+    """Shared-B h-halo mode (groups of 4 tiles of a CTA use one weight block per (fd, chunk), 8 TMEM
+    accumulators; taken by the 1- and 2-channel stems whose K chunk is 32), forced on small shapes: full / partial tile groups, several groups per CTA, ragged
+    bricks.  Must be bit-identical to the per-tile weight streaming (same MMA sequence per tile)."""
+    def build(g):
+        x = g.input(dhw + (c,), name="in")
+        x = g.conv3d(x, cout, (7, 7, 7), (2, 2, 2), "same", True, None, name="c")
+        x = g.bn(x, scale=True, name="b")
+        g.relu(x, name="r")
+    xs = clips(11, nb, dhw + (c,))
+    monkeypatch.setenv("CSE_BSHARE_MIN_TILES", "0")          # off
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c)
+    run(m, [xs])
+    ref = m.read_tensor(m.plan.tensors["r"], nb)
+    del m
+    monkeypatch.setenv("CSE_BSHARE_MIN_TILES", "1")          # always
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c)
+    assert [o for o in m.plan.ops if o.name == "c"][0].halo == 2
+    run(m, [xs])
+    got = m.read_tensor(m.plan.tensors["r"], nb)
+    assert np.array_equal(got, ref)
+    xin = torch.as_tensor((xs.astype(np.float64) - 128.0) / 64.0, dtype=T64)
+    kern, bias = w["c"]
+    y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (2, 2, 2), "same")
+    y = O.relu(O.batchnorm(y, *[torch.as_tensor(a, dtype=T64) for a in w["b"]])).numpy()
+    assert np.abs(got - y).max() / np.abs(y).max() <= 2.0 ** -7
+
+
 PAIR_POOL = [((4, 16, 16), 3, True), ((3, 12, 40), 3, True), ((5, 8, 24), 2, False), ((2, 34, 18), 3, True),
              ((3, 16, 112), 4, True)]
 
