@@ -53,11 +53,13 @@ WORKLOADS = {
 }
 
 
-def workload_config(name, groups, batch, world):
+def workload_config(name, groups, batch, world, by_members=False):
+    par = ("members sharded over %d GPU(s) by FLOPs, every GPU runs all %d clips, 1 all-gather of the fp32 member "
+           "probabilities per step, vote in member order" % (world, batch)) if by_members else (
+           "clips sharded over %d GPU(s), members replicated, 1 all-gather of int32 predictions per step" % world)
     return {"workload": name, "models": [g[0] for g in groups], "clips": [list(g[1]) for g in groups],
             "members": [g[2] for g in groups], "batch_per_gpu": batch, "vote": "SUM", "classes": 11,
-            "parallelism": "clips sharded over %d GPU(s), members replicated, 1 all-gather of int32 predictions per "
-                           "step" % world}
+            "parallelism": par}
 
 
 def load_peaks():
@@ -215,15 +217,33 @@ def run_ours(args):
         groups = [(mt, shape, m, args.micro_batch) for mt, shape, m, _ in groups]
     groups = [(mt, shape, m, min(mb, batch)) for mt, shape, m, mb in groups]
     lower_kw = json.loads(os.environ.get("CSE_LOWER_KW", "{}"))      # lowering experiments (e.g. {"fuse_pool": false})
+    by_members = args.shard == "members" and world > 1
+    all_graphs = [G.build_model_graph(mt, shape, 11) for mt, shape, _, _ in groups]
+    members = sum(m for _, _, m, _ in groups)
+    owned_all = None
+    mine = None
+    if by_members:
+        # member-sharded partition: every rank sees all clips and runs only the members it
+        # owns (balanced by FLOPs per clip); probabilities are all-gathered into member order
+        from cse_b200.ensemble import shard_members, gather_member_probs
+        if world > members:
+            raise SystemExit("--shard members needs at least one member per rank (%d members, %d ranks)" % (members, world))
+        costs = [g.total_flops() for g, (_, _, m, _) in zip(all_graphs, groups) for _ in range(m)]
+        owned_all = shard_members(costs, world)
+        mine = set(owned_all[rank])
     built, graphs = [], []
-    for gi, (mt, shape, m, mb) in enumerate(groups):
-        g = G.build_model_graph(mt, shape, 11)
-        graphs.append(g)
-        built.append((g, [synthetic_weights(g, seed=100 + 10 * gi + j) for j in range(m)], mb))
+    flat = 0
+    for gi, ((mt, shape, m, mb), g) in enumerate(zip(groups, all_graphs)):
+        ws = [synthetic_weights(g, seed=100 + 10 * gi + j) for j in range(m) if mine is None or flat + j in mine]
+        flat += m
+        if ws:
+            graphs.append(g)
+            built.append((g, ws, mb))
     ens = HeteroEnsemble(built, precision=args.precision, max_batch=batch, **lower_kw)
     del built
-    members = ens.M
-    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    if by_members:
+        ens.gather = lambda p: gather_member_probs(p, owned_all, members, dist, world)
+    gen = torch.Generator(device="cpu").manual_seed(1234 + (0 if by_members else rank))
     host = [[torch.randint(0, 256, (batch,) + tuple(g.shape(n)), dtype=torch.uint8, generator=gen).pin_memory()
              for n in g.inputs] for g in graphs]
     dev_in = [[h.cuda() for h in hs] for hs in host]
@@ -237,10 +257,12 @@ def run_ours(args):
 
     # N > 1: clips are sharded over the ranks (members replicated); the one exchange of the path is
     # the all-gather of the per-clip predictions (evaluate_ensemble.py:1262-1268 writes them all)
-    gathered = torch.empty((world * batch,), dtype=torch.int32, device="cuda") if world > 1 else None
+    gathered = torch.empty((world * batch,), dtype=torch.int32, device="cuda") if world > 1 and not by_members else None
 
     def step_resident():
         pred = ens.predict_device(dev_in)
+        if by_members:
+            return pred                  # every rank voted on the gathered [M, batch, C] block
         if world > 1:
             dist.all_gather_into_tensor(gathered, pred)
             return gathered
@@ -254,7 +276,9 @@ def run_ours(args):
         back (D2H); all of it inside the timed region."""
         out = None
         for pred in ens.stream_host(host for _ in range(nsteps)):
-            if world > 1:
+            if by_members:
+                pinned_pred[:batch].copy_(pred, non_blocking=True)
+            elif world > 1:
                 dist.all_gather_into_tensor(gathered, pred)
                 pinned_pred.copy_(gathered, non_blocking=True)
             else:
@@ -295,7 +319,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
-    total_clips = batch * world * args.steps
+    total_clips = batch * (1 if by_members else world) * args.steps
     value = total_clips / (ms / 1e3)
     e2e_value = total_clips / (ms_e2e / 1e3)
 
@@ -313,15 +337,15 @@ def run_ours(args):
                     "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (peaks["source"], peaks["bf16_burst"]),
                     "kernel_share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
                     "launches_per_step": len(tc),
-                    "whole_step_model_tflops": sum(m * g.total_flops() for g, (_, _, m, _) in zip(graphs, groups)) * batch
-                                               / (ms / args.steps / 1e3) / 1e12}
+                    "whole_step_model_tflops": sum(m * g.total_flops() for g, (_, _, m, _) in zip(all_graphs, groups)) * batch
+                                               / (ms / args.steps / 1e3) / 1e12 / (world if by_members else 1)}
         tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tpath):
             tr = json.load(open(tpath)).get(args.workload)
             if tr and [tr.get("micro_batch")] == ens.micro_batch and tr.get("launches_captured") == len(tc):
                 roofline["traffic"] = tr["dram_bytes_per_launch_avg"]
                 roofline["traffic_unit"] = "B per conv_tc launch (ncu dram read+write, avg over the member's launches)"
-                roofline["algorithmic_flops_per_launch_avg"] = tc_flops / (len(tc) * members * (batch // ens.micro_batch[0]))
+                roofline["algorithmic_flops_per_launch_avg"] = tc_flops / (len(tc) * ens.M * (batch // ens.micro_batch[0]))
         if args.profile_out:
             with open(args.profile_out, "w") as f:
                 json.dump({"workload": args.workload, "batch": batch, "members": members, "micro_batch": ens.micro_batch,
@@ -350,9 +374,10 @@ def run_ours(args):
                              "restatement (Keras 2.2.4/TF 1.15 not installable offline)" % (sample, members)}
         line = {
             "metric": "ensemble clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if by_members else "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": dict(workload_config(args.workload, groups, batch, world),
+            "config": dict(workload_config(args.workload, groups, batch, world, by_members),
                            l2_policy="input batch (%d MB uint8) and activations exceed the 126 MB L2" % (in_bytes >> 20)),
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": batch * 4},
@@ -392,6 +417,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--members", type=int, default=0)
     ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--shard", default="clips", choices=["clips", "members"],
+                    help="N > 1: shard the clips (default, weak scaling) or the ensemble members (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="")
     args = ap.parse_args()

@@ -288,6 +288,48 @@ def shard_indices(n: int, rank: int, world: int) -> np.ndarray:
     return np.arange(start, start + base + (1 if rank < extra else 0))
 
 
+def shard_members(costs, world: int):
+    """Member-sharded partition (alternative): which members each rank owns.  `costs` = one
+    cost per member (FLOPs per clip; equal costs for a homogeneous ensemble).  Longest-processing-time
+    greedy: members in decreasing cost go to the least loaded rank (ties -> lowest rank), which keeps
+    heterogeneous ensembles (I3D-64 : C3D : R3D-34 = 16.7 : 5.8 : 1) balanced.  -> list of sorted index
+    lists, one per rank; deterministic, identical on every rank."""
+    costs = [float(c) for c in costs]
+    load = [0.0] * world
+    owned = [[] for _ in range(world)]
+    for m in sorted(range(len(costs)), key=lambda i: (-costs[i], i)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owned[r].append(m)
+        load[r] += costs[m]
+    return [sorted(o) for o in owned]
+
+
+def gather_member_probs(local, owned, m_total: int, dist, world: int):
+    """All-gather of per-rank probability blocks of a member-sharded ensemble.  local: torch tensor
+    [len(owned[rank]), N, C] (any device the backend supports); -> [m_total, N, C] in MEMBER order, so
+    that the fixed-order fp64 vote that follows is bit-identical to the single-process one (an
+    all-reduce would make the summation order depend on the ring)."""
+    import torch
+    if world == 1:
+        return local
+    pad = max(len(o) for o in owned)
+    n, c = local.shape[1], local.shape[2]
+    buf = torch.zeros((pad, n, c), dtype=local.dtype, device=local.device)
+    buf[:local.shape[0]] = local
+    out = torch.empty((world * pad, n, c), dtype=local.dtype, device=local.device)
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(out, buf)
+    else:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        out = torch.cat(parts, dim=0)
+    index = torch.empty((m_total,), dtype=torch.long)
+    for r, ids in enumerate(owned):
+        for k, m in enumerate(ids):
+            index[m] = r * pad + k
+    return out.index_select(0, index.to(out.device))
+
+
 def _gather_rows(local: np.ndarray, n: int, dist, rank: int, world: int) -> np.ndarray:
     """All-gather of the per-rank [M, n_local, C] probability blocks into [M, n, C] (rank order =
     clip order because shards are contiguous)."""
@@ -306,6 +348,11 @@ def _gather_rows(local: np.ndarray, n: int, dist, rank: int, world: int) -> np.n
     return np.concatenate([o[:, :s].cpu().numpy() for o, s in zip(out, sizes)], axis=1)
 
 
+def _gather_device(dist):
+    import torch
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
 def _clip_device():
     """Where clips are assembled (select_frames + resize): on the GPU that runs the members
     (cse_assemble_clip, bit-identical to cv2.resize) unless CSE_CPU_RESIZE=1 asks for the cv2 path."""
@@ -313,6 +360,19 @@ def _clip_device():
         return None
     import torch
     return torch.device("cuda", torch.cuda.current_device())
+
+
+class _NoMembers:
+    """A rank that owns no member of a member-sharded ensemble."""
+    M = 0
+
+    def __init__(self, nb_classes):
+        import torch
+        self.nb_classes, self.device = nb_classes, torch.device("cpu")
+        self.probs = torch.zeros((0, 1, nb_classes), dtype=torch.float32)
+
+    def forward_members(self, inputs):
+        return inputs[0].shape[0]
 
 
 def _load_members(model_type, member_paths, input_shape, nb_classes, batch):
@@ -324,10 +384,17 @@ def _load_members(model_type, member_paths, input_shape, nb_classes, batch):
     return DeviceEnsemble(g, weight_sets, precision=zoo.DEFAULTS["precision"], max_batch=batch, micro_batch=batch)
 
 
-def _predict_members(ens, generator, n_clips, dist_state, chunk):
-    """-> float32 [M, n_clips, C]: every clip decoded once, pushed through every member."""
+def _predict_members(ens, generator, n_clips, dist_state, chunk, owned=None, m_total=None):
+    """-> float32 [M, n_clips, C]: every clip decoded once, pushed through every member.
+    Default partition: clips sharded over the ranks, members replicated.  owned = shard_members(...)
+    switches to the member-sharded partition: `ens` holds only this rank's members, every rank runs all
+    clips, and the probability blocks are all-gathered into member order."""
     import torch
     dist, rank, world = dist_state
+    if owned is not None and world > 1:
+        local = _predict_members(ens, generator, n_clips, (None, 0, 1), chunk)
+        full = gather_member_probs(torch.from_numpy(local).to(_gather_device(dist)), owned, m_total, dist, world)
+        return full.cpu().numpy()
     mine = shard_indices(n_clips, rank, world)
     bs = generator.batch_size
     out = np.zeros((ens.M, len(mine), ens.nb_classes), np.float32)
@@ -395,8 +462,15 @@ def store_probabilities(trained_models_folder, results_folder, involved_sets, ba
         val_folds_indices = [i for i in test_folds_indices if i != test_index]
         member_paths = [os.path.join(data_folder, models_name + "_split_test" + str(test_index) + "_val" +
                                      str(v) + "_weights.hdf5") for v in val_folds_indices]
-        ens = _load_members(model_type, member_paths, sample_input.shape, nb_classes, chunk)
-        probs = _predict_members(ens, generator, generator.n, dist_state, chunk)
+        owned = None
+        if dist_state[2] > 1 and os.environ.get("CSE_SHARD", "clips") == "members":
+            # member-sharded partition: this rank loads and runs only its own members on all clips
+            owned = shard_members([1.0] * len(member_paths), dist_state[2])
+        local_paths = member_paths if owned is None else [member_paths[m] for m in owned[rank]]
+        ens = _load_members(model_type, local_paths, sample_input.shape, nb_classes, chunk) if local_paths else None
+        if ens is None:         # more ranks than members: nothing to run here, but take part in the gather
+            ens = _NoMembers(nb_classes)
+        probs = _predict_members(ens, generator, generator.n, dist_state, chunk, owned, len(member_paths))
         del ens
         for j, path in enumerate(member_paths):
             print(probs[j].shape)

@@ -184,6 +184,8 @@ class HeteroEnsemble:
         if vote_weights is not None:
             self.vote_weights = torch.as_tensor(np.asarray(vote_weights, np.float64)).to(dev)
         self.last_launches = 0
+        # set by the caller when the members are sharded over the ranks (ensemble.gather_member_probs)
+        self.gather = None
 
     @property
     def micro_batch(self):
@@ -199,6 +201,8 @@ class HeteroEnsemble:
             ens.forward_members(inputs)
             launches += ens.last_launches
         probs = self.probs[:, :n].contiguous() if n != self.max_batch else self.probs
+        if self.gather is not None:          # member-sharded partition: [M_local, n, C] -> [M, n, C] in member order
+            probs = self.gather(probs)
         pred = rt.vote(probs, self.vote_weights, self.vote_mode)
         self.last_launches = launches + 1
         return pred

@@ -102,3 +102,76 @@ def test_vote_after_gather_is_rank_independent():
     glued = np.concatenate(parts, axis=1)
     assert np.array_equal(glued, ref)
     assert np.array_equal(OV.ensemble_predictions(glued, np.ones(M)), OV.ensemble_predictions(ref, np.ones(M)))
+
+
+# --------------------------------------------------------------------------- member-sharded partition
+def test_shard_members_balances_by_cost():
+    """LPT greedy over FLOPs per clip: the global C3D + I3D-64 + R3D-34 ensemble (4 members each,
+    77.1 / 222.3 / 13.3 GFLOP) on 2, 4 and 8 ranks; every member owned exactly once, deterministic."""
+    costs = [77.1] * 4 + [222.3] * 4 + [13.3] * 4
+    for world in (1, 2, 3, 4, 8, 12):
+        owned = E.shard_members(costs, world)
+        assert len(owned) == world and sorted(m for o in owned for m in o) == list(range(12))
+        assert owned == E.shard_members(costs, world)
+        load = [sum(costs[m] for m in o) for o in owned]
+        assert max(load) <= sum(costs) / world + max(costs)          # LPT bound
+    # 4 ranks: each gets one I3D member; the C3D / R3D members fill up the lightest ranks
+    assert all(sum(1 for m in o if 4 <= m < 8) == 1 for o in E.shard_members(costs, 4))
+    assert E.shard_members([1.0] * 4, 2) == [[0, 2], [1, 3]]
+
+
+def _member_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        owned = E.shard_members([3.0, 1.0, 2.0, 5.0, 1.0], world)
+
+        class Local(FakeEnsemble):
+            """Only this rank's members of the 5-member stand-in ensemble."""
+            def __init__(self):
+                super().__init__()
+                self.ids = owned[rank]
+                self.M = len(self.ids)
+                self.probs = torch.zeros((self.M, 64, C), dtype=torch.float32)
+
+            def forward_members(self, inputs):
+                x = inputs[0].to(torch.float32)
+                n = x.shape[0]
+                feat = x.reshape(n, -1)
+                for k, m in enumerate(self.ids):
+                    logits = torch.stack([(feat[:, (c + m)::C]).mean(dim=1) * (1 + 0.01 * c) for c in range(C)], dim=1)
+                    self.probs[k, :n] = torch.softmax(logits / 16.0, dim=1)
+                return n
+        got = E._predict_members(Local(), FakeSequence(N_CLIPS), N_CLIPS, (dist, rank, world), chunk=4,
+                                 owned=owned, m_total=5)
+        np.save(os.path.join(out_dir, "mrank%d.npy" % rank), got)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_member_sharded_probabilities_match_single_process(tmp_path, world):
+    """Members sharded over the ranks (every rank runs all clips through its own members), one
+    all-gather into MEMBER order: every rank must hold the single-process [M, N, C] block."""
+    class Five(FakeEnsemble):
+        def __init__(self):
+            super().__init__()
+            self.M = 5
+            self.probs = torch.zeros((5, 64, C), dtype=torch.float32)
+
+        def forward_members(self, inputs):
+            x = inputs[0].to(torch.float32)
+            n = x.shape[0]
+            feat = x.reshape(n, -1)
+            for m in range(5):
+                logits = torch.stack([(feat[:, (c + m)::C]).mean(dim=1) * (1 + 0.01 * c) for c in range(C)], dim=1)
+                self.probs[m, :n] = torch.softmax(logits / 16.0, dim=1)
+            return n
+    ref = E._predict_members(Five(), FakeSequence(N_CLIPS), N_CLIPS, (None, 0, 1), chunk=4)
+    mp.spawn(_member_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(str(tmp_path / ("mrank%d.npy" % r)))
+        assert got.shape == ref.shape == (5, N_CLIPS, C)
+        assert np.array_equal(got, ref), "rank %d: member-sharded gather differs" % r
