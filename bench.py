@@ -225,7 +225,7 @@ def run_ours(args):
     if by_members:
         # member-sharded partition: every rank sees all clips and runs only the members it
         # owns (balanced by FLOPs per clip); probabilities are all-gathered into member order
-        from cse_b200.ensemble import shard_members, gather_member_probs
+        from cse_b200.ensemble import shard_members, MemberGather
         if world > members:
             raise SystemExit("--shard members needs at least one member per rank (%d members, %d ranks)" % (members, world))
         costs = [g.total_flops() for g, (_, _, m, _) in zip(all_graphs, groups) for _ in range(m)]
@@ -242,7 +242,7 @@ def run_ours(args):
     ens = HeteroEnsemble(built, precision=args.precision, max_batch=batch, **lower_kw)
     del built
     if by_members:
-        ens.gather = lambda p: gather_member_probs(p, owned_all, members, dist, world)
+        ens.gather = MemberGather(owned_all, members, dist, world)
     gen = torch.Generator(device="cpu").manual_seed(1234 + (0 if by_members else rank))
     host = [[torch.randint(0, 256, (batch,) + tuple(g.shape(n)), dtype=torch.uint8, generator=gen).pin_memory()
              for n in g.inputs] for g in graphs]

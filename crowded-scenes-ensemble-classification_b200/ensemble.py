@@ -304,30 +304,54 @@ def shard_members(costs, world: int):
     return [sorted(o) for o in owned]
 
 
-def gather_member_probs(local, owned, m_total: int, dist, world: int):
-    """All-gather of per-rank probability blocks of a member-sharded ensemble.  local: torch tensor
-    [len(owned[rank]), N, C] (any device the backend supports); -> [m_total, N, C] in MEMBER order, so
+class MemberGather:
+    """All-gather of the per-rank probability blocks of a member-sharded ensemble into MEMBER order, so
     that the fixed-order fp64 vote that follows is bit-identical to the single-process one (an
-    all-reduce would make the summation order depend on the ring)."""
-    import torch
-    if world == 1:
-        return local
-    pad = max(len(o) for o in owned)
-    n, c = local.shape[1], local.shape[2]
-    buf = torch.zeros((pad, n, c), dtype=local.dtype, device=local.device)
-    buf[:local.shape[0]] = local
-    out = torch.empty((world * pad, n, c), dtype=local.dtype, device=local.device)
-    if dist.get_backend() == "nccl":
-        dist.all_gather_into_tensor(out, buf)
-    else:
-        parts = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(parts, buf)
-        out = torch.cat(parts, dim=0)
-    index = torch.empty((m_total,), dtype=torch.long)
-    for r, ids in enumerate(owned):
-        for k, m in enumerate(ids):
-            index[m] = r * pad + k
-    return out.index_select(0, index.to(out.device))
+    all-reduce would make the summation order depend on the ring).  Buffers and the re-ordering index
+    are allocated once and reused every step (no host <-> device traffic in the step)."""
+
+    def __init__(self, owned, m_total: int, dist, world: int):
+        self.owned, self.m_total, self.dist, self.world = owned, int(m_total), dist, int(world)
+        self.pad = max(len(o) for o in owned)
+        self._key = None
+
+    def _prepare(self, local):
+        import torch
+        key = (tuple(local.shape[1:]), local.dtype, local.device)
+        if key == self._key:
+            return
+        n, c = local.shape[1], local.shape[2]
+        self.buf = torch.zeros((self.pad, n, c), dtype=local.dtype, device=local.device)
+        self.out = torch.empty((self.world * self.pad, n, c), dtype=local.dtype, device=local.device)
+        index = torch.empty((self.m_total,), dtype=torch.long)
+        for r, ids in enumerate(self.owned):
+            for k, m in enumerate(ids):
+                index[m] = r * self.pad + k
+        self.index = index.to(local.device)
+        self.full = torch.empty((self.m_total, n, c), dtype=local.dtype, device=local.device)
+        self._key = key
+
+    def __call__(self, local):
+        """local: torch tensor [len(owned[rank]), N, C] -> [m_total, N, C]."""
+        import torch
+        if self.world == 1:
+            return local
+        self._prepare(local)
+        self.buf[:local.shape[0]].copy_(local)
+        if self.dist.get_backend() == "nccl":
+            self.dist.all_gather_into_tensor(self.out, self.buf)
+            out = self.out
+        else:
+            parts = [torch.empty_like(self.buf) for _ in range(self.world)]
+            self.dist.all_gather(parts, self.buf)
+            out = torch.cat(parts, dim=0)
+        torch.index_select(out, 0, self.index, out=self.full)
+        return self.full
+
+
+def gather_member_probs(local, owned, m_total: int, dist, world: int):
+    """One-shot form of MemberGather."""
+    return MemberGather(owned, m_total, dist, world)(local)
 
 
 def _gather_rows(local: np.ndarray, n: int, dist, rank: int, world: int) -> np.ndarray:
