@@ -68,20 +68,28 @@ def decode_frames(path: str, gray: bool = False) -> List[np.ndarray]:
     return [_gray(f) for f in frames] if gray else frames
 
 
-def _assemble(frames: List[np.ndarray], t: int, h: int, w: int, device=None):
-    """select_frames + resize -> uint8 [T,H,W(,C)].  device=None: on the CPU with cv2 (the reference's
-    own path); otherwise the selected frames are uploaded once and resized by cse_assemble_clip
-    (bit-identical output, csrc/ingest.cu) and the clip stays on the GPU."""
-    sel = select_frames(frames, t)
+def _select(frames: List[np.ndarray], t: int) -> np.ndarray:
+    """select_frames -> one contiguous uint8 array [T', Hs, Ws(, C)] (host only: safe in worker threads)."""
+    return np.ascontiguousarray(np.asarray(select_frames(frames, t), dtype=np.uint8))
+
+
+def _finish(sel: np.ndarray, t: int, h: int, w: int, device=None):
+    """Resize the selected frames -> uint8 [T,H,W(,C)].  device=None: on the CPU with cv2 (the reference's
+    own path); otherwise the frames are uploaded once and resized by cse_assemble_clip (bit-identical
+    output, csrc/ingest.cu) and the clip stays on the GPU."""
     if device is None:
         return np.asarray([_resize(f, w, h) for f in sel], dtype=np.uint8)
     from . import runtime as rt
     torch = rt.require_cuda()
     if len(sel) < t:
-        raise ValueError("video has %d frames, select_frames keeps %d < %d" % (len(frames), len(sel), t))
-    src = torch.from_numpy(np.ascontiguousarray(np.asarray(sel, dtype=np.uint8))).to(device)
+        raise ValueError("select_frames keeps %d < %d frames" % (len(sel), t))
+    src = torch.from_numpy(sel).to(device)
     with torch.cuda.device(src.device):
         return rt.assemble_clip(src, t, h, w)
+
+
+def _assemble(frames: List[np.ndarray], t: int, h: int, w: int, device=None):
+    return _finish(_select(frames, t), t, h, w, device)
 
 
 def load_rgb_clip(path: str, t: int, h: int, w: int, device=None):
@@ -130,21 +138,72 @@ class ClipSequence:
     def __len__(self):
         return int(np.ceil(self.n / self.batch_size))
 
-    def __getitem__(self, index):
+    # The work of one batch is split in two so that a pool of worker threads can decode ahead
+    # (cv2 releases the GIL) while the main thread keeps every CUDA call: load_raw = decode + select_frames
+    # (host only), assemble = resize (+ upload) and stacking.  __getitem__ = assemble(load_raw(i)).
+    def load_raw(self, index):
         idx = range(index * self.batch_size, min((index + 1) * self.batch_size, self.n))
-        t, h, w = self.input_shape[:3]
+        t = self.input_shape[0]
         vd = self.video_data
         labels = np.asarray([vd["class"].values[i] for i in idx], dtype=int)
         onehot = np.zeros((len(labels), self.num_classes), np.float32)
         onehot[np.arange(len(labels)), labels % self.num_classes] = 1.0
+        raw = []
+        for i in idx:
+            item = {"rgb": _select(decode_frames(vd["rgbclips_path"].values[i]), t)}
+            if self.model_type == "TWOSTREAM_I3D":
+                item["fx"] = _select(decode_frames(vd["x_axis_flowclips_path"].values[i], gray=True), t)
+                item["fy"] = _select(decode_frames(vd["y_axis_flowclips_path"].values[i], gray=True), t)
+            raw.append(item)
+        return raw, onehot
+
+    def assemble(self, raw):
+        t, h, w = self.input_shape[:3]
         if self.device is None:
-            stack = np.stack
+            stack, last = np.stack, (lambda a, b: np.stack([a, b], axis=-1))
         else:
             import torch
-            stack = torch.stack
-        rgb = stack([load_rgb_clip(vd["rgbclips_path"].values[i], t, h, w, self.device) for i in idx])
+            stack, last = torch.stack, (lambda a, b: torch.stack([a, b], dim=-1).contiguous())
+        rgb = stack([_finish(r["rgb"], t, h, w, self.device) for r in raw])
+        if tuple(rgb.shape[1:]) != (t, h, w, 3):
+            raise ValueError("clips decode to %r, expected %r" % (tuple(rgb.shape[1:]), (t, h, w, 3)))
         if self.model_type == "TWOSTREAM_I3D":
-            flow = stack([load_flow_clip(vd["x_axis_flowclips_path"].values[i],
-                                         vd["y_axis_flowclips_path"].values[i], t, h, w, self.device) for i in idx])
-            return [rgb, flow], onehot
-        return rgb, onehot
+            flow = stack([last(_finish(r["fx"], t, h, w, self.device), _finish(r["fy"], t, h, w, self.device))
+                          for r in raw])
+            if tuple(flow.shape[1:]) != (t, h, w, 2):
+                raise ValueError("flow clips decode to %r, expected %r" % (tuple(flow.shape[1:]), (t, h, w, 2)))
+            return [rgb, flow]
+        return rgb
+
+    def __getitem__(self, index):
+        raw, onehot = self.load_raw(index)
+        return self.assemble(raw), onehot
+
+
+def iterate_batches(generator, first: int, last: int, workers: int = 1, depth: int = 0):
+    """Yields generator[first] .. generator[last] in order.  With workers > 1 and a generator that offers
+    load_raw / assemble (ClipSequence), decoding runs `depth` batches ahead in a thread pool - the
+    reference's `workers` (evaluate_ensemble.py:1053-1056 passes it to predict_generator) - while the
+    results are consumed strictly in order on the calling thread."""
+    n = last - first + 1
+    if n <= 0:
+        return
+    if workers is None or workers <= 1 or not hasattr(generator, "load_raw"):
+        for b in range(first, last + 1):
+            yield generator[b]
+        return
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    depth = depth or 2 * workers
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        pending = deque()
+        nxt = first
+        while nxt <= last and len(pending) < depth:
+            pending.append(pool.submit(generator.load_raw, nxt))
+            nxt += 1
+        while pending:
+            raw, onehot = pending.popleft().result()
+            if nxt <= last:
+                pending.append(pool.submit(generator.load_raw, nxt))
+                nxt += 1
+            yield generator.assemble(raw), onehot

@@ -408,7 +408,7 @@ def _load_members(model_type, member_paths, input_shape, nb_classes, batch):
     return DeviceEnsemble(g, weight_sets, precision=zoo.DEFAULTS["precision"], max_batch=batch, micro_batch=batch)
 
 
-def _predict_members(ens, generator, n_clips, dist_state, chunk, owned=None, m_total=None):
+def _predict_members(ens, generator, n_clips, dist_state, chunk, owned=None, m_total=None, workers=1):
     """-> float32 [M, n_clips, C]: every clip decoded once, pushed through every member.
     Default partition: clips sharded over the ranks, members replicated.  owned = shard_members(...)
     switches to the member-sharded partition: `ens` holds only this rank's members, every rank runs all
@@ -416,7 +416,7 @@ def _predict_members(ens, generator, n_clips, dist_state, chunk, owned=None, m_t
     import torch
     dist, rank, world = dist_state
     if owned is not None and world > 1:
-        local = _predict_members(ens, generator, n_clips, (None, 0, 1), chunk)
+        local = _predict_members(ens, generator, n_clips, (None, 0, 1), chunk, workers=workers)
         full = gather_member_probs(torch.from_numpy(local).to(_gather_device(dist)), owned, m_total, dist, world)
         return full.cpu().numpy()
     mine = shard_indices(n_clips, rank, world)
@@ -439,8 +439,9 @@ def _predict_members(ens, generator, n_clips, dist_state, chunk, owned=None, m_t
         pend, pend_n = [], 0
 
     first_batch, last_batch = (mine[0] // bs, mine[-1] // bs) if len(mine) else (0, -1)
-    for b in range(first_batch, last_batch + 1):
-        x, _ = generator[b]
+    from .clips import iterate_batches
+    for b, (x, _) in zip(range(first_batch, last_batch + 1),
+                         iterate_batches(generator, first_batch, last_batch, workers)):
         xs = x if isinstance(x, (list, tuple)) else [x]
         lo = b * bs
         keep = [i for i in range(xs[0].shape[0]) if mine[0] <= lo + i <= mine[-1]]
@@ -494,7 +495,8 @@ def store_probabilities(trained_models_folder, results_folder, involved_sets, ba
         ens = _load_members(model_type, local_paths, sample_input.shape, nb_classes, chunk) if local_paths else None
         if ens is None:         # more ranks than members: nothing to run here, but take part in the gather
             ens = _NoMembers(nb_classes)
-        probs = _predict_members(ens, generator, generator.n, dist_state, chunk, owned, len(member_paths))
+        probs = _predict_members(ens, generator, generator.n, dist_state, chunk, owned, len(member_paths),
+                                 workers=int(workers) if workers else 1)
         del ens
         for j, path in enumerate(member_paths):
             print(probs[j].shape)

@@ -63,3 +63,28 @@ def test_clip_assembly_equals_reference_functions(tag):
         assert np.array_equal(rgb, g["rgb_" + tag]) and np.array_equal(flow, g["flow_" + tag])
     assert np.array_equal(clips.load_rgb_clip(rgb_path, t, h, w), rgb)
     assert np.array_equal(clips.load_flow_clip(fx, fy, t, h, w), flow)
+
+
+def test_parallel_decode_keeps_order_and_bytes(tmp_path):
+    """clips.iterate_batches with worker threads (the reference's `workers`): same batches, same order."""
+    import pandas as pd
+    rgb = os.path.join(GOLD, "clip_rgb.avi")
+    fx, fy = os.path.join(GOLD, "clip_flow_x.avi"), os.path.join(GOLD, "clip_flow_y.avi")
+    # different clips = different pre-decoded frame ranges of the same video
+    frames = np.asarray(clips.decode_frames(rgb))
+    paths = []
+    for k in range(7):
+        p = str(tmp_path / ("clip%d.npy" % k))
+        np.save(p, frames[k:k + 20])
+        paths.append(p)
+    data = pd.DataFrame({"rgbclips_path": paths, "x_axis_flowclips_path": [fx] * 7, "y_axis_flowclips_path": [fy] * 7,
+                         "class": list(range(7))})
+    for mt, shape in (("C3D", (16, 40, 52, 3)), ("TWOSTREAM_I3D", (8, 32, 32, 0))):
+        seq = clips.ClipSequence(data, mt, shape, 11, batch_size=2)
+        serial = [seq[i] for i in range(len(seq))]
+        threaded = list(clips.iterate_batches(seq, 0, len(seq) - 1, workers=3))
+        assert len(threaded) == len(serial) == 4
+        for (xa, ya), (xb, yb) in zip(serial, threaded):
+            xa, xb = (xa if isinstance(xa, list) else [xa]), (xb if isinstance(xb, list) else [xb])
+            assert all(np.array_equal(a, b) for a, b in zip(xa, xb)) and np.array_equal(ya, yb)
+        assert list(clips.iterate_batches(seq, 2, 1, workers=3)) == []
