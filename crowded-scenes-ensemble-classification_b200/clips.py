@@ -13,7 +13,6 @@ outside the accelerated path: clips can equally be pre-decoded ``.
 """
 from __future__ import annotations
 
-import os
 from typing import List, Sequence
 
 import numpy as np

@@ -9,7 +9,7 @@ one [M, N, C] device buffer that the vote kernel reduces.  Members share one wor
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import numpy as np
 

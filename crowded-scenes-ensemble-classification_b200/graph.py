@@ -28,7 +28,7 @@ from __future__ import annotations
 import math
 from collections import OrderedDict
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 BN_EPS = 1e-3  # Keras BatchNormalization default epsilon
 

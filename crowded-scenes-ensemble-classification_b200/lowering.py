@@ -805,7 +805,6 @@ class Lowerer:
                 k2[:, :, 0, j * 8:j * 8 + ci, :] = kernel[:, :, j, :, :]
             assert x.wpad == 1 and x.ld == 8
             view = TRef(x.buf, 0, 32, 8, x.dims, x.dtype, x.wpitch, x.wpad)
-        saved = self.tc_strided
         op = self._conv_like(node.name, view, k2, bias, (3, 3, 1), (1, 1, 1), (1, 1, 0), out_dims, chain_bn, relu,
                              final, layers, flops=flops, halo=self.stem_halo, pool=pool)
         if op.engine != rt.ENGINE_TCGEN05:
