@@ -249,7 +249,7 @@ def choose_bn(co: int, m_tiles: int = 0) -> Tuple[int, int]:
     only pay off when the wide tiling would leave SMs idle (small-M layers: R3D stages 3-4, I3D 5x)."""
     best, best_key = None, None
     min_t = -(-co // 256)
-    for n_tiles in range(min_t, max(min_t + 1, 9)):
+    for n_tiles in range(min_t, max(min_t + 1, 9, co // 64 + 1)):      # up to 64-wide tiles (dense heads: M is 1-2 tiles)
         bn = _round_up(-(-co // n_tiles), 16)
         if n_tiles > min_t and bn < 64:
             break
