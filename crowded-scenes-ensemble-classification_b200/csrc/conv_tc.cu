@@ -28,7 +28,15 @@ namespace cse {
 
 constexpr int TC_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_BM = 128;
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_STAGES = 24;         // small stages (kc = 16 / 32) need a deep ring: stage time = TMA latency / stages
+// mbarrier byte offsets inside `bars`: full[stage] at 0, then
+constexpr uint32_t BAR_EMPTY = 8u * TC_MAX_STAGES;            // empty[stage]
+constexpr uint32_t BAR_TMEM_FULL = 16u * TC_MAX_STAGES;       // tmem_full[8]
+constexpr uint32_t BAR_TMEM_EMPTY = BAR_TMEM_FULL + 64u;      // tmem_empty[8]
+constexpr uint32_t BAR_B_RESIDENT = BAR_TMEM_EMPTY + 64u;     // resident-B full
+constexpr uint32_t BAR_B_FULL = BAR_B_RESIDENT + 8u;          // shared-B ring full[3]
+constexpr uint32_t BAR_B_EMPTY = BAR_B_FULL + 24u;            // shared-B ring empty[3]
+constexpr int BAR_COUNT = (int)(BAR_B_EMPTY + 24u) / 8;
 constexpr uint32_t TC_TMEM_COLS = 512;
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -322,10 +330,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr uint32_t STG_BYTES = TC_BM * EC * 2;       // one staged [128][EC] bf16 tile
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // barriers: [0,8) full, [8,16) empty, [16,20) tmem_full, [20,24) tmem_empty  (byte offsets 0/64/128/160)
-  // byte offsets: full[8] 0, empty[8] 64, tmem_full[8] 128, tmem_empty[8] 192, resident-B full 256,
-  // shared-B ring full[3] 264, empty[3] 288
-  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 16 + 1 + 6];
+  // mbarriers: see the BAR_* offsets
+  __shared__ __align__(8) uint64_t bars[BAR_COUNT];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_par[2][4][256];                   // per epilogue group: scale0, shift0, scale1, shift1
 
@@ -341,16 +347,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(bar_base + 8u * s, 1);
-      mbar_init(bar_base + 64u + 8u * s, 1);
+      mbar_init(bar_base + BAR_EMPTY + 8u * s, 1);
     }
     for (int b = 0; b < 8; ++b) {
-      mbar_init(bar_base + 128u + 8u * b, 1);
-      mbar_init(bar_base + 192u + 8u * b, 128);
+      mbar_init(bar_base + BAR_TMEM_FULL + 8u * b, 1);
+      mbar_init(bar_base + BAR_TMEM_EMPTY + 8u * b, 128);
     }
-    mbar_init(bar_base + 256u, 1);
+    mbar_init(bar_base + BAR_B_RESIDENT, 1);
     for (int b = 0; b < 3; ++b) {
-      mbar_init(bar_base + 264u + 8u * b, 1);
-      mbar_init(bar_base + 288u + 8u * b, 1);
+      mbar_init(bar_base + BAR_B_FULL + 8u * b, 1);
+      mbar_init(bar_base + BAR_B_EMPTY + 8u * b, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -382,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t phase = 0;
     if (a.b_resident) {
       // the whole (single N tile) weight matrix stays in shared memory for the CTA's lifetime
-      const uint32_t bb = bar_base + 256u;
+      const uint32_t bb = bar_base + BAR_B_RESIDENT;
       mbar_expect_tx_p(leader, bb, a.b_bytes);
       const uint32_t b_tap = (uint32_t)a.bn * ROW_BYTES;        // resident B: one box per (fd,fh) tap
       for (int t = 0; t < a.kd * a.kh; ++t)
@@ -404,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int fh = 0; fh < a.kh; ++fh)
             for (int fw = 0; fw < a.kw; ++fw)
               for (int ch = 0; ch < a.kchunks; ++ch, kcoord += KC) {
-                mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);
+                mbar_wait(bar_base + BAR_EMPTY + 8u * stage, phase ^ 1u);
                 const uint32_t fb = bar_base + 8u * stage;
                 mbar_expect_tx_p(leader, fb, (two ? 2u : 1u) * a.a_bytes + a.b_bytes);
                 const uint32_t sa = smem_base + stage * stage_bytes;
@@ -428,8 +434,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       while (tg[0].tile < a.num_tiles) {
         for (int fd = 0; fd < a.kd; ++fd)
           for (int ch = 0; ch < a.kchunks; ++ch) {
-            mbar_wait(bar_base + 288u + 8u * bs, bphase ^ 1u);
-            const uint32_t bf = bar_base + 264u + 8u * bs;
+            mbar_wait(bar_base + BAR_B_EMPTY + 8u * bs, bphase ^ 1u);
+            const uint32_t bf = bar_base + BAR_B_FULL + 8u * bs;
             mbar_expect_tx_p(leader, bf, a.b_bytes);
             tma_load_2d(leader, smem_base + a.b_region + (uint32_t)bs * a.b_stage, &tmap_b, bf, 0,
                         (fd * a.kchunks + ch) * a.kh * a.bn);
@@ -439,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (j < G && tg[j].tile < a.num_tiles) {
                 const int iw0 = tg[j].tw * a.b_w * a.sw - a.pw, ih0 = tg[j].th * a.b_h * a.sh - a.ph;
                 const int id0 = tg[j].td * a.b_d * a.sd - a.pd, n0 = tg[j].tn * a.b_n;
-                mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);
+                mbar_wait(bar_base + BAR_EMPTY + 8u * stage, phase ^ 1u);
                 const uint32_t fb = bar_base + 8u * stage;
                 mbar_expect_tx_p(leader, fb, a.a_bytes);
                 tma_load_5d(leader, smem_base + stage * stage_bytes, &tmap_a, fb, ch * KC, iw0, ih0, id0 + fd, n0);
@@ -464,7 +470,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // tap is a swizzle-atom-aligned row offset into it; B holds the kh taps of that (fd, chunk)
         for (int fd = 0; fd < a.kd; ++fd)
           for (int ch = 0; ch < a.kchunks; ++ch) {
-            mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);
+            mbar_wait(bar_base + BAR_EMPTY + 8u * stage, phase ^ 1u);
             const uint32_t fb = bar_base + 8u * stage;
             mbar_expect_tx_p(leader, fb, a.a_bytes + a.b_bytes);
             const uint32_t sa = smem_base + stage * stage_bytes;
@@ -477,7 +483,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (a.halo) {
         // halo mode: the A box carries kd-1 / kh-1 extra planes / rows; every (fd,fh) tap is a
         // swizzle-atom-aligned row offset into it, so one load feeds all taps of the tile
-        mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);
+        mbar_wait(bar_base + BAR_EMPTY + 8u * stage, phase ^ 1u);
         const uint32_t fb = bar_base + 8u * stage;
         mbar_expect_tx_p(leader, fb, a.b_resident ? a.a_bytes : a.a_bytes + a.b_bytes);
         const uint32_t sa = smem_base + stage * stage_bytes;
@@ -495,7 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int fh = 0; fh < a.kh; ++fh)
           for (int fw = 0; fw < a.kw; ++fw)
             for (int ch = 0; ch < a.kchunks; ++ch, kcoord += KC) {
-              mbar_wait(bar_base + 64u + 8u * stage, phase ^ 1u);          // empty[stage]
+              mbar_wait(bar_base + BAR_EMPTY + 8u * stage, phase ^ 1u);          // empty[stage]
               const uint32_t fb = bar_base + 8u * stage;                   // full[stage]
               mbar_expect_tx_p(leader, fb, a.a_bytes + a.b_bytes);
               const uint32_t sa = smem_base + stage * stage_bytes;
@@ -518,7 +524,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     int buf = 0;
     if (a.b_resident) {
-      mbar_wait(bar_base + 256u, 0u);
+      mbar_wait(bar_base + BAR_B_RESIDENT, 0u);
       tc_fence_after();
     }
     if (a.twin) {
@@ -528,8 +534,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool two = tile + (int)gridDim.x < a.num_tiles;
         const uint32_t b0 = (uint32_t)(pp * 2), b1 = b0 + 1u;
         const uint32_t ep_ = pp ? eph[1] : eph[0];
-        mbar_wait(bar_base + 192u + 8u * b0, ep_ ^ 1u);
-        mbar_wait(bar_base + 192u + 8u * b1, ep_ ^ 1u);
+        mbar_wait(bar_base + BAR_TMEM_EMPTY + 8u * b0, ep_ ^ 1u);
+        mbar_wait(bar_base + BAR_TMEM_EMPTY + 8u * b1, ep_ ^ 1u);
         tc_fence_after();
         const uint32_t d0 = b0 * 128u, d1 = b1 * 128u;
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -539,10 +545,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t bl = dlo(sa + 2u * A_STAGE);
           tc_mma_k<KC / 16>(leader, d0, dlo(sa), bl, desc_hi32, idesc, ks > 0 ? 1u : 0u);
           if (two) tc_mma_k<KC / 16>(leader, d1, dlo(sa + A_STAGE), bl, desc_hi32, idesc, ks > 0 ? 1u : 0u);
-          tc_commit(leader, bar_base + 64u + 8u * stage);
+          tc_commit(leader, bar_base + BAR_EMPTY + 8u * stage);
           if (ks == ksteps - 1) {
-            tc_commit(leader, bar_base + 128u + 8u * b0);
-            if (two) tc_commit(leader, bar_base + 128u + 8u * b1);
+            tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * b0);
+            if (two) tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * b1);
           }
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
@@ -565,11 +571,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (tile0 + j * (int)gridDim.x < a.num_tiles) nvalid = j + 1;
         for (int j = 0; j < nvalid; ++j) {
           const uint32_t i = i0 + (uint32_t)j;
-          mbar_wait(bar_base + 192u + 8u * (i & bmask), ((i / (uint32_t)a.nbuf) & 1u) ^ 1u);
+          mbar_wait(bar_base + BAR_TMEM_EMPTY + 8u * (i & bmask), ((i / (uint32_t)a.nbuf) & 1u) ^ 1u);
         }
         tc_fence_after();
         for (int st = 0; st < nst; ++st) {
-          mbar_wait(bar_base + 264u + 8u * bs, bphase);
+          mbar_wait(bar_base + BAR_B_FULL + 8u * bs, bphase);
           tc_fence_after();
           const uint32_t sb = smem_base + a.b_region + (uint32_t)bs * a.b_stage;
           const uint32_t bl0 = dlo(sb);
@@ -587,18 +593,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tc_mma_k<KC / 16>(leader, d_tmem, al0 + (uint32_t)fh * a_fh, bl0 + (uint32_t)fh * b_tap, desc_hi32, idesc,
                                   (st > 0 || fh > 0) ? 1u : 0u);
             }
-            tc_commit(leader, bar_base + 64u + 8u * stage);
-            if (st == nst - 1) tc_commit(leader, bar_base + 128u + 8u * bj);
+            tc_commit(leader, bar_base + BAR_EMPTY + 8u * stage);
+            if (st == nst - 1) tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * bj);
             if (++stage == a.stages) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(leader, bar_base + 288u + 8u * bs);
+          tc_commit(leader, bar_base + BAR_B_EMPTY + 8u * bs);
           if (++bs == a.b_slots) { bs = 0; bphase ^= 1u; }
         }
       }
     }
     for (int tile = (a.twin || a.bshare) ? a.num_tiles : blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const uint32_t aph = buf ? acc_phase1 : acc_phase0;
-      mbar_wait(bar_base + 192u + 8u * buf, aph ^ 1u);                   // tmem_empty[buf]
+      mbar_wait(bar_base + BAR_TMEM_EMPTY + 8u * buf, aph ^ 1u);                   // tmem_empty[buf]
       tc_fence_after();
       const uint32_t d_tmem = (uint32_t)buf * 256u;                       // TMEM base is 0 (asserted)
       if (a.halo == 2) {
@@ -620,8 +626,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               acc = 1u;
             }
           }
-          tc_commit(leader, bar_base + 64u + 8u * stage);
-          if (st == nst - 1) tc_commit(leader, bar_base + 128u + 8u * buf);
+          tc_commit(leader, bar_base + BAR_EMPTY + 8u * stage);
+          if (st == nst - 1) tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * buf);
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
         if (buf) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
@@ -642,8 +648,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int fh = 0; fh < a.kh; ++fh, ++tap)
             tc_mma_k<KC / 16>(leader, d_tmem, al0 + (uint32_t)fd * a_fd + (uint32_t)fh * a_fh, bl0 + tap * b_tap, desc_hi32, idesc,
                               tap > 0 ? 1u : 0u);
-        tc_commit(leader, bar_base + 64u + 8u * stage);
-        tc_commit(leader, bar_base + 128u + 8u * buf);
+        tc_commit(leader, bar_base + BAR_EMPTY + 8u * stage);
+        tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * buf);
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         if (buf) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
         buf ^= 1;
@@ -654,8 +660,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         const uint32_t sa = smem_base + stage * stage_bytes;
         tc_mma_k<KC / 16>(leader, d_tmem, dlo(sa), dlo(sa + A_STAGE), desc_hi32, idesc, ks > 0 ? 1u : 0u);
-        tc_commit(leader, bar_base + 64u + 8u * stage);                    // frees the smem stage when the MMAs retire
-        if (ks == ksteps - 1) tc_commit(leader, bar_base + 128u + 8u * buf);   // tmem_full[buf]
+        tc_commit(leader, bar_base + BAR_EMPTY + 8u * stage);                    // frees the smem stage when the MMAs retire
+        if (ks == ksteps - 1) tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * buf);   // tmem_full[buf]
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       }
       if (buf) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
@@ -760,7 +766,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         last_nt = nt;
       }
 
-      mbar_wait(bar_base + 128u + 8u * buf, acc_phase);
+      mbar_wait(bar_base + BAR_TMEM_FULL + 8u * buf, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + buf_col;
       if (EC == 64 && a.pair_pool) {
@@ -788,7 +794,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_wait_ld();
           if (q == 3) {
             tc_fence_before();
-            mbar_arrive(bar_base + 192u + 8u * buf);
+            mbar_arrive(bar_base + BAR_TMEM_EMPTY + 8u * buf);
           }
           uint32_t pk[8];
 #pragma unroll
@@ -842,7 +848,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp
           // before the math / staging / store of this last chunk
           tc_fence_before();
-          mbar_arrive(bar_base + 192u + 8u * buf);
+          mbar_arrive(bar_base + BAR_TMEM_EMPTY + 8u * buf);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         const uint32_t s0 = my_stg + (uint32_t)slot * slot_bytes + (uint32_t)row * (EC * 2);
