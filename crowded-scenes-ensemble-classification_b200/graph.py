@@ -3,7 +3,7 @@
 One node per Keras layer of the reference model (including weight-less ones:
 InputLayer, Activation, Dropout, Flatten, ...), because
 
-* the CPU oracle (``oracle/nn_oracle.py``) interprets exactly this graph,
+* the tests compare it with the independently written CPU oracle (``oracle/models.py``; traces, FLOPs, parameters),
 * the device lowering (``lowering.py``) pattern-matches it into fused kernels,
 * Keras' ``model.layers`` order (needed to read ``*_weights.hdf5`` positionally,
   the way ``model.load_weights`` of the reference does, train.py:1731-1769)
