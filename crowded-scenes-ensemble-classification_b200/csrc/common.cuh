@@ -29,6 +29,19 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncSetAttribute (opt-in dynamic shared memory) is a per-DEVICE setting: one flag per device ordinal and
+// per kernel instantiation.  A racing second thread at worst sets the attribute twice.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  int dev = 0;
+  bool need() {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    dev &= 63;
+    return !done[dev];
+  }
+  void mark() { done[dev] = true; }
+};
 static inline size_t dtype_size(int dt) { return dt == CSE_F32 ? 4 : (dt == CSE_BF16 ? 2 : 1); }
 
 // ---- dtype load/store helpers ------------------------------------------------

@@ -21,6 +21,7 @@
 // (train.py:653-658, 1230-1258, 1294-1298 ...), with the fused bias / BatchNormalization /
 // ReLU / residual-add / second BN-ReLU output / channel-offset (concat) write epilogue.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -1304,10 +1305,10 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
 
 template <int KC, int EC>
 static int launch_tc_t(const ConvTcDesc& d, const ConvTcArgs& args, int grid, size_t smem_bytes, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     CSE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));
-    attr_set = true;
+    once.mark();
   }
   conv_tc_kernel<KC, EC><<<grid, TC_THREADS, smem_bytes, st>>>(d.tmap_a, d.tmap_b, d.tmap_o0, d.tmap_o1, d.tmap_o2, args);
   CSE_CUDA(cudaGetLastError());
@@ -1321,6 +1322,16 @@ static int launch_tc_kc(const ConvTcDesc& d, const ConvTcArgs& a, int grid, size
     case 32: return launch_tc_t<KC, 32>(d, a, grid, smem_bytes, st);
     default: return launch_tc_t<KC, 16>(d, a, grid, smem_bytes, st);
   }
+}
+
+// Tile-count thresholds of the shared-B / twin modes; -1 = the built-in default.  Set through cse_tune() (tests force
+// the modes on small shapes); never read from the environment on the launch path.
+struct TcTune { int bshare_min_tiles = -1, twin_min_tiles = -1; };
+static TcTune tc_tune;
+int conv_tc_tune(const char* key, int value) {
+  if (!strcmp(key, "bshare_min_tiles")) { tc_tune.bshare_min_tiles = value; return CSE_OK; }
+  if (!strcmp(key, "twin_min_tiles")) { tc_tune.twin_min_tiles = value; return CSE_OK; }
+  return CSE_ERR_INVALID;
 }
 
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st) {
@@ -1353,8 +1364,7 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   size_t smem_bytes = d.smem_bytes;
   a.twin = 0;
   a.bshare = 0; a.b_slots = 2; a.b_stage = 0; a.nbuf = 2; a.acc_cols = 256;
-  int bs_min = 8 * sm_count;
-  if (const char* e = getenv("CSE_BSHARE_MIN_TILES")) bs_min = atoi(e);      // tests force the shared-B path on small shapes
+  const int bs_min = tc_tune.bshare_min_tiles >= 0 ? tc_tune.bshare_min_tiles : 8 * sm_count;
   if (d.bs_group && bs_min > 0 && a.num_tiles >= bs_min) {
     a.bshare = d.bs_group; a.b_slots = d.bs_slots;
     a.nbuf = 2 * d.bs_group; a.acc_cols = 512u / (uint32_t)a.nbuf;
@@ -1362,8 +1372,7 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
     a.stage_region = d.bs_stage_region; a.nslots = d.bs_nslots;
     smem_bytes = d.bs_smem_bytes;
   }
-  int twin_min = 2 * sm_count;
-  if (const char* e = getenv("CSE_TWIN_MIN_TILES")) twin_min = atoi(e);      // tests force the twin path on small shapes
+  const int twin_min = tc_tune.twin_min_tiles >= 0 ? tc_tune.twin_min_tiles : 2 * sm_count;
   if (d.twin_ok && twin_min > 0 && a.num_tiles >= twin_min) {
     // enough tiles to keep every SM busy with tile pairs
     a.twin = 1;

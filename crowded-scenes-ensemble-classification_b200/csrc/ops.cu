@@ -561,7 +561,7 @@ maxpool3s1_sweep_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __r
 
 template <int WT, int NG>
 static int maxpool3s1_sweep_launch(const void* in, void* out, int n, const WinGeom& g, int vpc, cudaStream_t st) {
-  static bool attr_set = false;
+  static PerDeviceOnce once;
   // strip height: <= 224 threads x NG groups of WT pixels, equal strips
   const int per_row = (g.Wi / WT) * vpc;
   int hs = max(1, min(g.Hi, 224 * NG / per_row));
@@ -569,9 +569,9 @@ static int maxpool3s1_sweep_launch(const void* in, void* out, int n, const WinGe
   const int threads = ceil_div(ceil_div(hs * per_row, NG), 32) * 32;
   const size_t smem = (size_t)SWEEP_STAGES * (hs + 2) * g.Wi * vpc * sizeof(uint4);
   if (threads > 224 || smem > 72 * 1024) return -1;
-  if (!attr_set) {
+  if (once.need()) {
     CSE_CUDA(cudaFuncSetAttribute(maxpool3s1_sweep_kernel<WT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
+    once.mark();
   }
   const int nchunks = ceil_div(g.Co / 8, vpc);
   const int nstrips = ceil_div(g.Hi, hs);

@@ -29,6 +29,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return CSE_ERR_CUDA;
 }
 
+int conv_tc_tune(const char* key, int value);
 int vote_launch(const void* probs, int is_f64, const double* weights, int mode, int M, int N, int C,
                 int32_t* pred, double* summed, cudaStream_t st);
 int vote_search_launch(const double* probs, const double* weights, const int32_t* labels, int W, int M, int N,
@@ -105,6 +106,13 @@ int cse_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_major) *cc_major = mj;
   if (cc_minor) *cc_minor = mn;
   return CSE_OK;
+}
+
+int cse_tune(const char* key, int value) {
+  CSE_REQUIRE(key != nullptr, "tune: NULL key");
+  int rc = conv_tc_tune(key, value);
+  if (rc) set_error("tune: unknown key '%s'", key);
+  return rc;
 }
 
 int cse_plan_create(cse_plan** out, int max_batch, int nb_classes) {

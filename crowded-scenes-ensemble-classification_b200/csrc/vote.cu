@@ -17,10 +17,10 @@ constexpr int VOTE_BLOCK = 128;
 template <typename T>
 __global__ void __launch_bounds__(VOTE_BLOCK)
 vote_kernel(const T* __restrict__ probs, const double* __restrict__ weights, int mode, int M, int N, int C,
-            int32_t* __restrict__ pred, double* __restrict__ summed) {
-  extern __shared__ double tile[];   // [VOTE_BLOCK * C]
-  const int n0 = blockIdx.x * VOTE_BLOCK;
-  const int rows = min(VOTE_BLOCK, N - n0);
+            int32_t* __restrict__ pred, double* __restrict__ summed, int rows_per_block) {
+  extern __shared__ double tile[];   // [rows_per_block * C]
+  const int n0 = blockIdx.x * rows_per_block;
+  const int rows = min(rows_per_block, N - n0);
   const int tid = threadIdx.x;
   double acc[VOTE_MAX_C];
   double best = -INFINITY;
@@ -60,12 +60,14 @@ int vote_launch(const void* probs, int is_f64, const double* weights, int mode, 
   CSE_REQUIRE(M >= 1 && N >= 0 && C >= 1 && C <= VOTE_MAX_C, "vote: M=%d N=%d C=%d (C <= %d)", M, N, C, VOTE_MAX_C);
   CSE_REQUIRE(mode == 0 || mode == 1, "vote: mode %d", mode);
   if (N == 0) return CSE_OK;
-  const int blocks = ceil_div(N, VOTE_BLOCK);
-  const size_t smem = (size_t)VOTE_BLOCK * C * sizeof(double);
+  // the fp64 tile stays inside the 48 KB every kernel gets without an opt-in: C <= 48 -> 128 clips per block, else 64
+  const int rpb = (size_t)VOTE_BLOCK * C * sizeof(double) <= 48 * 1024 ? VOTE_BLOCK : VOTE_BLOCK / 2;
+  const int blocks = ceil_div(N, rpb);
+  const size_t smem = (size_t)rpb * C * sizeof(double);
   if (is_f64)
-    vote_kernel<double><<<blocks, VOTE_BLOCK, smem, st>>>((const double*)probs, weights, mode, M, N, C, pred, summed);
+    vote_kernel<double><<<blocks, VOTE_BLOCK, smem, st>>>((const double*)probs, weights, mode, M, N, C, pred, summed, rpb);
   else
-    vote_kernel<float><<<blocks, VOTE_BLOCK, smem, st>>>((const float*)probs, weights, mode, M, N, C, pred, summed);
+    vote_kernel<float><<<blocks, VOTE_BLOCK, smem, st>>>((const float*)probs, weights, mode, M, N, C, pred, summed, rpb);
   CSE_CUDA(cudaGetLastError());
   return CSE_OK;
 }

@@ -133,6 +133,13 @@ def convert_array2listofarrays(probabilities_array):
     return [p for p in probabilities_array]
 
 
+def _plain_ints(predictions):
+    """Predictions column of the results CSVs: plain Python ints.  The reference's consumers
+    ast.literal_eval this cell (evaluate_ensemble.py:424, 513, 553, 661); numpy >= 2 would print a list of
+    np.int64 scalars as "[np.int64(1), ...]", which literal_eval rejects."""
+    return [int(p) for p in predictions]
+
+
 class _ProbabilityCache:
     """One parse per (file, mtime) instead of one per call (evaluate_ensemble.py:345)."""
 
@@ -349,6 +356,54 @@ class MemberGather:
         return self.full
 
 
+def shard_units(costs, n_clips: int, world: int, chunk: int = 0):
+    """2-D partition of an ensemble step over the ranks: work units are (member, clip chunk) pairs, so that heavy
+    members (one I3D-64 member is 17.8 % of the global C3D + I3D + R3D-34 step) are split across GPUs instead of
+    bounding the step.  Every member's clips are cut into chunks of `chunk` clips (default ceil(n_clips / world));
+    units go, in decreasing cost (cost = member FLOPs per clip x clips; ties: member, then chunk order), to the
+    least loaded rank (ties -> lowest rank).  With members x chunks that divide evenly this degenerates to plain
+    clip sharding (rank r runs chunk r of every member).  -> one list of (member, lo, hi) per rank, sorted;
+    deterministic, identical on every rank."""
+    costs = [float(c) for c in costs]
+    chunk = int(chunk) if chunk else -(-int(n_clips) // int(world))
+    chunk = max(1, chunk)
+    units = [(m, lo, min(lo + chunk, n_clips)) for m in range(len(costs)) for lo in range(0, n_clips, chunk)]
+    load = [0.0] * world
+    owned = [[] for _ in range(world)]
+    for u in sorted(units, key=lambda u: (-costs[u[0]] * (u[2] - u[1]), u[0], u[1])):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owned[r].append(u)
+        load[r] += costs[u[0]] * (u[2] - u[1])
+    return [sorted(o) for o in owned]
+
+
+class UnitGather:
+    """Merges the per-rank probability blocks of a unit-sharded step (shard_units) into the full [M, N, C] block on
+    every rank.  Each (member, clip) row is produced by exactly one rank and is zero everywhere else, so ONE
+    all-reduce(SUM) of the fp32 block is exact in any reduction order (x + 0 + ... + 0 = x bit for bit; probabilities
+    are positive).  The soft vote that follows still runs over all M members in member order in fp64, identical to
+    the single-process vote.  The buffer is allocated once; no host <-> device traffic in the step."""
+
+    def __init__(self, units, m_total: int, n_clips: int, nb_classes: int, dist, world: int, device):
+        import torch
+        self.units, self.dist, self.world = units, dist, int(world)
+        seen = np.zeros((m_total, n_clips), np.int32)
+        for owned in units:
+            for m, lo, hi in owned:
+                seen[m, lo:hi] += 1
+        if not (seen == 1).all():
+            raise ValueError("units must cover every (member, clip) exactly once")
+        self.full = torch.zeros((m_total, n_clips, nb_classes), dtype=torch.float32, device=device)
+
+    def __call__(self, local):
+        """local: [M, N, C] fp32 with this rank's units filled in and zeros elsewhere -> the full block."""
+        if self.world == 1:
+            return local
+        self.full.copy_(local)
+        self.dist.all_reduce(self.full)
+        return self.full
+
+
 def gather_member_probs(local, owned, m_total: int, dist, world: int):
     """One-shot form of MemberGather."""
     return MemberGather(owned, m_total, dist, world)(local)
@@ -547,7 +602,7 @@ def evaluate_ensembles(trained_models_folder, results_folder, weights_type, hist
             accuracy, single_model_predictions = evaluate_single_model(trained_model_path, test_labels,
                                                                        test_probabilities_file, nb_classes)
             print("Model val %d : %f" % (val_index, accuracy))
-            store_models_predictions.append([trained_model_path, convert_array2listofarrays(single_model_predictions)])
+            store_models_predictions.append([trained_model_path, _plain_ints(single_model_predictions)])
             trained_model_paths.append(trained_model_path)
         ensemble_models_number = nb_folds - 1
         weights = None
@@ -576,7 +631,7 @@ def evaluate_ensembles(trained_models_folder, results_folder, weights_type, hist
             trained_model_paths, weights, test_probabilities_file, test_labels, nb_classes)
         print("Fold %d : %f" % (test_index, ensemble_model_accuracy))
         ensemble_model_name = "Ensemble_" + models_name + "_split_test" + str(test_index)
-        store_models_predictions.append([ensemble_model_name, convert_array2listofarrays(ensemble_model_predictions)])
+        store_models_predictions.append([ensemble_model_name, _plain_ints(ensemble_model_predictions)])
     csv_file_path = os.path.join(results_folder, "weighted_prediction_results_" + models_name + ".csv")
     if _dist()[1] == 0:
         pd.DataFrame(store_models_predictions, columns=["path", "predictions"]).to_csv(csv_file_path)
@@ -589,9 +644,14 @@ def evaluate_ensembles(trained_models_folder, results_folder, weights_type, hist
 # Global_evaluate_models / Combine_ensembles (evaluate_ensemble.py:1280-1474)
 # --------------------------------------------------------------------------- #
 def compute_combinations(models_list):
+    """Every non-empty subset of models_list (evaluate_ensemble.py:1280-1295).  The reference builds each size
+    class through set(), whose order depends on per-process string hashing; under torchrun every rank must walk
+    the combinations in the SAME order (they meet in collectives inside global_evaluate_ensembles), so the
+    deterministic itertools order is kept (duplicates in models_list are dropped, as set() would)."""
+    models_list = list(dict.fromkeys(models_list))
     combinations = []
     for k in range(1, len(models_list) + 1):
-        combinations.append(list(set(itertools.combinations(models_list, k))))
+        combinations.append(list(itertools.combinations(models_list, k)))
     combinations = list(itertools.chain.from_iterable(combinations))
     return len(combinations), combinations
 
@@ -666,7 +726,7 @@ def global_evaluate_ensembles(nb_folds, trained_models_parent_folder, models_lis
         store_models_accuracies.append(accuracy)
         print("Fold %d : %f" % (test_index, accuracy))
         store_models_predictions.append(["Global_Ensemble_" + all_models_names_string + "_split_test" +
-                                         str(test_index), convert_array2listofarrays(predictions)])
+                                         str(test_index), _plain_ints(predictions)])
     csv_file_path = os.path.join(results_folder, "global_ensemble_summed_prediction_results_" + str(nb_folds) +
                                  "_folds_" + all_models_names_string + "_.csv")
     if _dist()[1] == 0:

@@ -74,6 +74,24 @@ class DeviceEnsemble:
         self.last_launches = launches
         return n
 
+    def forward_subset(self, inputs_u8, member_ids, lo: int = 0):
+        """Runs only the members `member_ids` (indices into self.members) on the given clips and writes their rows
+        probs[j, lo : lo + n] (unit-sharded steps: this rank owns clip chunk [lo, lo + n) of these members)."""
+        n = inputs_u8[0].shape[0]
+        if lo + n > self.max_batch:
+            raise ValueError("clip range [%d, %d) exceeds max_batch %d" % (lo, lo + n, self.max_batch))
+        launches = 0
+        mb = self.micro_batch
+        for i in range(0, n, mb):
+            chunk = [x[i:i + mb] for x in inputs_u8]
+            for k, j in enumerate(member_ids):
+                m = self.members[j]
+                m.forward_device(chunk, self.logits[j, lo + i:lo + i + mb], self.probs[j, lo + i:lo + i + mb],
+                                 skip_input_ops=self.share_input and k > 0)
+                launches += m.launches
+        self.last_launches += launches
+        return n
+
     def vote(self, n):
         probs = self.probs[:, :n].contiguous() if n != self.max_batch else self.probs
         pred = rt.vote(probs, self.vote_weights, self.vote_mode)
@@ -186,6 +204,7 @@ class HeteroEnsemble:
         self.last_launches = 0
         # set by the caller when the members are sharded over the ranks (ensemble.gather_member_probs)
         self.gather = None
+        self._unit_plan = None
 
     @property
     def micro_batch(self):
@@ -193,8 +212,13 @@ class HeteroEnsemble:
 
     def predict_device(self, group_inputs):
         """group_inputs[k] = list of uint8 CUDA tensors for architecture k (same n for all)."""
+        if getattr(self, "_unit_plan", None) is not None:
+            return self.predict_units(group_inputs)
         n = group_inputs[0][0].shape[0]
         launches = 0
+        if self.torch.cuda.current_device() != self.device.index:
+            raise rt.CseError("HeteroEnsemble on %s called while cuda:%d is current; wrap the call in "
+                              "torch.cuda.device(ens.device)" % (self.device, self.torch.cuda.current_device()))
         for ens, inputs in zip(self.groups, group_inputs):
             if inputs[0].shape[0] != n:
                 raise ValueError("every architecture must see the same clips")
@@ -207,53 +231,97 @@ class HeteroEnsemble:
         self.last_launches = launches + 1
         return pred
 
+    def set_units(self, my_units, gather):
+        """Unit-sharded step (ensemble.shard_units): this rank runs only `my_units` = [(member, lo, hi)] (global
+        member index in group order) and `gather` (ensemble.UnitGather) merges the blocks of all ranks."""
+        plan = []
+        m0 = 0
+        for ens in self.groups:
+            by_range = {}
+            for m, lo, hi in my_units:
+                if m0 <= m < m0 + ens.M:
+                    by_range.setdefault((lo, hi), []).append(m - m0)
+            plan.append(sorted(by_range.items()))
+            m0 += ens.M
+        self._unit_plan, self.gather = plan, gather
+
+    def predict_units(self, group_inputs):
+        """group_inputs as in predict_device (all n clips; only the owned ranges are read)."""
+        n = group_inputs[0][0].shape[0]
+        self.probs.zero_()
+        launches = 1
+        for ens, inputs, ranges in zip(self.groups, group_inputs, self._unit_plan):
+            ens.last_launches = 0
+            for (lo, hi), member_ids in ranges:
+                ens.forward_subset([x[lo:hi] for x in inputs], member_ids, lo)
+            launches += ens.last_launches
+        probs = self.probs[:, :n].contiguous() if n != self.max_batch else self.probs
+        probs = self.gather(probs)
+        pred = rt.vote(probs, self.vote_weights, self.vote_mode)
+        self.last_launches = launches + 1
+        return pred
+
     def predict_host(self, host_group_inputs):
         dev = [[h.to(self.device, non_blocking=True) for h in inputs] for inputs in host_group_inputs]
         return self.predict_device(dev).cpu().numpy()
 
-    def stream_host(self, batches):
-        """Pipelined host path: `batches` yields pinned uint8 host inputs (group_inputs layout); the
-        H2D copy of batch i+1 runs on a copy stream while batch i computes (two device buffer sets).
-        Yields the int32 prediction tensor (device) of every batch, in order; the caller reads it back."""
+    def _pipeline(self, batch, depth: int):
+        """Copy stream, `depth` device buffer sets and their ready / free events, created once and reused by every
+        stream_host call (they live on the object, like the buffers they guard)."""
         torch = self.torch
-        comp = torch.cuda.current_stream()
-        if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._dev_bufs = [None, None]
-        copy = self._copy_stream
-        ready = [None, None]
-        free = [None, None]
+        shapes = [[tuple(h.shape) for h in hs] for hs in batch]
+        p = getattr(self, "_pipe", None)
+        if p is None or p["shapes"] != shapes or p["depth"] != depth:
+            with torch.cuda.device(self.device):
+                p = {"shapes": shapes, "depth": depth, "copy": torch.cuda.Stream(device=self.device),
+                     "bufs": [[[torch.empty(sh, dtype=torch.uint8, device=self.device) for sh in hs] for hs in shapes]
+                              for _ in range(depth)],
+                     "ready": [torch.cuda.Event() for _ in range(depth)],
+                     "free": [torch.cuda.Event() for _ in range(depth)],
+                     "used": [False] * depth}
+            self._pipe = p
+        return p
 
-        def upload(k, batch):
-            if self._dev_bufs[k] is None or any(d.shape != h.shape for ds, hs in zip(self._dev_bufs[k], batch)
-                                                for d, h in zip(ds, hs)):
-                self._dev_bufs[k] = [[torch.empty(h.shape, dtype=torch.uint8, device=self.device) for h in hs]
-                                     for hs in batch]
-            with torch.cuda.stream(copy):
-                if free[k] is not None:
-                    copy.wait_event(free[k])         # the compute that read this buffer set has finished
-                for ds, hs in zip(self._dev_bufs[k], batch):
-                    for d, h in zip(ds, hs):
-                        d.copy_(h, non_blocking=True)
-                ready[k] = torch.cuda.Event()
-                ready[k].record(copy)
-
+    def stream_host(self, batches, depth: int = 3):
+        """Pipelined host path: `batches` yields pinned uint8 host inputs (group_inputs layout); the H2D copies of
+        the next depth-1 batches run on a copy stream while batch i computes.  Yields the int32 prediction tensor
+        (device) of every batch, in order; the caller reads it back.  The buffer sets and their events persist on
+        the object: a later call (or one started after an abandoned generator) first waits, on the copy stream,
+        for the compute that last read the buffer set it is about to overwrite."""
+        torch = self.torch
         it = iter(batches)
-        nxt = next(it, None)
-        k = 0
-        if nxt is not None:
-            upload(0, nxt)
-        while nxt is not None:
-            cur_k = k
-            nxt = next(it, None)
-            if nxt is not None:
-                upload(cur_k ^ 1, nxt)
-            comp.wait_event(ready[cur_k])
-            pred = self.predict_device(self._dev_bufs[cur_k])
-            free[cur_k] = torch.cuda.Event()
-            free[cur_k].record(comp)
-            yield pred
-            k ^= 1
+        first = next(it, None)
+        if first is None:
+            return
+        with torch.cuda.device(self.device):
+            comp = torch.cuda.current_stream()
+            p = self._pipeline(first, depth)
+            copy = p["copy"]
+
+            def upload(k, batch):
+                with torch.cuda.stream(copy):
+                    if p["used"][k]:
+                        copy.wait_event(p["free"][k])     # the compute that read this buffer set has finished
+                    for ds, hs in zip(p["bufs"][k], batch):
+                        for d, h in zip(ds, hs):
+                            d.copy_(h, non_blocking=True)
+                    p["ready"][k].record(copy)
+
+            queue = []                     # buffer sets uploaded and not yet computed, in order
+            nxt_slot = 0
+            pending = first
+            while pending is not None or queue:
+                while pending is not None and len(queue) < depth:
+                    upload(nxt_slot, pending)
+                    queue.append(nxt_slot)
+                    nxt_slot = (nxt_slot + 1) % depth
+                    pending = next(it, None)
+                k = queue.pop(0)
+                comp.wait_event(p["ready"][k])
+                pred = self.predict_device(p["bufs"][k])
+                p["free"][k].record(comp)
+                p["used"][k] = True
+                yield pred
 
     def profile_ops(self, group_inputs, iters: int = 2):
         out = []

@@ -18,7 +18,7 @@ ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 OP_PREPROCESS, OP_CONV3D, OP_MAXPOOL3D, OP_AVGPOOL3D, OP_AFFINE, OP_ADD, OP_SOFTMAX = 1, 2, 3, 4, 5, 6, 7
 OP_NAMES = {1: "preprocess", 2: "conv3d", 3: "maxpool3d", 4: "avgpool3d", 5: "affine", 6: "add", 7: "softmax"}
 
-EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_plan_create", "cse_plan_add_op",
+EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_tune", "cse_plan_create", "cse_plan_add_op",
            "cse_plan_finalize", "cse_plan_run", "cse_plan_run_from", "cse_plan_num_input_ops", "cse_plan_run_range",
            "cse_plan_num_ops",
            "cse_plan_last_launches", "cse_plan_destroy", "cse_preprocess", "cse_vote", "cse_vote_search",
@@ -65,6 +65,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cse_abi_version.restype = C.c_int
     lib.cse_last_error.restype = C.c_char_p
     lib.cse_device_info.argtypes = [C.POINTER(C.c_int)] * 3
+    lib.cse_tune.argtypes = [C.c_char_p, i32]
     lib.cse_plan_create.argtypes = [C.POINTER(vp), i32, i32]
     lib.cse_plan_add_op.argtypes = [vp, C.POINTER(CseOp)]
     lib.cse_plan_finalize.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i64, i64]
@@ -100,6 +101,11 @@ def require_cuda():
     if not torch.cuda.is_available():
         raise CseError("no CUDA device: the cse_b200 hot path has no CPU fallback")
     return torch
+
+
+def tune(key: str, value: int) -> None:
+    """cse_tune: override a launch heuristic (tests force the twin / shared-B conv modes on small shapes)."""
+    check(load_library().cse_tune(key.encode(), int(value)))
 
 
 def device_info():

@@ -175,3 +175,62 @@ def test_member_sharded_probabilities_match_single_process(tmp_path, world):
         got = np.load(str(tmp_path / ("mrank%d.npy" % r)))
         assert got.shape == ref.shape == (5, N_CLIPS, C)
         assert np.array_equal(got, ref), "rank %d: member-sharded gather differs" % r
+
+
+# --------------------------------------------------------------------------- (member, clip-chunk) units
+def test_shard_units_balances_and_covers():
+    """LPT over (member, clip chunk) units: the global C3D + I3D-64 + R3D-34 ensemble (4 members each) on 256 clips;
+    every (member, clip) owned exactly once; load within one unit of perfect; 8 ranks = plain clip sharding."""
+    costs = [77.1] * 4 + [222.3] * 4 + [13.3] * 4
+    for world in (1, 2, 3, 5, 8):
+        units = E.shard_units(costs, 256, world)
+        assert units == E.shard_units(costs, 256, world)
+        seen = np.zeros((12, 256), int)
+        for owned in units:
+            for m, lo, hi in owned:
+                seen[m, lo:hi] += 1
+        assert (seen == 1).all()
+        load = [sum(costs[m] * (hi - lo) for m, lo, hi in o) for o in units]
+        biggest = max(costs) * -(-256 // world)
+        assert max(load) - min(load) <= biggest
+        assert max(load) <= sum(costs) * 256 / world + biggest
+    u8 = E.shard_units(costs, 256, 8)
+    assert all(sorted(o) == [(m, 32 * r, 32 * r + 32) for m in range(12)] for r, o in enumerate(u8))
+    # ragged: 23 clips on 3 ranks, one heavy member is split over all ranks
+    u3 = E.shard_units([10.0, 1.0], 23, 3)
+    assert all(any(m == 0 for m, _, _ in o) for o in u3)
+
+
+def _unit_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        costs = [3.0, 1.0, 2.0, 5.0, 1.0]
+        units = E.shard_units(costs, N_CLIPS, world)
+        seq = FakeSequence(N_CLIPS)
+        x = torch.from_numpy(seq.clips).to(torch.float32)
+        feat = x.reshape(N_CLIPS, -1)
+        local = torch.zeros((5, N_CLIPS, C), dtype=torch.float32)
+        for m, lo, hi in units[rank]:                       # only this rank's (member, clip-chunk) units
+            logits = torch.stack([(feat[lo:hi, (c + m)::C]).mean(dim=1) * (1 + 0.01 * c) for c in range(C)], dim=1)
+            local[m, lo:hi] = torch.softmax(logits / 16.0, dim=1)
+        gather = E.UnitGather(units, 5, N_CLIPS, C, dist, world, torch.device("cpu"))
+        np.save(os.path.join(out_dir, "urank%d.npy" % rank), gather(local).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_unit_sharded_probabilities_match_single_process(tmp_path, world):
+    """(member, clip-chunk) units sharded over the ranks, merged by one all-reduce of disjoint blocks: every rank must
+    hold the single-process [M, N, C] block bit for bit, hence vote identically."""
+    seq = FakeSequence(N_CLIPS)
+    feat = torch.from_numpy(seq.clips).to(torch.float32).reshape(N_CLIPS, -1)
+    ref = np.stack([torch.softmax(torch.stack([(feat[:, (c + m)::C]).mean(dim=1) * (1 + 0.01 * c) for c in range(C)],
+                                              dim=1) / 16.0, dim=1).numpy() for m in range(5)])
+    mp.spawn(_unit_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(str(tmp_path / ("urank%d.npy" % r)))
+        assert np.array_equal(got, ref), "rank %d: unit-sharded merge differs" % r

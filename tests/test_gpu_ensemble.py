@@ -7,7 +7,6 @@ oracle: probabilities CSV (bf16 tolerance on the values, exact on the wire forma
 (:1161, :1406), GRID_SEARCH weights (:322-339) and the global ensemble (:1329-1474)."""
 import ast
 import os
-import re
 from itertools import product
 
 import numpy as np
@@ -99,7 +98,7 @@ def test_evaluate_ensembles_sum_end_to_end(dataset, monkeypatch):
     assert list(df.columns[1:]) == ["path", "probabilities"] and len(df) == FOLDS * (FOLDS - 1)
     table = {p: OV.parse_probabilities_cell(c) for p, c in zip(df["path"], df["probabilities"])}     # reference's parser
     preds = pd.read_csv(pred_csv)
-    pred_table = {p: ast.literal_eval(re.sub(r"np\.int64\((\d+)\)", r"\1", c)) for p, c in zip(preds["path"], preds["predictions"])}
+    pred_table = {p: ast.literal_eval(c) for p, c in zip(preds["path"], preds["predictions"])}
     for i in range(FOLDS):
         members = []
         for j in [k for k in range(FOLDS) if k != i]:
@@ -134,7 +133,7 @@ def test_cached_probabilities_are_reused(dataset, monkeypatch):
     df = pd.read_csv(prob_csv)
     table = {p: OV.parse_probabilities_cell(c) for p, c in zip(df["path"], df["probabilities"])}
     preds = pd.read_csv(pred_csv)
-    pred_table = {p: ast.literal_eval(re.sub(r"np\.int64\((\d+)\)", r"\1", c)) for p, c in zip(preds["path"], preds["predictions"])}
+    pred_table = {p: ast.literal_eval(c) for p, c in zip(preds["path"], preds["predictions"])}
     for i in range(FOLDS):
         keys = [os.path.join(ds["sub"], "TestSplit%d" % i, "%s_split_test%d_val%d_weights" % (ds["name"], i, j))
                 for j in range(FOLDS) if j != i]

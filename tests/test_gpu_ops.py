@@ -24,6 +24,21 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 T64 = torch.float64
 
+_tuned = set()
+
+
+def tune(key, value):
+    """cse_tune with automatic reset to the built-in default after the test (see _reset_tuning)."""
+    _tuned.add(key)
+    rt.tune(key, value)
+
+
+@pytest.fixture(autouse=True)
+def _reset_tuning():
+    yield
+    while _tuned:
+        rt.tune(_tuned.pop(), -1)
+
 
 def bf16_round(a):
     return torch.as_tensor(np.asarray(a, np.float32)).to(torch.bfloat16).to(torch.float64)
@@ -213,11 +228,11 @@ TWIN_CASES = [((4, 8, 8), 64, 128, (3, 3, 3), 2), ((5, 9, 9), 192, 64, (1, 1, 1)
 
 
 @pytest.mark.parametrize("dhw,cin,cout,k,nb", TWIN_CASES)
-def test_conv_tcgen05_twin_tiles(dhw, cin, cout, k, nb, monkeypatch):
+def test_conv_tcgen05_twin_tiles(dhw, cin, cout, k, nb):
     """Twin-tile mode (two M tiles share every weight stage, four TMEM accumulators), forced on small
     shapes so that even and odd tile counts, several tiles per CTA and the residual / second-output
     epilogue all run through it."""
-    monkeypatch.setenv("CSE_TWIN_MIN_TILES", "2")
+    tune("twin_min_tiles", 2)
 
     def build(g):
         x = g.input(dhw + (3,), name="in")
@@ -239,7 +254,7 @@ def test_conv_tcgen05_twin_tiles(dhw, cin, cout, k, nb, monkeypatch):
     assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
 
 
-def test_twin_tiles_whole_r3d_matches_default(monkeypatch):
+def test_twin_tiles_whole_r3d_matches_default():
     """R3D_18 (residual + second-output epilogues, strided convs) with the twin path forced everywhere
     it is legal gives bit-identical logits to the default tiling: same products, same per-tile
     accumulation order."""
@@ -247,10 +262,10 @@ def test_twin_tiles_whole_r3d_matches_default(monkeypatch):
     g = G.build_model_graph("R3D_18", shape, 11)
     w = synthetic_weights(g, seed=5, nontrivial=True)
     x = torch.from_numpy(clips(30, 3, shape)).cuda()
-    monkeypatch.setenv("CSE_TWIN_MIN_TILES", "0")
+    tune("twin_min_tiles", 0)
     base, _ = Member(g, w, precision="bf16", max_batch=3).forward_device([x])
     base = base.cpu().numpy()
-    monkeypatch.setenv("CSE_TWIN_MIN_TILES", "2")
+    tune("twin_min_tiles", 2)
     twin, _ = Member(g, w, precision="bf16", max_batch=3).forward_device([x])
     assert np.array_equal(base, twin.cpu().numpy())
 
@@ -310,7 +325,7 @@ def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb, halo):
 
 
 @pytest.mark.parametrize("dhw,c,cout,nb", S2D_STEM + [((16, 48, 48), 2, 64, 5), ((10, 30, 44), 1, 32, 3), ((12, 40, 40), 2, 128, 2)])
-def test_conv_tcgen05_s2d_stem_shared_weights(dhw, c, cout, nb, monkeypatch):
+def test_conv_tcgen05_s2d_stem_shared_weights(dhw, c, cout, nb):
     """Shared-B h-halo mode (groups of 4 tiles of a CTA use one weight block per (fd, chunk), 8 TMEM
     accumulators; taken by the 1- and 2-channel stems whose K chunk is 32), forced on small shapes: full / partial tile groups, several groups per CTA, ragged
     bricks.  Must be bit-identical to the per-tile weight streaming (same MMA sequence per tile)."""
@@ -320,12 +335,12 @@ def test_conv_tcgen05_s2d_stem_shared_weights(dhw, c, cout, nb, monkeypatch):
         x = g.bn(x, scale=True, name="b")
         g.relu(x, name="r")
     xs = clips(11, nb, dhw + (c,))
-    monkeypatch.setenv("CSE_BSHARE_MIN_TILES", "0")          # off
+    tune("bshare_min_tiles", 0)          # off
     g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c)
     run(m, [xs])
     ref = m.read_tensor(m.plan.tensors["r"], nb)
     del m
-    monkeypatch.setenv("CSE_BSHARE_MIN_TILES", "1")          # always
+    tune("bshare_min_tiles", 1)          # always
     g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c)
     assert [o for o in m.plan.ops if o.name == "c"][0].halo == 2
     run(m, [xs])
