@@ -53,13 +53,23 @@ WORKLOADS = {
 }
 
 
-def workload_config(name, groups, batch, world, by_members=False):
-    par = ("members sharded over %d GPU(s) by FLOPs, every GPU runs all %d clips, 1 all-gather of the fp32 member "
-           "probabilities per step, vote in member order" % (world, batch)) if by_members else (
-           "clips sharded over %d GPU(s), members replicated, 1 all-gather of int32 predictions per step" % world)
+def workload_config(name, groups, batch, world, shard="clips"):
+    """The `config` object of the JSON line - identical in both arms (ours and --impl reference)."""
+    par = {"members": "members sharded over %d GPU(s) by FLOPs, every GPU runs all %d clips, 1 all-gather of the fp32 member "
+                      "probabilities per step, vote in member order" % (world, batch),
+           "units": "ONE batch of %d clips: (member, clip-chunk) units spread over %d GPU(s) by FLOPs, 1 all-reduce of the "
+                    "disjoint fp32 probability blocks per step, vote in member order" % (batch, world),
+           "clips": "clips sharded over %d GPU(s), members replicated, 1 all-gather of int32 predictions per step" % world}[shard]
+    chans = lambda mt, shape: 5 if mt == "TWOSTREAM_I3D" else shape[3]
+    in_mb = sum(batch * shape[0] * shape[1] * shape[2] * chans(mt, shape) for mt, shape, _, _ in groups) >> 20
+    l2 = ("input batch (%d MB uint8) and activations exceed the 126 MB L2" % in_mb) if in_mb > 126 else (
+        "input batch %d MB uint8; every member streams its own weights and activations (> L2 per step)" % in_mb)
     return {"workload": name, "models": [g[0] for g in groups], "clips": [list(g[1]) for g in groups],
             "members": [g[2] for g in groups], "batch_per_gpu": batch, "vote": "SUM", "classes": 11,
-            "parallelism": par}
+            "parallelism": par, "l2_policy": l2,
+            "cpu_sample_clips": cpu_sample_size(groups),
+            "cpu_sample_note": "the CPU arm (cpu_baseline / --impl reference) runs a bounded sample of this workload: "
+                               "cpu_sample_clips clips x all members per step"}
 
 
 def load_peaks():
@@ -194,43 +204,51 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- our arm
-def run_ours(args):
+def measure(name, args, steps, warmup, headline):
+    """Builds the ensemble of workload `name` on this rank's GPU, times `steps` resident steps and `steps` end-to-end
+    steps, self-checks the predictions it timed, profiles every op launch (rank 0) and returns the result dict."""
     import torch
     import torch.distributed as dist
     from cse_b200 import graph as G, runtime as rt
     from cse_b200.ensemble_runtime import HeteroEnsemble
     from cse_b200.weights import synthetic_weights
+    from oracle import vote as OV
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rt.load_library()
-    groups, batch = WORKLOADS[args.workload]
-    if args.batch:
-        batch = args.batch
-    if args.members:
-        groups = [(mt, shape, args.members, mb) for mt, shape, _, mb in groups]
-    if args.micro_batch:
-        groups = [(mt, shape, m, args.micro_batch) for mt, shape, m, _ in groups]
+    groups, batch = WORKLOADS[name]
+    if headline:
+        if args.batch:
+            batch = args.batch
+        if args.members:
+            groups = [(mt, shape, args.members, mb) for mt, shape, _, mb in groups]
+        if args.micro_batch:
+            groups = [(mt, shape, m, args.micro_batch) for mt, shape, m, _ in groups]
+    shard = args.shard if headline else ("units" if name in STRONG_WORKLOADS else "clips")
+    by_members = shard == "members" and world > 1
+    by_units = shard == "units" and world > 1
+    strong = by_members or by_units
     groups = [(mt, shape, m, min(mb, batch)) for mt, shape, m, mb in groups]
     lower_kw = json.loads(os.environ.get("CSE_LOWER_KW", "{}"))      # lowering experiments (e.g. {"fuse_pool": false})
-    by_members = args.shard == "members" and world > 1
     all_graphs = [G.build_model_graph(mt, shape, 11) for mt, shape, _, _ in groups]
     members = sum(m for _, _, m, _ in groups)
-    owned_all = None
-    mine = None
+    costs = [g.total_flops() for g, (_, _, m, _) in zip(all_graphs, groups) for _ in range(m)]
+    owned_all = mine = units = None
     if by_members:
         # member-sharded partition (SURVEY 8e): every rank sees all clips and runs only the members it
         # owns (balanced by FLOPs per clip); probabilities are all-gathered into member order
         from cse_b200.ensemble import shard_members, MemberGather
         if world > members:
             raise SystemExit("--shard members needs at least one member per rank (%d members, %d ranks)" % (members, world))
-        costs = [g.total_flops() for g, (_, _, m, _) in zip(all_graphs, groups) for _ in range(m)]
         owned_all = shard_members(costs, world)
         mine = set(owned_all[rank])
+    if by_units:
+        # (member, clip-chunk) units spread over the ranks by FLOPs: strong scaling of ONE batch (latency mode)
+        from cse_b200.ensemble import shard_units, UnitGather
+        units = shard_units(costs, batch, world)
+        longest = max(hi - lo for o in units for _, lo, hi in o)
+        groups = [(mt, shape, m, min(mb, longest)) for mt, shape, m, mb in groups]
     built, graphs = [], []
     flat = 0
     for gi, ((mt, shape, m, mb), g) in enumerate(zip(groups, all_graphs)):
@@ -243,7 +261,9 @@ def run_ours(args):
     del built
     if by_members:
         ens.gather = MemberGather(owned_all, members, dist, world)
-    gen = torch.Generator(device="cpu").manual_seed(1234 + (0 if by_members else rank))
+    if by_units:
+        ens.set_units(units[rank], UnitGather(units, members, batch, 11, dist, world, ens.device))
+    gen = torch.Generator(device="cpu").manual_seed(1234 + (0 if strong else rank))
     host = [[torch.randint(0, 256, (batch,) + tuple(g.shape(n)), dtype=torch.uint8, generator=gen).pin_memory()
              for n in g.inputs] for g in graphs]
     dev_in = [[h.cuda() for h in hs] for hs in host]
@@ -255,14 +275,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # N > 1: clips are sharded over the ranks (members replicated); the one exchange of the path is
-    # the all-gather of the per-clip predictions (evaluate_ensemble.py:1262-1268 writes them all)
-    gathered = torch.empty((world * batch,), dtype=torch.int32, device="cuda") if world > 1 and not by_members else None
+    # N > 1, clips sharded over the ranks (members replicated): the one exchange of the path is the all-gather of
+    # the per-clip predictions (evaluate_ensemble.py:1262-1268 writes them all)
+    gathered = torch.empty((world * batch,), dtype=torch.int32, device="cuda") if world > 1 and not strong else None
 
     def step_resident():
         pred = ens.predict_device(dev_in)
-        if by_members:
-            return pred                  # every rank voted on the gathered [M, batch, C] block
+        if strong:
+            return pred                  # every rank voted on the merged [M, batch, C] block
         if world > 1:
             dist.all_gather_into_tensor(gathered, pred)
             return gathered
@@ -271,23 +291,20 @@ def run_ours(args):
     pinned_pred = torch.empty((world * batch,), dtype=torch.int32).pin_memory()
 
     def run_e2e(nsteps):
-        """Host API: every step uploads its pinned uint8 batch (H2D on a copy stream, overlapped with
-        the previous step's compute), runs members + vote (+ all-gather), and reads the predictions
-        back (D2H); all of it inside the timed region."""
-        out = None
+        """Host API: every step uploads its pinned uint8 batch (H2D on a copy stream, overlapped with the previous
+        steps' compute), runs members + vote (+ exchange), and reads the predictions back (D2H); all of it inside
+        the timed region."""
         for pred in ens.stream_host(host for _ in range(nsteps)):
-            if by_members:
+            if strong or world == 1:
                 pinned_pred[:batch].copy_(pred, non_blocking=True)
-            elif world > 1:
+            else:
                 dist.all_gather_into_tensor(gathered, pred)
                 pinned_pred.copy_(gathered, non_blocking=True)
-            else:
-                pinned_pred[:batch].copy_(pred, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return pinned_pred
 
     # ---- kernel-resident timing ----
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -295,60 +312,82 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         pred = step_resident()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ens.last_launches * args.steps
+    launches = ens.last_launches * steps
     clocks = sampler.stop() if sampler else None
+    pred_resident = pred.cpu().numpy().copy()
+    probs_gpu = (ens.gather.full if by_units else ens.probs)[:, :batch].cpu().numpy().astype(np.float64) \
+        if not by_members else None
 
     # ---- end-to-end timing (host buffers, H2D + D2H inside) ----
-    run_e2e(max(1, args.warmup // 2))
+    run_e2e(max(1, warmup // 2))
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
-    run_e2e(args.steps)
+    pred_e2e = run_e2e(steps)
     e3.record(stream)
     barrier()
     ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+    pred_e2e = pred_e2e.numpy().copy()
+
+    # ---- self-check of what was timed: resident == end-to-end == oracle vote on the GPU's own probabilities ----
+    ncheck = len(pred_resident)
+    if not np.array_equal(pred_resident, pred_e2e[:ncheck]):
+        raise SystemExit("selfcheck failed (%s): resident and end-to-end predictions differ" % name)
+    if probs_gpu is not None:
+        mine_pred = pred_resident[rank * batch:(rank + 1) * batch] if (world > 1 and not strong) else pred_resident
+        exp = OV.ensemble_predictions(probs_gpu, np.ones(probs_gpu.shape[0])).astype(np.int32)
+        if not np.array_equal(mine_pred, exp):
+            raise SystemExit("selfcheck failed (%s): GPU vote differs from the oracle vote on the same probabilities" % name)
+        if not (np.isfinite(probs_gpu).all() and np.abs(probs_gpu.sum(-1) - 1.0).max() < 1e-4):
+            raise SystemExit("selfcheck failed (%s): member probabilities are not normalised" % name)
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
-    total_clips = batch * (1 if by_members else world) * args.steps
-    value = total_clips / (ms / 1e3)
-    e2e_value = total_clips / (ms_e2e / 1e3)
-
+    total_clips = batch * (1 if strong else world) * steps
+    res = None
     if rank == 0:
         peaks = load_peaks()
-        prof = ens.profile_ops(dev_in, iters=2)
+        prof = ens.profile_ops(dev_in, iters=2) if not by_units else []
         tc = [p for p in prof if p["engine"] == "tcgen05"]
         tc_flops = sum(p["flops"] for p in tc)
         tc_ms = sum(p["ms"] for p in tc)
         step_ms_prof = sum(p["ms"] for p in prof)
         achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
+        model_flops = sum(m * g.total_flops() for g, (_, _, m, _) in zip(all_graphs, groups)) * batch
         roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (peaks["source"], peaks["bf16_burst"]),
                     "kernel_share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
                     "launches_per_step": len(tc),
-                    "whole_step_model_tflops": sum(m * g.total_flops() for g, (_, _, m, _) in zip(all_graphs, groups)) * batch
-                                               / (ms / args.steps / 1e3) / 1e12 / (world if by_members else 1)}
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
-            tr = json.load(open(tpath)).get(args.workload)
-            if tr and [tr.get("micro_batch")] == ens.micro_batch and tr.get("launches_captured") == len(tc):
-                roofline["traffic"] = tr["dram_bytes_per_launch_avg"]
-                roofline["traffic_unit"] = "B per conv_tc launch (ncu dram read+write, avg over the member's launches)"
-                roofline["algorithmic_flops_per_launch_avg"] = tc_flops / (len(tc) * ens.M * (batch // ens.micro_batch[0]))
-        if args.profile_out:
+                    "whole_step_model_tflops": model_flops / (ms / steps / 1e3) / 1e12 / (world if strong else 1)}
+        if by_units:
+            roofline.update(achieved=roofline["whole_step_model_tflops"], frac=roofline["whole_step_model_tflops"] / peak,
+                            note="unit-sharded step: whole-step model FLOPs / step time / GPU (no per-op profile)")
+        tr = None
+        for tname in ("r2_traffic.json", "r1_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if tr is None and os.path.exists(tpath):
+                tr = json.load(open(tpath)).get(name)
+                if tr and not ([tr.get("micro_batch")] == ens.micro_batch and tr.get("launches_captured") == len(tc)):
+                    tr = None
+                if tr:
+                    roofline["traffic"] = tr["dram_bytes_per_launch_avg"]
+                    roofline["traffic_unit"] = "B per conv_tc launch (ncu dram read+write, avg over the member's launches)"
+                    roofline["traffic_source"] = "static: one ncu --set full capture of this configuration, profiles/" + tname
+                    roofline["algorithmic_flops_per_launch_avg"] = tc_flops / (len(tc) * ens.M * (batch // ens.micro_batch[0]))
+        if headline and args.profile_out:
             with open(args.profile_out, "w") as f:
-                json.dump({"workload": args.workload, "batch": batch, "members": members, "micro_batch": ens.micro_batch,
+                json.dump({"workload": name, "batch": batch, "members": members, "micro_batch": ens.micro_batch,
                            "ops": prof}, f, indent=1)
         # HBM-bound kernels of the path (pre-processing, pooling): algorithmic bytes / CUDA-event time
         hbm = {}
@@ -365,24 +404,68 @@ def run_ours(args):
         roofline["top_ops"] = [{"op": p["name"], "engine": p["engine"], "ms": round(p["ms"], 3),
                                 "tflops": round(p["flops"] / (p["ms"] / 1e3) / 1e12, 1) if p["ms"] > 0 else 0}
                                for p in top]
+        h2d_gbs = in_bytes / (ms_e2e / steps / 1e3) / 1e9
+        res = {
+            "metric": "ensemble clips/sec", "value": total_clips / (ms / 1e3), "unit": "clips/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(name, WORKLOADS[name][0] if not headline else groups, batch, world,
+                                      shard if world > 1 else "clips"),
+            "e2e": {"value": total_clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": batch * 4, "ms_per_step": ms_e2e / steps,
+                    "h2d_gbs_sustained": round(h2d_gbs, 2), "pipeline_depth": 3},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "selfcheck": "ok",
+        }
+    del ens, dev_in, host
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+# every BASELINE.json configuration is timed in the default run, after the headline (configs[1])
+EXTRA_WORKLOADS = ["c3d_single_b8", "i3d64_ens", "twostream64_ens", "global_hetero", "i3d20_ens", "twostream20_ens",
+                   "r3d34_ens"]
+STRONG_WORKLOADS = {"global_hetero"}       # N > 1: ONE 256-clip batch split into (member, clip-chunk) units
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cse_b200 import runtime as rt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rt.load_library()
+    line = measure(args.workload, args, args.steps, args.warmup, True)
+    extra = []
+    if args.workload == "c3d_ens" and not args.no_workloads and args.shard == "clips" and not (args.batch or args.members or args.micro_batch):
+        for name in EXTRA_WORKLOADS:
+            r = measure(name, args, max(3, min(args.steps, 8)), 3, False)
+            if r is not None:
+                extra.append({k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "selfcheck",
+                                                "gpu_launches")}
+                             | {"workload": name, "config": r["config"],
+                                "roofline": {k: r["roofline"].get(k) for k in ("achieved", "peak", "unit", "frac", "kernel_share_of_step",
+                                                                               "whole_step_model_tflops", "hbm_kernels", "top_ops", "note")}})
+    if rank == 0:
+        groups, _ = WORKLOADS[args.workload]
         cpu = None
         if not args.no_cpu_baseline:
-            sample = cpu_sample_size(groups, 6000.0)
+            sample = cpu_sample_size(groups)
+            members = sum(g[2] for g in groups)
             v, sec, threads = cpu_reference_clips_per_s(groups, sample, 2, 1)
             cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
                    "sample": "%d clips x %d members per pass, 1 warm-up + 2 timed passes, torch CPU fp32 oracle "
                              "restatement (Keras 2.2.4/TF 1.15 not installable offline)" % (sample, members)}
-        line = {
-            "metric": "ensemble clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if by_members else "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": dict(workload_config(args.workload, groups, batch, world, by_members),
-                           l2_policy="input batch (%d MB uint8) and activations exceed the 126 MB L2" % (in_bytes >> 20)),
-            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": in_bytes,
-                    "d2h_bytes_per_step": batch * 4},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        }
+        line["cpu_baseline"] = cpu
+        if extra:
+            line["workloads"] = extra
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -417,8 +500,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--members", type=int, default=0)
     ap.add_argument("--micro-batch", type=int, default=0)
-    ap.add_argument("--shard", default="clips", choices=["clips", "members"],
-                    help="N > 1: shard the clips (default, weak scaling) or the ensemble members (strong scaling)")
+    ap.add_argument("--shard", default="clips", choices=["clips", "members", "units"],
+                    help="N > 1: shard the clips (default, weak scaling), the ensemble members, or (member, clip-chunk) "
+                         "units of ONE batch (strong scaling)")
+    ap.add_argument("--no-workloads", action="store_true", help="time the headline workload only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="")
     args = ap.parse_args()
