@@ -833,112 +833,181 @@ preprocess_kernel(const uint8_t* __restrict__ src, TO* __restrict__ out, long lo
   }
 }
 
-// Packed-stem variant: output pixel w carries its 3 horizontal neighbours (w-1, w, w+1; zero
-// outside the row) x C channels, tightly packed (index j*C + c) and zero-padded to 16 channels
-// -> [n,T,H,W,16] bf16 (32 B per pixel).  The 3 kw taps of a 3x3x3 stem conv then are one
-// contiguous, aligned K=16 chunk per pixel.
-// NB = 3: per output pixel w, neighbours w-1..w+1.  NB = 4 ("pair" mode, pair-packed stem): the
-// output element is the pixel pair p = (2p, 2p+1) carrying pixels 2p-1..2p+2; a.Wo = number of pairs.
-template <int NB, int C>
-__global__ void __launch_bounds__(256)
-preprocess_unroll_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, long long total,
-                         PreArgs a) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  long long t = idx;
-  const int w = (int)(t % a.Wo); t /= a.Wo;
-  const int h = (int)(t % a.Ho); t /= a.Ho;
-  const int d = (int)(t % a.To); const long long nn = t / a.To;
-  __align__(16) __nv_bfloat16 v[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) v[c] = __float2bfloat16_rn(0.f);
-  const long long row = ((nn * a.T + (d + a.t0)) * a.H + (h + a.h0)) * a.W + a.w0;
-  const int wlim = (NB == 4) ? (a.W - a.w0) : a.Wo;         // pixels available in the (cropped) row
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    const int ws = (NB == 4 ? 2 * w : w) - 1 + j;
-    if (ws >= 0 && ws < wlim) {
-      const uint8_t* s = src + (row + ws) * C;        // C is a template constant: v[] stays in registers
-#pragma unroll
-      for (int c = 0; c < C; ++c) v[j * C + c] = __float2bfloat16_rn(((float)__ldg(s + c) - a.mean[c]) * a.scale[c]);
-    }
-  }
-  uint4* o = reinterpret_cast<uint4*>(out + idx * 16);
-  o[0] = reinterpret_cast<const uint4*>(v)[0];
-  o[1] = reinterpret_cast<const uint4*>(v)[1];
-}
+// ---------------------------------------------------------------------------------------------------
+// Stem layouts (packed / pair-packed C3D stem, 2-D and 3-D space-to-depth for the stride-2 7x7x7 stems).
+// One CTA converts PRE_RH output rows of one output plane: the source rows it needs are staged in shared
+// memory with coalesced 16-byte loads (uint8 rows: W*C bytes, read exactly once), then every thread
+// builds 16-byte chunks (8 bf16 channels) of output positions from the staged bytes and stores them
+// with fully coalesced 128-bit stores.
+//
+//   MODE 3 / 4  packed stem: output pixel w carries its horizontal neighbours w-1, w, w+1 (MODE 3) or the
+//               pixel pair p = (2p, 2p+1) carries pixels 2p-1 .. 2p+2 (MODE 4, a.Wo = pairs); channel
+//               index j*C + c, zero-padded to 16; pixels outside the row are zeros.  The kw taps of a 3x3x3
+//               stem conv (train.py:1230) then are one contiguous K chunk per position.
+//   MODE 20     2x2 space-to-depth over (H, W) (7x7x7 / stride 2 stems, train.py:1026, 1481): output cell
+//               (h2, w2) carries the input pixels (2*h2+ph, 2*w2+pw) x C channels at (ph*2+pw)*C + c.
+//   MODE 21     2x2x2 space-to-depth over (T, H, W): cell (d2, h2, w2) carries (2*d2+pd, 2*h2+ph, 2*w2+pw)
+//               at ((pd*2+ph)*2+pw)*C + c: 8*C channels without padding (C = 3: 24 channels = 48 bytes), so
+//               the stride-2 stem becomes a stride-1 4x4x4-cell conv with K = 512*C instead of 7*4*4*16.
+//   Pixels outside the frame, the wpad / right pad positions of a row and channels beyond the packed ones
+//   are exact zeros (they meet zero weights or stand for the conv's zero padding).
+// ---------------------------------------------------------------------------------------------------
+constexpr int PRE_THREADS = 256;
 
-// Stride-2 stem variant (7x7x7 / stride 2 stems of I3D and R3D, train.py:1026, 1481): 2x2
-// space-to-depth over (H, W).  Output cell (h2, w2) carries the 2x2 input pixels (2*h2+ph, 2*w2+pw)
-// x C channels, packed (ph*2+pw)*C + c and zero-padded to out_ld (8 or 16) channels; pixels outside
-// the frame and the wpad / right pad columns of the row are zeros.  A stride-2 window of 7 (+1
-// zero-weighted) input columns then is 4 neighbouring cells = one contiguous K chunk per pixel.
-template <int CL, int C>
-__global__ void __launch_bounds__(256)
-preprocess_s2d_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, long long total,
-                      PreArgs a) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  long long t = idx;
-  const int wp = (int)(t % a.wpitch); t /= a.wpitch;
-  const int h2 = (int)(t % a.Ho); t /= a.Ho;
-  const int d = (int)(t % a.To); const long long nn = t / a.To;
-  const int w2 = wp - a.wpad;
-  __align__(16) __nv_bfloat16 v[CL];
-#pragma unroll
-  for (int c = 0; c < CL; ++c) v[c] = __float2bfloat16_rn(0.f);
-  if (w2 >= 0 && w2 < a.Wo) {
-#pragma unroll
-    for (int ph = 0; ph < 2; ++ph) {
-      const int hs = 2 * h2 + ph;
-      if (hs >= a.H) continue;
-      const uint8_t* row = src + (((nn * a.T + d) * a.H + hs) * a.W) * C;
-#pragma unroll
-      for (int pw = 0; pw < 2; ++pw) {
-        const int ws = 2 * w2 + pw;
-        if (ws >= a.W) continue;
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-          if ((ph * 2 + pw) * C + c < CL)
-            v[(ph * 2 + pw) * C + c] = __float2bfloat16_rn(((float)__ldg(row + ws * C + c) - a.mean[c]) * a.scale[c]);
+struct PreRowArgs {
+  int T, H, W;             // source clip
+  int To, Ho, Wo;          // output grid: planes, rows, real positions per row
+  int wpitch, wpad;        // output row: wpitch positions, the first wpad and everything beyond wpad + Wo are zeros
+  int t0, h0, w0;          // crop (packed stem modes)
+  int rh;                  // output rows per CTA
+  int hgroups;             // ceil(Ho / rh)
+  int row_bytes, row_pitch;// W*C and its 16-byte rounded smem pitch
+  int aligned;             // source rows start 16-byte aligned
+  float mean[4], scale[4];
+};
+
+template <int MODE, int C, int CL>
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, PreRowArgs a) {
+  constexpr int NPL = (MODE == 21) ? 2 : 1;               // source planes per output plane
+  constexpr int NR = (MODE >= 20) ? 2 : 1;                // source rows per output row
+  constexpr int Q = CL / 8;                               // 16-byte chunks per output position
+  constexpr int KREAL = (MODE == 21) ? 8 * C : (MODE == 20 ? 4 * C : MODE * C);
+  extern __shared__ __align__(16) uint8_t rows[];         // [rh][NPL][NR][row_pitch]
+  int b = blockIdx.x;
+  const int hg = b % a.hgroups; b /= a.hgroups;
+  const int d = b % a.To;
+  const long long n = b / a.To;
+  const int h_first = hg * a.rh;
+  const int nrows = min(a.rh, a.Ho - h_first);
+  // ---- stage the source rows ----
+  const int staged = nrows * NPL * NR;
+  if (a.aligned) {
+    const int v_per_row = a.row_bytes >> 4;
+    for (int i = threadIdx.x; i < staged * v_per_row; i += PRE_THREADS) {
+      const int r = i / v_per_row, v = i - r * v_per_row;
+      const int rr = r % NR, pl = (r / NR) % NPL, rh = r / (NR * NPL);
+      const int ts = (MODE == 21) ? 2 * d + pl : d + a.t0;
+      const int hs = (MODE >= 20) ? 2 * (h_first + rh) + rr : h_first + rh + a.h0;
+      if (ts < a.T && hs < a.H) {
+        const uint4* g = reinterpret_cast<const uint4*>(src + (((n * a.T + ts) * a.H + hs) * (long long)a.W) * C);
+        reinterpret_cast<uint4*>(rows + (size_t)r * a.row_pitch)[v] = __ldg(g + v);
       }
     }
+  } else {
+    for (int i = threadIdx.x; i < staged * a.row_bytes; i += PRE_THREADS) {
+      const int r = i / a.row_bytes, v = i - r * a.row_bytes;
+      const int rr = r % NR, pl = (r / NR) % NPL, rh = r / (NR * NPL);
+      const int ts = (MODE == 21) ? 2 * d + pl : d + a.t0;
+      const int hs = (MODE >= 20) ? 2 * (h_first + rh) + rr : h_first + rh + a.h0;
+      if (ts < a.T && hs < a.H) rows[(size_t)r * a.row_pitch + v] = __ldg(src + (((n * a.T + ts) * a.H + hs) * (long long)a.W) * C + v);
+    }
   }
-  uint4* o = reinterpret_cast<uint4*>(out + idx * CL);
+  __syncthreads();
+  // ---- build and store the output chunks ----
+  const int per_row = a.wpitch * Q;
+  __nv_bfloat16* obase = out + (((n * a.To + d) * a.Ho + h_first) * (long long)a.wpitch) * CL;
+  for (int i = threadIdx.x; i < nrows * per_row; i += PRE_THREADS) {
+    const int rh = i / per_row, rem = i - rh * per_row;
+    const int x = rem / Q, q = rem - x * Q;
+    const int xo = x - a.wpad;                                  // real output position
+    const bool xreal = xo >= 0 && xo < a.Wo;
+    const int h = h_first + rh;
+    uint32_t pk[4];
 #pragma unroll
-  for (int q = 0; q < CL / 8; ++q) o[q] = reinterpret_cast<const uint4*>(v)[q];
+    for (int e2 = 0; e2 < 4; ++e2) {
+      float f[2];
+#pragma unroll
+      for (int e1 = 0; e1 < 2; ++e1) {
+        const int k = q * 8 + e2 * 2 + e1;
+        float val = 0.f;
+        if (xreal && k < KREAL) {
+          const int sub = k / C, c = k - sub * C;
+          int srow, sx;
+          bool ok;
+          if (MODE >= 20) {
+            const int pd = (MODE == 21) ? (sub >> 2) : 0, ph = (sub >> 1) & 1, pw = sub & 1;
+            srow = (rh * NPL + pd) * NR + ph;
+            sx = 2 * xo + pw;
+            ok = (2 * h + ph < a.H) && sx < a.W && ((MODE == 21) ? (2 * d + pd < a.T) : true);
+          } else {
+            srow = rh;
+            const int ws = (MODE == 4 ? 2 * xo : xo) - 1 + sub;
+            const int wlim = (MODE == 4) ? (a.W - a.w0) : a.Wo;   // pixels available in the (cropped) row
+            ok = ws >= 0 && ws < wlim;
+            sx = ws + a.w0;
+          }
+          if (ok) val = ((float)rows[(size_t)srow * a.row_pitch + sx * C + c] - a.mean[c]) * a.scale[c];
+        }
+        f[e1] = val;
+      }
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(f[0], f[1]);
+      pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(obase + (size_t)i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+template <int MODE, int C, int CL>
+static int preprocess_rows_launch(const uint8_t* src, void* out, int n, PreRowArgs a, cudaStream_t st) {
+  a.row_bytes = a.W * C;
+  a.row_pitch = (a.row_bytes + 15) & ~15;
+  a.aligned = (a.row_bytes % 16 == 0) && (((uintptr_t)src) % 16 == 0);
+  constexpr int NPL = (MODE == 21) ? 2 : 1, NR = (MODE >= 20) ? 2 : 1;
+  // rows per CTA: ~8 chunk stores per thread, <= 40 KB of staged rows
+  const int per_row = a.wpitch * (CL / 8);
+  int rh = max(1, (8 * PRE_THREADS) / max(per_row, 1));
+  rh = min(rh, max(1, (40 * 1024) / (NPL * NR * a.row_pitch)));
+  rh = min(rh, a.Ho);
+  a.rh = rh;
+  a.hgroups = ceil_div(a.Ho, rh);
+  const size_t smem = (size_t)rh * NPL * NR * a.row_pitch;
+  CSE_REQUIRE(smem <= 48 * 1024, "preprocess: source row of %d bytes is too long to stage", a.row_bytes);
+  const long long blocks = (long long)n * a.To * a.hgroups;
+  CSE_REQUIRE(blocks < (1ll << 31), "preprocess: too many blocks");
+  if (blocks == 0) return CSE_OK;
+  preprocess_rows_kernel<MODE, C, CL><<<(unsigned)blocks, PRE_THREADS, smem, st>>>(src, (__nv_bfloat16*)out, a);
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
 }
 
 int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int t0, int h0, int w0,
                       int To, int Ho, int Wo, const float* mean, const float* scale, void* out,
                       int out_dt, int out_ld, cudaStream_t st, int wpitch, int wpad, int unroll_w, int s2d) {
   if (s2d) {
-    // To,Ho,Wo = T, ceil(H/2), ceil(W/2): the space-to-depth grid
-    CSE_REQUIRE(out_dt == CSE_BF16 && (out_ld == 8 || out_ld == 16) && C >= 1 && C <= 4 && 4 * C <= out_ld && unroll_w == 0,
-                "preprocess: s2d needs bf16, out_ld 8/16 >= 4*C (C=%d, out_ld=%d)", C, out_ld);
-    CSE_REQUIRE(t0 == 0 && h0 == 0 && w0 == 0 && To == T && Ho == (H + 1) / 2 && Wo == (W + 1) / 2,
+    // s2d = 1: To,Ho,Wo = T, ceil(H/2), ceil(W/2); s2d = 2: ceil(T/2), ceil(H/2), ceil(W/2) - the space-to-depth grid
+    const int cells = s2d == 2 ? 8 : 4;
+    CSE_REQUIRE((s2d == 1 || s2d == 2) && out_dt == CSE_BF16 && C >= 1 && C <= 4 && out_ld % 8 == 0 && cells * C <= out_ld &&
+                    out_ld <= 32 && unroll_w == 0,
+                "preprocess: s2d needs bf16 and out_ld in {8,16,24,32} >= %d*C (C=%d, out_ld=%d)", cells, C, out_ld);
+    CSE_REQUIRE(t0 == 0 && h0 == 0 && w0 == 0 && To == (s2d == 2 ? (T + 1) / 2 : T) && Ho == (H + 1) / 2 && Wo == (W + 1) / 2,
                 "preprocess: s2d output grid (%d,%d,%d) does not match clip (%d,%d,%d)", To, Ho, Wo, T, H, W);
     if (wpitch <= 0) { wpitch = Wo; wpad = 0; }
     CSE_REQUIRE(wpad >= 0 && wpitch >= Wo + wpad, "preprocess: row pitch %d < Wo %d + pad %d", wpitch, Wo, wpad);
-    PreArgs a;
-    a.T = T; a.H = H; a.W = W; a.C = C; a.t0 = 0; a.h0 = 0; a.w0 = 0;
-    a.To = To; a.Ho = Ho; a.Wo = Wo; a.out_ld = out_ld; a.wpitch = wpitch; a.wpad = wpad;
+    PreRowArgs a;
+    a.T = T; a.H = H; a.W = W; a.t0 = 0; a.h0 = 0; a.w0 = 0;
+    a.To = To; a.Ho = Ho; a.Wo = Wo; a.wpitch = wpitch; a.wpad = wpad;
     for (int c = 0; c < 4; ++c) {
       a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
       a.scale[c] = (scale && c < C) ? scale[c] : 1.f;
     }
-    const long long total = (long long)n * To * Ho * wpitch;
-    if (total == 0) return CSE_OK;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
-#define S2D_CASE(CL_, C_) preprocess_s2d_kernel<CL_, C_><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a)
-    if (out_ld == 16) {
-      switch (C) { case 1: S2D_CASE(16, 1); break; case 2: S2D_CASE(16, 2); break; case 3: S2D_CASE(16, 3); break; default: S2D_CASE(16, 4); }
+#define S2D_CASE(M_, C_, CL_) return preprocess_rows_launch<M_, C_, CL_>(src, out, n, a, st)
+    if (s2d == 2) {
+      if (C == 1 && out_ld == 8) S2D_CASE(21, 1, 8);
+      if (C == 2 && out_ld == 16) S2D_CASE(21, 2, 16);
+      if (C == 3 && out_ld == 24) S2D_CASE(21, 3, 24);
+      if (C == 4 && out_ld == 32) S2D_CASE(21, 4, 32);
     } else {
-      switch (C) { case 1: S2D_CASE(8, 1); break; default: S2D_CASE(8, 2); }
+      if (C == 1 && out_ld == 8) S2D_CASE(20, 1, 8);
+      if (C == 2 && out_ld == 8) S2D_CASE(20, 2, 8);
+      if (C == 1 && out_ld == 16) S2D_CASE(20, 1, 16);
+      if (C == 2 && out_ld == 16) S2D_CASE(20, 2, 16);
+      if (C == 3 && out_ld == 16) S2D_CASE(20, 3, 16);
+      if (C == 4 && out_ld == 16) S2D_CASE(20, 4, 16);
     }
 #undef S2D_CASE
-    CSE_CUDA(cudaGetLastError());
-    return CSE_OK;
+    set_error("preprocess: s2d=%d with C=%d, out_ld=%d is not instantiated", s2d, C, out_ld);
+    return CSE_ERR_INVALID;
   }
   if (unroll_w > 0) {
     CSE_REQUIRE((unroll_w == 3 || unroll_w == 4) && out_dt == CSE_BF16 && out_ld == 16 && C >= 1 && C <= 4 && C * unroll_w <= 16 &&
@@ -947,25 +1016,20 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
     CSE_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + To <= T && h0 + Ho <= H &&
                     w0 + (unroll_w == 4 ? 2 * Wo - 1 : Wo) <= W,
                 "preprocess: crop outside clip");
-    PreArgs a;
-    a.T = T; a.H = H; a.W = W; a.C = C; a.t0 = t0; a.h0 = h0; a.w0 = w0;
-    a.To = To; a.Ho = Ho; a.Wo = Wo; a.out_ld = out_ld; a.wpitch = Wo; a.wpad = 0;
+    PreRowArgs a;
+    a.T = T; a.H = H; a.W = W; a.t0 = t0; a.h0 = h0; a.w0 = w0;
+    a.To = To; a.Ho = Ho; a.Wo = Wo; a.wpitch = Wo; a.wpad = 0;
     for (int c = 0; c < 4; ++c) {
       a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
       a.scale[c] = (scale && c < C) ? scale[c] : 1.f;
     }
-    const long long total = (long long)n * To * Ho * Wo;
-    if (total == 0) return CSE_OK;
-#define UNR_CASE(NB_, C_) \
-  preprocess_unroll_kernel<NB_, C_><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, (__nv_bfloat16*)out, total, a)
+#define UNR_CASE(NB_, C_) return preprocess_rows_launch<NB_, C_, 16>(src, out, n, a, st)
     if (unroll_w == 4) {
-      switch (C) { case 1: UNR_CASE(4, 1); break; case 2: UNR_CASE(4, 2); break; case 3: UNR_CASE(4, 3); break; default: UNR_CASE(4, 4); }
+      switch (C) { case 1: UNR_CASE(4, 1); case 2: UNR_CASE(4, 2); case 3: UNR_CASE(4, 3); default: UNR_CASE(4, 4); }
     } else {
-      switch (C) { case 1: UNR_CASE(3, 1); break; case 2: UNR_CASE(3, 2); break; case 3: UNR_CASE(3, 3); break; default: UNR_CASE(3, 4); }
+      switch (C) { case 1: UNR_CASE(3, 1); case 2: UNR_CASE(3, 2); case 3: UNR_CASE(3, 3); default: UNR_CASE(3, 4); }
     }
 #undef UNR_CASE
-    CSE_CUDA(cudaGetLastError());
-    return CSE_OK;
   }
   CSE_REQUIRE(C >= 1 && C <= 4, "preprocess: C=%d not in 1..4", C);
   CSE_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + To <= T && h0 + Ho <= H && w0 + Wo <= W,

@@ -276,9 +276,10 @@ class HeteroEnsemble:
                 p = {"shapes": shapes, "depth": depth, "copy": torch.cuda.Stream(device=self.device),
                      "bufs": [[[torch.empty(sh, dtype=torch.uint8, device=self.device) for sh in hs] for hs in shapes]
                               for _ in range(depth)],
-                     "ready": [torch.cuda.Event() for _ in range(depth)],
+                     "ready": [torch.cuda.Event(enable_timing=True) for _ in range(depth)],
+                     "start": [torch.cuda.Event(enable_timing=True) for _ in range(depth)],
                      "free": [torch.cuda.Event() for _ in range(depth)],
-                     "used": [False] * depth}
+                     "used": [False] * depth, "bytes": sum(int(np.prod(sh)) for hs in shapes for sh in hs)}
             self._pipe = p
         return p
 
@@ -302,6 +303,7 @@ class HeteroEnsemble:
                 with torch.cuda.stream(copy):
                     if p["used"][k]:
                         copy.wait_event(p["free"][k])     # the compute that read this buffer set has finished
+                    p["start"][k].record(copy)
                     for ds, hs in zip(p["bufs"][k], batch):
                         for d, h in zip(ds, hs):
                             d.copy_(h, non_blocking=True)
@@ -322,6 +324,15 @@ class HeteroEnsemble:
                 p["free"][k].record(comp)
                 p["used"][k] = True
                 yield pred
+
+    def h2d_copy_gbs(self):
+        """Achieved host -> device bandwidth of the most recent uploads of stream_host (CUDA events on the copy
+        stream around each batch's copies; call after a synchronize)."""
+        p = getattr(self, "_pipe", None)
+        if p is None or not any(p["used"]):
+            return None
+        ms = [p["start"][k].elapsed_time(p["ready"][k]) for k in range(p["depth"]) if p["used"][k]]
+        return p["bytes"] / (min(ms) / 1e3) / 1e9 if ms and min(ms) > 0 else None
 
     def profile_ops(self, group_inputs, iters: int = 2):
         out = []

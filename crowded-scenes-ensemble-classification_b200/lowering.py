@@ -353,7 +353,8 @@ class Lowerer:
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
                  stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True,
                  balance_n: bool = True, pair_pool: bool = True, persist_input: bool = False,
-                 fuse_siblings: bool = True):
+                 fuse_siblings: bool = True, s2d_depth: bool = True):
+        self.s2d_depth = s2d_depth
         self.keep_all = keep_all
         self.fuse_siblings = fuse_siblings
         self.persist_input = persist_input
@@ -541,10 +542,19 @@ class Lowerer:
             pb_w = first.attrs["pads_before"][2]
             wpad = (pb_w + 1) // 2
             wpitch = w2 + 3
-            b = self.new_buf(node.name, (t, h2, wpitch), cell, self.act)
-            out = TRef(b, 0, cell, cell, (t, h2, w2), self.act, wpitch, wpad, 0, 1, c)
             mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
             scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
+            # 2x2x2 cells (depth too) carry 8*C channels without padding: the stem becomes a stride-1 4x4x4-cell conv
+            # with K = 16 x (4 cells x 8C) instead of 28 x (4 cells x round_up(4C, 8)).  C = 3: 1536 vs 1792 (real
+            # 1029); C = 1: 512 vs 896; worse for C = 2 / 4 (7 -> 8 taps in depth without a channel-padding gain).
+            if self.s2d_depth and self.stem_halo and 16 * 4 * 8 * c < 28 * 4 * cell:
+                t2 = (t + 1) // 2
+                cell3 = 8 * c
+                b = self.new_buf(node.name, (t2, h2, wpitch), cell3, self.act)
+                out = TRef(b, 0, cell3, cell3, (t2, h2, w2), self.act, wpitch, wpad, 0, 2, c)
+            else:
+                b = self.new_buf(node.name, (t, h2, wpitch), cell, self.act)
+                out = TRef(b, 0, cell, cell, (t, h2, w2), self.act, wpitch, wpad, 0, 1, c)
             self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
                             src_dims=(t, h, w, c), pre_mean=mean, pre_scale=scale, layers=(node.name,)))
             self.val[node.name] = out
@@ -879,22 +889,32 @@ class Lowerer:
         assert (kd, kh, kw) == (7, 7, 7) and ci == x.src_c
         cell = x.ld
         pb = node.attrs["pads_before"]
-        off_h, off_w = pb[1] - 2 * ((pb[1] + 1) // 2), pb[2] - 2 * ((pb[2] + 1) // 2)     # 0 (pb even) or -1 (odd)
-        k2 = np.zeros((7, 4, 1, 4 * cell, co), np.float32)
-        for fh in range(4):
-            for ph in range(2):
-                th = 2 * fh + ph + off_h
-                if not 0 <= th < 7:
+        off_d, off_h, off_w = (p - 2 * ((p + 1) // 2) for p in pb)                 # 0 (pad even) or -1 (odd)
+        depth = x.s2d == 2          # 2x2x2 cells: depth is regrouped like H and W (4 cell taps, stride 1)
+        k2 = np.zeros((4 if depth else 7, 4, 1, 4 * cell, co), np.float32)
+        for fd in range(k2.shape[0]):
+            for pd in range(2 if depth else 1):
+                td = 2 * fd + pd + off_d if depth else fd
+                if not 0 <= td < 7:
                     continue
-                for fw in range(4):
-                    for pw in range(2):
-                        tw = 2 * fw + pw + off_w
-                        if not 0 <= tw < 7:
+                for fh in range(4):
+                    for ph in range(2):
+                        th = 2 * fh + ph + off_h
+                        if not 0 <= th < 7:
                             continue
-                        c0 = fw * cell + (ph * 2 + pw) * ci
-                        k2[:, fh, 0, c0:c0 + ci, :] = kernel[:, th, tw, :, :]
+                        for fw in range(4):
+                            for pw in range(2):
+                                tw = 2 * fw + pw + off_w
+                                if not 0 <= tw < 7:
+                                    continue
+                                c0 = fw * cell + ((pd * 2 + ph) * 2 + pw) * ci
+                                k2[fd, fh, 0, c0:c0 + ci, :] = kernel[td, th, tw, :, :]
         view = TRef(x.buf, 0, 4 * cell, cell, x.dims, x.dtype, x.wpitch, x.wpad)
-        op = self._conv_like(node.name, view, k2, bias, (7, 4, 1), (2, 1, 1), (pb[0], (pb[1] + 1) // 2, 0), out_dims,
+        if depth:
+            k_, s_, pad_ = (4, 4, 1), (1, 1, 1), ((pb[0] + 1) // 2, (pb[1] + 1) // 2, 0)
+        else:
+            k_, s_, pad_ = (7, 4, 1), (2, 1, 1), (pb[0], (pb[1] + 1) // 2, 0)
+        op = self._conv_like(node.name, view, k2, bias, k_, s_, pad_, out_dims,
                              chain_bn, relu, final, layers, flops=flops, halo=2 if self.stem_halo else 0)
         if op.engine != rt.ENGINE_TCGEN05:
             raise RuntimeError("s2d stem must lower to the tcgen05 engine")

@@ -139,6 +139,12 @@ AGREE_CLIPS = 10240
 # clips sit on a decision boundary of these RANDOM-weight nets (fp32 top-2 margin below the bf16 logit tolerance
 # itself); for those the measured number is recorded and every flip must be explained by that tolerance.
 AGREE_REQUIRED = {"C3D": 0.999, "I3D": 0.999}
+# The logit tolerance here is the MAXIMUM over 10 240 clips.  R3D-34 at 16x32x32 (random weights, 34 layers, 1x1x1
+# feature maps in the last stages) has its bf16 quantisation floor at that level: the oracle's own bf16-storage
+# emulation (fp64 accumulation, no kernel involved) is 1.2e-2 off the fp32 logits on the worst of 512 of these clips
+# (measured on the CPU; cf. test_oracle.py::test_bf16_quantisation_floor_r3d50), the device path 1.3e-2 on the worst
+# of 10 240.  The two-clip full-geometry test above keeps 1e-2 for R3D-34.
+AGREE_LOGIT_TOL = {"R3D_34": 2e-2}
 
 
 @pytest.mark.parametrize("mt,shape", AGREE_CASES)
@@ -186,8 +192,9 @@ def test_bf16_top1_agreement(mt, shape):
         allrec[mt] = rec
         json.dump(allrec, open(path, "w"), indent=1)
     print(rec)
-    assert rec["max_rel_logit_err"] <= BF16_TOL.get(mt, 1e-2)
-    assert len(flipped) <= rec["clips_with_margin_below_2e-2"] and rec["max_rel_margin_of_flipped"] <= 2e-2, rec
+    tol = AGREE_LOGIT_TOL.get(mt, 1e-2)
+    assert rec["max_rel_logit_err"] <= tol
+    assert len(flipped) <= int((margin <= 2 * tol).sum()) and rec["max_rel_margin_of_flipped"] <= 2 * tol, rec
     assert agree >= AGREE_REQUIRED.get(mt, 0.0), "unfiltered top-1 agreement %.5f (%d of %d clips flipped)" % (
         agree, len(flipped), AGREE_CLIPS)
 

@@ -296,21 +296,25 @@ S2D_STEM = [((8, 16, 16), 3, 64, 2), ((9, 21, 19), 3, 64, 2), ((6, 20, 28), 2, 6
             ((7, 10, 34), 1, 16, 1)]
 
 
-@pytest.mark.parametrize("halo", [True, False])
+@pytest.mark.parametrize("halo,depth", [(True, True), (True, False), (False, False)])
 @pytest.mark.parametrize("dhw,c,cout,nb", S2D_STEM)
-def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb, halo):
+def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb, halo, depth):
     """7x7x7 / stride 2 'same' stem on the raw clip (I3D Conv3d_1a_7x7, R3D stem) on the tcgen05 engine:
     2x2 space-to-depth cells written by the pre-processing kernel, 4-cell window through an
     overlapping-stride TMA view, k=(7,4,1) stride (2,1,1) with a zero-extended regrouped kernel.
-    Even and odd extents (TF 'same' pads (2,3) resp. (3,3)) and C = 1, 2, 3."""
+    Even and odd extents (TF 'same' pads (2,3) resp. (3,3)) and C = 1, 2, 3.  depth: 2x2x2 cells (8*C channels without
+    padding, k=(4,4,1) stride 1) where that shrinks K (C = 1, 3)."""
     def build(g):
         x = g.input(dhw + (c,), name="in")
         x = g.conv3d(x, cout, (7, 7, 7), (2, 2, 2), "same", True, None, name="c")
         x = g.bn(x, scale=True, name="b")
         g.relu(x, name="r")
-    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c, stem_halo=halo)
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c, stem_halo=halo, s2d_depth=depth)
     op = [o for o in m.plan.ops if o.name == "c"][0]
-    assert op.engine == rt.ENGINE_TCGEN05 and op.k == (7, 4, 1) and op.s == (2, 1, 1)
+    if depth and c in (1, 3):
+        assert op.engine == rt.ENGINE_TCGEN05 and op.k == (4, 4, 1) and op.s == (1, 1, 1) and op.in0.C == 32 * c
+    else:
+        assert op.engine == rt.ENGINE_TCGEN05 and op.k == (7, 4, 1) and op.s == (2, 1, 1)
     assert op.halo == (2 if halo else 0)      # h-halo: one A box per input plane feeds the 4 kh taps
     xs = clips(11, nb, dhw + (c,))
     run(m, [xs])
@@ -324,7 +328,8 @@ def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb, halo):
     assert err <= 2.0 ** -7, "rel err %g (kc=%d bn=%d brick=%s)" % (err, op.kc, op.bn, op.brick)
 
 
-@pytest.mark.parametrize("dhw,c,cout,nb", S2D_STEM + [((16, 48, 48), 2, 64, 5), ((10, 30, 44), 1, 32, 3), ((12, 40, 40), 2, 128, 2)])
+@pytest.mark.parametrize("dhw,c,cout,nb", S2D_STEM + [((16, 48, 48), 2, 64, 5), ((10, 30, 44), 1, 32, 3), ((12, 40, 40), 2, 128, 2),
+                                            ((16, 56, 56), 3, 64, 4), ((11, 30, 30), 3, 64, 3)])
 def test_conv_tcgen05_s2d_stem_shared_weights(dhw, c, cout, nb):
     """Shared-B h-halo mode (groups of 4 tiles of a CTA use one weight block per (fd, chunk), 8 TMEM
     accumulators; taken by the 1- and 2-channel stems whose K chunk is 32), forced on small shapes: full / partial tile groups, several groups per CTA, ragged
