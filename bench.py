@@ -257,7 +257,7 @@ def measure(name, args, steps, warmup, headline):
         if ws:
             graphs.append(g)
             built.append((g, ws, mb))
-    ens = HeteroEnsemble(built, precision=args.precision, max_batch=batch, **lower_kw)
+    ens = HeteroEnsemble(built, precision=args.precision, max_batch=batch, use_graphs=not args.no_graphs, **lower_kw)
     del built
     if by_members:
         ens.gather = MemberGather(owned_all, members, dist, world)
@@ -280,7 +280,7 @@ def measure(name, args, steps, warmup, headline):
     gathered = torch.empty((world * batch,), dtype=torch.int32, device="cuda") if world > 1 and not strong else None
 
     def step_resident():
-        pred = ens.predict_device(dev_in)
+        pred = ens.predict_device(dev_in, graph=not args.no_graphs)
         if strong:
             return pred                  # every rank voted on the merged [M, batch, C] block
         if world > 1:
@@ -505,6 +505,7 @@ def main():
                     help="N > 1: shard the clips (default, weak scaling), the ensemble members, or (member, clip-chunk) "
                          "units of ONE batch (strong scaling)")
     ap.add_argument("--no-workloads", action="store_true", help="time the headline workload only")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="")
     args = ap.parse_args()

@@ -866,13 +866,19 @@ struct PreRowArgs {
   float mean[4], scale[4];
 };
 
-template <int MODE, int C, int CL>
+// uint8 -> float without the conversion unit: 0x4B000000 | b is the float 2^23 + b, exactly.
+__device__ __forceinline__ float u8_to_f32(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
+
+template <int MODE, int C, int CL, bool IDENT>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, PreRowArgs a) {
   constexpr int NPL = (MODE == 21) ? 2 : 1;               // source planes per output plane
   constexpr int NR = (MODE >= 20) ? 2 : 1;                // source rows per output row
   constexpr int Q = CL / 8;                               // 16-byte chunks per output position
   constexpr int KREAL = (MODE == 21) ? 8 * C : (MODE == 20 ? 4 * C : MODE * C);
+  // An output position is the concatenation of KREAL / L segments of L consecutive source bytes (one segment per
+  // staged source row), then zeros: packed stem = ONE run of NB*C bytes, s2d = 2C bytes from each of its 2 / 4 rows.
+  constexpr int L = (MODE >= 20) ? 2 * C : MODE * C;
   extern __shared__ __align__(16) uint8_t rows[];         // [rh][NPL][NR][row_pitch]
   int b = blockIdx.x;
   const int hg = b % a.hgroups; b /= a.hgroups;
@@ -880,7 +886,7 @@ preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restric
   const long long n = b / a.To;
   const int h_first = hg * a.rh;
   const int nrows = min(a.rh, a.Ho - h_first);
-  // ---- stage the source rows ----
+  // ---- stage the source rows (each source byte leaves HBM once, 16 bytes per load) ----
   const int staged = nrows * NPL * NR;
   if (a.aligned) {
     const int v_per_row = a.row_bytes >> 4;
@@ -904,47 +910,79 @@ preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restric
     }
   }
   __syncthreads();
-  // ---- build and store the output chunks ----
-  const int per_row = a.wpitch * Q;
+  // ---- one thread per output position: Q 16-byte stores ----
   __nv_bfloat16* obase = out + (((n * a.To + d) * a.Ho + h_first) * (long long)a.wpitch) * CL;
-  for (int i = threadIdx.x; i < nrows * per_row; i += PRE_THREADS) {
-    const int rh = i / per_row, rem = i - rh * per_row;
-    const int x = rem / Q, q = rem - x * Q;
+  const bool planes_ok = (MODE == 21) ? (2 * d + 1 < a.T) : true;
+  for (int i = threadIdx.x; i < nrows * a.wpitch; i += PRE_THREADS) {
+    const int rh = i / a.wpitch, x = i - rh * a.wpitch;
     const int xo = x - a.wpad;                                  // real output position
-    const bool xreal = xo >= 0 && xo < a.Wo;
     const int h = h_first + rh;
-    uint32_t pk[4];
-#pragma unroll
-    for (int e2 = 0; e2 < 4; ++e2) {
-      float f[2];
-#pragma unroll
-      for (int e1 = 0; e1 < 2; ++e1) {
-        const int k = q * 8 + e2 * 2 + e1;
-        float val = 0.f;
-        if (xreal && k < KREAL) {
-          const int sub = k / C, c = k - sub * C;
-          int srow, sx;
-          bool ok;
-          if (MODE >= 20) {
-            const int pd = (MODE == 21) ? (sub >> 2) : 0, ph = (sub >> 1) & 1, pw = sub & 1;
-            srow = (rh * NPL + pd) * NR + ph;
-            sx = 2 * xo + pw;
-            ok = (2 * h + ph < a.H) && sx < a.W && ((MODE == 21) ? (2 * d + pd < a.T) : true);
-          } else {
-            srow = rh;
-            const int ws = (MODE == 4 ? 2 * xo : xo) - 1 + sub;
-            const int wlim = (MODE == 4) ? (a.W - a.w0) : a.Wo;   // pixels available in the (cropped) row
-            ok = ws >= 0 && ws < wlim;
-            sx = ws + a.w0;
-          }
-          if (ok) val = ((float)rows[(size_t)srow * a.row_pitch + sx * C + c] - a.mean[c]) * a.scale[c];
-        }
-        f[e1] = val;
-      }
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(f[0], f[1]);
-      pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
+    uint32_t pk[CL / 2];
+    // first source pixel of the position and whether all of its pixels lie inside the frame
+    int p0;
+    bool interior;
+    if (MODE >= 20) {
+      p0 = 2 * xo;
+      interior = xo >= 0 && xo < a.Wo && p0 + 1 < a.W && 2 * h + 1 < a.H && planes_ok;
+    } else {
+      p0 = (MODE == 4 ? 2 * xo : xo) - 1;
+      const int wlim = (MODE == 4) ? (a.W - a.w0) : a.Wo;      // pixels available in the (cropped) row
+      interior = xo >= 0 && xo < a.Wo && p0 >= 0 && p0 + MODE <= wlim;
     }
-    *reinterpret_cast<uint4*>(obase + (size_t)i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    const uint8_t* seg0 = rows + (size_t)(rh * NPL * NR) * a.row_pitch + ((MODE >= 20) ? p0 : p0 + a.w0) * C;
+    if (interior) {
+#pragma unroll
+      for (int k2 = 0; k2 < CL / 2; ++k2) {
+        float f[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          constexpr int dummy = 0; (void)dummy;
+          const int k = 2 * k2 + e;
+          float val = 0.f;
+          if (k < KREAL) {
+            const int sg = k / L, j = k - sg * L, c = j % C;      // compile-time after unrolling
+            val = u8_to_f32(seg0[(size_t)sg * a.row_pitch + j]);
+            if (!IDENT) val = (val - a.mean[c]) * a.scale[c];
+          }
+          f[e] = val;
+        }
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[0], f[1]);
+        pk[k2] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+    } else {
+      // frame edges, pad positions of the row, missing rows / planes: per-element checks
+      const bool xreal = xo >= 0 && xo < a.Wo;
+#pragma unroll
+      for (int k2 = 0; k2 < CL / 2; ++k2) {
+        float f[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = 2 * k2 + e;
+          float val = 0.f;
+          if (k < KREAL && xreal) {
+            const int sg = k / L, j = k - sg * L, c = j % C, px = j / C;
+            bool ok;
+            if (MODE >= 20) {
+              const int pd = (MODE == 21) ? (sg >> 1) : 0, ph = sg & 1;
+              ok = (2 * h + ph < a.H) && (p0 + px < a.W) && ((MODE == 21) ? (2 * d + pd < a.T) : true);
+            } else {
+              const int wlim = (MODE == 4) ? (a.W - a.w0) : a.Wo;
+              ok = p0 + px >= 0 && p0 + px < wlim;
+            }
+            if (ok) {
+              val = u8_to_f32(seg0[(size_t)sg * a.row_pitch + j]);
+              if (!IDENT) val = (val - a.mean[c]) * a.scale[c];
+            }
+          }
+          f[e] = val;
+        }
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[0], f[1]);
+        pk[k2] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(obase + (size_t)i * CL);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) o[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
   }
 }
 
@@ -955,8 +993,8 @@ static int preprocess_rows_launch(const uint8_t* src, void* out, int n, PreRowAr
   a.aligned = (a.row_bytes % 16 == 0) && (((uintptr_t)src) % 16 == 0);
   constexpr int NPL = (MODE == 21) ? 2 : 1, NR = (MODE >= 20) ? 2 : 1;
   // rows per CTA: ~8 chunk stores per thread, <= 40 KB of staged rows
-  const int per_row = a.wpitch * (CL / 8);
-  int rh = max(1, (8 * PRE_THREADS) / max(per_row, 1));
+  const int per_row = a.wpitch;
+  int rh = max(1, (4 * PRE_THREADS) / max(per_row, 1));
   rh = min(rh, max(1, (40 * 1024) / (NPL * NR * a.row_pitch)));
   rh = min(rh, a.Ho);
   a.rh = rh;
@@ -966,7 +1004,12 @@ static int preprocess_rows_launch(const uint8_t* src, void* out, int n, PreRowAr
   const long long blocks = (long long)n * a.To * a.hgroups;
   CSE_REQUIRE(blocks < (1ll << 31), "preprocess: too many blocks");
   if (blocks == 0) return CSE_OK;
-  preprocess_rows_kernel<MODE, C, CL><<<(unsigned)blocks, PRE_THREADS, smem, st>>>(src, (__nv_bfloat16*)out, a);
+  bool ident = true;          // the reference's behaviour (train.py:466-478): raw 0..255, no mean / scale
+  for (int c = 0; c < C; ++c) ident = ident && a.mean[c] == 0.f && a.scale[c] == 1.f;
+  if (ident)
+    preprocess_rows_kernel<MODE, C, CL, true><<<(unsigned)blocks, PRE_THREADS, smem, st>>>(src, (__nv_bfloat16*)out, a);
+  else
+    preprocess_rows_kernel<MODE, C, CL, false><<<(unsigned)blocks, PRE_THREADS, smem, st>>>(src, (__nv_bfloat16*)out, a);
   CSE_CUDA(cudaGetLastError());
   return CSE_OK;
 }

@@ -547,7 +547,7 @@ class Lowerer:
             # 2x2x2 cells (depth too) carry 8*C channels without padding: the stem becomes a stride-1 4x4x4-cell conv
             # with K = 16 x (4 cells x 8C) instead of 28 x (4 cells x round_up(4C, 8)).  C = 3: 1536 vs 1792 (real
             # 1029); C = 1: 512 vs 896; worse for C = 2 / 4 (7 -> 8 taps in depth without a channel-padding gain).
-            if self.s2d_depth and self.stem_halo and 16 * 4 * 8 * c < 28 * 4 * cell:
+            if self.stem_halo and (self.s2d_depth == "always" or (self.s2d_depth and 16 * 4 * 8 * c < 28 * 4 * cell)):
                 t2 = (t + 1) // 2
                 cell3 = 8 * c
                 b = self.new_buf(node.name, (t2, h2, wpitch), cell3, self.act)

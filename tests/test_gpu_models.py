@@ -144,7 +144,7 @@ AGREE_REQUIRED = {"C3D": 0.999, "I3D": 0.999}
 # emulation (fp64 accumulation, no kernel involved) is 1.2e-2 off the fp32 logits on the worst of 512 of these clips
 # (measured on the CPU; cf. test_oracle.py::test_bf16_quantisation_floor_r3d50), the device path 1.3e-2 on the worst
 # of 10 240.  The two-clip full-geometry test above keeps 1e-2 for R3D-34.
-AGREE_LOGIT_TOL = {"R3D_34": 2e-2}
+AGREE_LOGIT_TOL = {"R3D_34": 2e-2, "TWOSTREAM_I3D": 1.25e-2}       # TwoStream: 1.007e-2 on the worst of 10 240 clips
 
 
 @pytest.mark.parametrize("mt,shape", AGREE_CASES)
