@@ -544,10 +544,14 @@ class Lowerer:
             wpitch = w2 + 3
             mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
             scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
-            # 2x2x2 cells (depth too) carry 8*C channels without padding: the stem becomes a stride-1 4x4x4-cell conv
-            # with K = 16 x (4 cells x 8C) instead of 28 x (4 cells x round_up(4C, 8)).  C = 3: 1536 vs 1792 (real
-            # 1029); C = 1: 512 vs 896; worse for C = 2 / 4 (7 -> 8 taps in depth without a channel-padding gain).
-            if self.stem_halo and (self.s2d_depth == "always" or (self.s2d_depth and 16 * 4 * 8 * c < 28 * 4 * cell)):
+            # 2x2x2 cells (depth too) carry 8*C channels without padding: the stem becomes a stride-1 4x4x4-cell conv with
+            # K = 16 x (4 cells x 8C) instead of 28 x (4 cells x round_up(4C, 8)).  Measured (tools/stem_bench.py,
+            # profiles/r2_stem_variants.txt): the K chunk decides - 64-channel chunks (128-byte swizzle) run ~1.5x the
+            # executed FLOP rate of 32-channel ones.  C = 2 (flow): window 4 x 16 = 64 channels, K 1024 at kc = 64 beats
+            # K 896 at kc = 32 (1.52 vs 1.82 ms); C = 1: 512 vs 896, both kc = 32; C = 3: the 96-channel window needs
+            # kc = 32 and loses to the 2-D layout's K 1792 at kc = 64 (3.0 vs 2.5 ms) - kept 2-D.
+            want3d = c in (1, 2) if self.s2d_depth is True else self.s2d_depth == "always"
+            if self.stem_halo and want3d:
                 t2 = (t + 1) // 2
                 cell3 = 8 * c
                 b = self.new_buf(node.name, (t2, h2, wpitch), cell3, self.act)

@@ -303,7 +303,7 @@ def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb, halo, depth):
     2x2 space-to-depth cells written by the pre-processing kernel, 4-cell window through an
     overlapping-stride TMA view, k=(7,4,1) stride (2,1,1) with a zero-extended regrouped kernel.
     Even and odd extents (TF 'same' pads (2,3) resp. (3,3)) and C = 1, 2, 3.  depth: 2x2x2 cells (8*C channels without
-    padding, k=(4,4,1) stride 1) where that shrinks K (C = 1, 3)."""
+    padding, k=(4,4,1) stride 1) for C = 1, 2 (see lowering._input for the measured choice)."""
     def build(g):
         x = g.input(dhw + (c,), name="in")
         x = g.conv3d(x, cout, (7, 7, 7), (2, 2, 2), "same", True, None, name="c")
@@ -311,7 +311,7 @@ def test_conv_tcgen05_s2d_stem(dhw, c, cout, nb, halo, depth):
         g.relu(x, name="r")
     g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c, stem_halo=halo, s2d_depth=depth)
     op = [o for o in m.plan.ops if o.name == "c"][0]
-    if depth and c in (1, 3):
+    if depth and c in (1, 2):
         assert op.engine == rt.ENGINE_TCGEN05 and op.k == (4, 4, 1) and op.s == (1, 1, 1) and op.in0.C == 32 * c
     else:
         assert op.engine == rt.ENGINE_TCGEN05 and op.k == (7, 4, 1) and op.s == (2, 1, 1)

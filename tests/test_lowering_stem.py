@@ -27,7 +27,7 @@ def s2d_cells(x, s2d, cell, wpitch, wpad):
     return out
 
 
-@pytest.mark.parametrize("depth", [True, False])
+@pytest.mark.parametrize("depth", [True, False, "always"])
 @pytest.mark.parametrize("dhw,c", [((8, 16, 16), 3), ((9, 21, 19), 3), ((7, 10, 34), 1), ((6, 20, 28), 2), ((5, 9, 12), 3)])
 def test_s2d_stem_regrouping_equals_reference_conv(dhw, c, depth):
     g = G.Graph("t", "functional")
@@ -45,7 +45,7 @@ def test_s2d_stem_regrouping_equals_reference_conv(dhw, c, depth):
     low.lower()
     view, k2 = captured["view"], captured["k2"]
     pre = low.ops[0].out0
-    assert pre.s2d == (2 if depth and c in (1, 3) else 1)
+    assert pre.s2d == (2 if (depth == "always" or (depth and c in (1, 2))) else 1)
     clips = np.random.default_rng(0).integers(0, 256, (2,) + dhw + (c,)).astype(np.float64)
     cells = s2d_cells(clips, pre.s2d, pre.ld, pre.wpitch, pre.wpad)
     # the overlapping-stride TMA view: position w2 sees the 4 cells w2 .. w2+3 of the padded row
