@@ -101,6 +101,11 @@ struct ConvTcDesc {            // built once at plan finalize
   int bs_stages, bs_nslots, bs_slots;
   uint32_t bs_b_region, bs_b_stage, bs_stage_region;
   size_t bs_smem_bytes;
+  CUtensorMap tmap_bh;         // CTA-pair mode: weight map with a box of bn/2 rows (each CTA loads half of every tap)
+  int pair_ok;                 // CTA-pair (cta_group::2) layout available: h-halo mode, single N tile, plain epilogue
+  int p2_stages, p2_nslots;
+  uint32_t p2_stage_bytes, p2_stage_region;
+  size_t p2_smem_bytes;
   int twin_ok;                 // twin-tile layout available (two M tiles share every B stage)
   uint32_t tw_stage_bytes, tw_stage_region;
   int tw_stages, tw_nslots;
@@ -122,5 +127,6 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
                   int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
                   const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_split2, void* out2, int out2_ld);
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);
+int launch_conv_tc_pair(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);   // conv_tc2.cu
 
 }  // namespace cse

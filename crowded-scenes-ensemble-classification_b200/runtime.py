@@ -87,6 +87,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     if lib.cse_abi_version() != 1:
         raise CseError("ABI version mismatch: library %d, binding 1" % lib.cse_abi_version())
     _lib = lib
+    # experiments: CSE_TUNE="pair_min_tiles=0,twin_min_tiles=2" is applied ONCE here (never read on the launch path)
+    for item in filter(None, os.environ.get("CSE_TUNE", "").split(",")):
+        key, _, val = item.partition("=")
+        check(lib.cse_tune(key.strip().encode(), int(val)))
     return lib
 
 

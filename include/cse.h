@@ -121,9 +121,9 @@ const char* cse_last_error(void);
 /* sm count / compute capability of the current device; fails without a CUDA device */
 int         cse_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* Tuning / test hook: overrides a launch heuristic for the whole process.  Keys: "twin_min_tiles", "bshare_min_tiles"
- * (tile counts from which the twin-tile / shared-B conv modes are used; 0 = never, -1 = built-in default),
- * "splitk_min_ksteps" (see DESIGN.md).  Unknown key -> CSE_ERR_INVALID. */
+/* Tuning / test hook: overrides a launch heuristic for the whole process.  Keys: "twin_min_tiles", "bshare_min_tiles",
+ * "pair_min_tiles" (tile counts from which the twin-tile / shared-B / CTA-pair conv modes are used; 0 = never,
+ * -1 = built-in default).  Unknown key -> CSE_ERR_INVALID. */
 int         cse_tune(const char* key, int value);
 
 /* ---- member plan: replaces evaluate_load_model + predict_generator ------------------------ */

@@ -358,6 +358,40 @@ def test_conv_tcgen05_s2d_stem_shared_weights(dhw, c, cout, nb):
     assert np.abs(got - y).max() / np.abs(y).max() <= 2.0 ** -7
 
 
+@pytest.mark.parametrize("dhw,c,cout,nb,depth", [((8, 16, 16), 3, 64, 2, False), ((9, 21, 19), 3, 64, 3, False),
+                                                 ((6, 20, 28), 2, 64, 3, True), ((4, 12, 12), 3, 32, 2, False),
+                                                 ((16, 48, 48), 2, 64, 5, False), ((11, 30, 30), 3, 64, 3, False),
+                                                 ((7, 10, 34), 1, 16, 1, True), ((12, 40, 40), 2, 128, 2, True)])
+def test_conv_tcgen05_stem_cta_pair(dhw, c, cout, nb, depth):
+    """CTA-pair mode (tcgen05 cta_group::2: one 256 x N x 16 MMA per two CTAs, every CTA stages its own A box and half
+    of the weight rows; conv_tc2.cu), forced on small shapes: even and odd tile counts (the last CTA of an odd count
+    re-runs a tile without storing it), several tile pairs per cluster, ragged bricks, kc = 32 and 64, N = 16 .. 128.
+    Every tile accumulates the same products in the same order as the single-CTA h-halo path -> bit-identical."""
+    def build(g):
+        x = g.input(dhw + (c,), name="in")
+        x = g.conv3d(x, cout, (7, 7, 7), (2, 2, 2), "same", True, None, name="c")
+        x = g.bn(x, scale=True, name="b")
+        g.relu(x, name="r")
+    xs = clips(11, nb, dhw + (c,))
+    tune("bshare_min_tiles", 0)
+    tune("pair_min_tiles", 0)            # off
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c, s2d_depth=depth)
+    run(m, [xs])
+    ref = m.read_tensor(m.plan.tensors["r"], nb)
+    del m
+    tune("pair_min_tiles", 1)            # always
+    g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * c, mean=[128.0] * c, s2d_depth=depth)
+    assert [o for o in m.plan.ops if o.name == "c"][0].halo == 2
+    run(m, [xs])
+    got = m.read_tensor(m.plan.tensors["r"], nb)
+    xin = torch.as_tensor((xs.astype(np.float64) - 128.0) / 64.0, dtype=T64)
+    kern, bias = w["c"]
+    y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (2, 2, 2), "same")
+    y = O.relu(O.batchnorm(y, *[torch.as_tensor(a, dtype=T64) for a in w["b"]])).numpy()
+    assert np.abs(got - y).max() / np.abs(y).max() <= 2.0 ** -7
+    assert np.array_equal(got, ref)
+
+
 PAIR_POOL = [((4, 16, 16), 3, True), ((3, 12, 40), 3, True), ((5, 8, 24), 2, False), ((2, 34, 18), 3, True),
              ((3, 16, 112), 4, True)]
 

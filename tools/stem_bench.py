@@ -43,21 +43,23 @@ def main():
         w = synthetic_weights(g, seed=1)
         x = torch.randint(0, 256, (n,) + shape, dtype=torch.uint8, device="cuda")
         flops = 2.0 * n * np.prod([s // 2 for s in shape[:3]]) * 64 * 343 * c
-        for depth in (False, True, "always"):
-            for bshare in (-1, 0, 1):
+        for depth, bshare, pair in ((False, -1, 0), (False, 0, -1), ("always", -1, 0), ("always", 0, -1)):
+            if True:
                 rt.tune("bshare_min_tiles", bshare)
+                rt.tune("pair_min_tiles", pair)
                 m = Member(g, w, precision="bf16", max_batch=n, s2d_depth=depth)
                 op = [o for o in m.plan.ops if o.name == "c"][0]
                 idx = m.plan.ops.index(op)
                 ms = time_op(m, x, idx)
                 pre = time_op(m, x, 0)
-                rec = {"C": c, "shape": shape, "n": n, "s2d_depth": depth, "bshare_min_tiles": bshare, "k": op.k, "kc": op.kc,
+                rec = {"C": c, "shape": shape, "n": n, "s2d_depth": depth, "bshare_min_tiles": bshare, "pair_min_tiles": pair, "k": op.k, "kc": op.kc,
                        "Cin": op.in0.C, "brick": op.brick, "halo": op.halo, "stem_ms": round(ms, 3),
                        "alg_tflops": round(flops / ms / 1e9, 1), "preprocess_ms": round(pre, 3)}
                 print(json.dumps(rec), flush=True)
                 out.append(rec)
                 del m
     rt.tune("bshare_min_tiles", -1)
+    rt.tune("pair_min_tiles", -1)
 
 
 if __name__ == "__main__":
