@@ -5,6 +5,11 @@ train.py:132-145), ``cv2.resize``s each frame to (W, H) (bilinear) and stores th
 into a float32 batch - no crop, no mean/std (train.py:245-291, 466-478).  TwoStream clips add a
 2-channel flow volume built from two gray videos (TV-L1, train.py:196-221).
 
+The FarneBack_onTheFly TwoStream variant (train.py:294-332, the SPECIALCASE token of the default global list,
+evaluate_ensemble.py:1365-1386) computes a dense float32 flow between consecutive frames in the loader with OpenCV;
+``farneback_flow`` makes the same OpenCV calls in the same order (loader-side, like the reference: decode and flow
+extraction are CPU I/O in front of the accelerated path), and the float32 flow volume goes to the GPU as is.
+
 ``ClipSequence`` keeps the keras.utils.Sequence protocol (``__len__``, ``__getitem__(i) ->
 (x | [x_rgb, x_flow], y_onehot)``) but yields uint8 arrays (what the frames are before the float32
 store) so a clip costs 1 byte per value on the way to the GPU.  Video decoding is CPU I/O and
@@ -113,6 +118,43 @@ def load_flow_clip(xpath: str, ypath: str, t: int, h: int, w: int, device=None):
     return out
 
 
+def farneback_flow(frames: Sequence[np.ndarray]) -> np.ndarray:
+    """Dense Farneback flow between consecutive frames -> float32 [len(frames) - 1, h', w', 2], as
+    opticalflow_FarneBack_extractor does it (train.py:294-332): the first frame is resized so that its longest side
+    (of H, W, 3) becomes 224 and THEN converted to gray, every later frame is converted to gray first and then
+    resized by the same factor (the order matters for the bytes); flow parameters pyr_scale 0.5, 5 levels, window 11,
+    5 iterations, poly_n 5, poly_sigma 1.1, no flags."""
+    import cv2
+    factor = 224 / max(frames[0].shape)
+    previous = cv2.cvtColor(cv2.resize(frames[0], None, fx=factor, fy=factor), cv2.COLOR_BGR2GRAY)
+    flows = []
+    for frame in frames[1:]:
+        if frame is None:
+            continue
+        current = cv2.resize(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY), None, fx=factor, fy=factor)
+        flows.append(cv2.calcOpticalFlowFarneback(previous, current, None, pyr_scale=0.5, levels=5, winsize=11,
+                                                  iterations=5, poly_n=5, poly_sigma=1.1, flags=0))
+        previous = current
+    return np.asarray(flows)
+
+
+def farneback_flow_clip(frames: Sequence[np.ndarray], t: int, h: int, w: int) -> np.ndarray:
+    """-> float32 [T,H,W,2]: select_frames over the len(frames) - 1 flow fields, each resized to (W, H) (bilinear,
+    float) - the FarneBack branch of get_twostream_videoclip (train.py:223-239)."""
+    import cv2
+    sel = select_frames(list(farneback_flow(frames)), t)
+    out = np.asarray([cv2.resize(f, (w, h)) for f in sel], dtype=np.float32)
+    if tuple(out.shape) != (t, h, w, 2):
+        raise ValueError("flow clip has shape %r, expected %r" % (tuple(out.shape), (t, h, w, 2)))
+    return out
+
+
+def load_farneback_twostream_clip(path: str, t: int, h: int, w: int):
+    """-> (uint8 [T,H,W,3] BGR, float32 [T,H,W,2] flow) of one video, decoded once."""
+    frames = decode_frames(path)
+    return _assemble(frames, t, h, w), farneback_flow_clip(frames, t, h, w)
+
+
 class ClipSequence:
     """DataGenerator for evaluation: ordered, not shuffled, non-augmented (evaluate_ensemble.py:1032-1040)."""
 
@@ -124,8 +166,9 @@ class ClipSequence:
         tensors, which Member.predict / predict_generator take directly."""
         if shuffle or augmentation_status != "non_augmented":
             raise ValueError("evaluation clips are ordered and non-augmented")
-        if model_type == "TWOSTREAM_I3D" and optical_flow_status != "TVL1_precomputed":
-            raise NotImplementedError("on-the-fly Farneback flow is outside the accelerated path (SURVEY §8f)")
+        if optical_flow_status not in ("TVL1_precomputed", "FarneBack_onTheFly"):
+            raise ValueError("optical_flow_status must be TVL1_precomputed or FarneBack_onTheFly")
+        self.farneback = model_type == "TWOSTREAM_I3D" and optical_flow_status == "FarneBack_onTheFly"
         self.video_data = video_data
         self.model_type = model_type
         self.input_shape = tuple(input_shape)
@@ -149,8 +192,11 @@ class ClipSequence:
         onehot[np.arange(len(labels)), labels % self.num_classes] = 1.0
         raw = []
         for i in idx:
-            item = {"rgb": _select(decode_frames(vd["rgbclips_path"].values[i]), t)}
-            if self.model_type == "TWOSTREAM_I3D":
+            frames = decode_frames(vd["rgbclips_path"].values[i])
+            item = {"rgb": _select(frames, t)}
+            if self.farneback:                    # dense flow in the loader thread, like the reference's workers
+                item["flow"] = farneback_flow_clip(frames, t, self.input_shape[1], self.input_shape[2])
+            elif self.model_type == "TWOSTREAM_I3D":
                 item["fx"] = _select(decode_frames(vd["x_axis_flowclips_path"].values[i], gray=True), t)
                 item["fy"] = _select(decode_frames(vd["y_axis_flowclips_path"].values[i], gray=True), t)
             raw.append(item)
@@ -166,6 +212,12 @@ class ClipSequence:
         rgb = stack([_finish(r["rgb"], t, h, w, self.device) for r in raw])
         if tuple(rgb.shape[1:]) != (t, h, w, 3):
             raise ValueError("clips decode to %r, expected %r" % (tuple(rgb.shape[1:]), (t, h, w, 3)))
+        if self.farneback:
+            flow = np.stack([r["flow"] for r in raw])
+            if self.device is not None:
+                import torch
+                flow = torch.from_numpy(flow).to(self.device)
+            return [rgb, flow]
         if self.model_type == "TWOSTREAM_I3D":
             flow = stack([last(_finish(r["fx"], t, h, w, self.device), _finish(r["fy"], t, h, w, self.device))
                           for r in raw])

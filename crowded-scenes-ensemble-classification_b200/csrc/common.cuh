@@ -87,7 +87,8 @@ int launch_add(int dt, const void* a, int a_ld, const void* b, int b_ld, void* o
 int launch_softmax(const float* in, float* out, int rows, int C, cudaStream_t st);
 int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int t0, int h0, int w0,
                       int To, int Ho, int Wo, const float* mean3, const float* scale3, void* out,
-                      int out_dt, int out_ld, cudaStream_t st, int wpitch = 0, int wpad = 0, int unroll_w = 0, int s2d = 0);
+                      int out_dt, int out_ld, cudaStream_t st, int wpitch = 0, int wpad = 0, int unroll_w = 0, int s2d = 0,
+                      int src_dt = CSE_U8);
 
 // tcgen05 engine
 struct ConvTcDesc {            // built once at plan finalize

@@ -805,9 +805,9 @@ struct PreArgs {
   float mean[4], scale[4];
 };
 
-template <typename TO, int CO>
+template <typename TO, int CO, typename TS>
 __global__ void __launch_bounds__(256)
-preprocess_kernel(const uint8_t* __restrict__ src, TO* __restrict__ out, long long total, PreArgs a) {
+preprocess_kernel(const TS* __restrict__ src, TO* __restrict__ out, long long total, PreArgs a) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   int wp = (int)(idx % a.wpitch); long long t = idx / a.wpitch;
@@ -816,7 +816,7 @@ preprocess_kernel(const uint8_t* __restrict__ src, TO* __restrict__ out, long lo
   const int w = wp - a.wpad;
   const bool real = (w >= 0 && w < a.Wo);         // pad columns of the row are written as zeros
   long long spix = ((nn * a.T + (d + a.t0)) * a.H + (h + a.h0)) * a.W + (real ? (w + a.w0) : 0);
-  const uint8_t* s = src + spix * a.C;
+  const TS* s = src + spix * a.C;
   __align__(16) TO v[CO];
 #pragma unroll
   for (int c = 0; c < CO; ++c) {
@@ -869,9 +869,16 @@ struct PreRowArgs {
 // uint8 -> float without the conversion unit: 0x4B000000 | b is the float 2^23 + b, exactly.
 __device__ __forceinline__ float u8_to_f32(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
 
-template <int MODE, int C, int CL, bool IDENT>
+// source element -> float: uint8 frames (the reference's decoded BGR / TV-L1 gray values) or float32 (the dense flow
+// of the FarneBack_onTheFly variant, train.py:294-332)
+__device__ __forceinline__ float src_to_f32(const uint8_t* p) { return u8_to_f32(*p); }
+__device__ __forceinline__ float src_to_f32(const float* p) { return *p; }
+
+template <int MODE, int C, int CL, bool IDENT, typename TS>
 __global__ void __launch_bounds__(PRE_THREADS)
-preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, PreRowArgs a) {
+preprocess_rows_kernel(const TS* __restrict__ src_t, __nv_bfloat16* __restrict__ out, PreRowArgs a) {
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(src_t);
+  constexpr int ES = (int)sizeof(TS);                     // bytes per source element
   constexpr int NPL = (MODE == 21) ? 2 : 1;               // source planes per output plane
   constexpr int NR = (MODE >= 20) ? 2 : 1;                // source rows per output row
   constexpr int Q = CL / 8;                               // 16-byte chunks per output position
@@ -896,7 +903,7 @@ preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restric
       const int ts = (MODE == 21) ? 2 * d + pl : d + a.t0;
       const int hs = (MODE >= 20) ? 2 * (h_first + rh) + rr : h_first + rh + a.h0;
       if (ts < a.T && hs < a.H) {
-        const uint4* g = reinterpret_cast<const uint4*>(src + (((n * a.T + ts) * a.H + hs) * (long long)a.W) * C);
+        const uint4* g = reinterpret_cast<const uint4*>(src + (((n * a.T + ts) * a.H + hs) * (long long)a.W) * (C * ES));
         reinterpret_cast<uint4*>(rows + (size_t)r * a.row_pitch)[v] = __ldg(g + v);
       }
     }
@@ -906,7 +913,7 @@ preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restric
       const int rr = r % NR, pl = (r / NR) % NPL, rh = r / (NR * NPL);
       const int ts = (MODE == 21) ? 2 * d + pl : d + a.t0;
       const int hs = (MODE >= 20) ? 2 * (h_first + rh) + rr : h_first + rh + a.h0;
-      if (ts < a.T && hs < a.H) rows[(size_t)r * a.row_pitch + v] = __ldg(src + (((n * a.T + ts) * a.H + hs) * (long long)a.W) * C + v);
+      if (ts < a.T && hs < a.H) rows[(size_t)r * a.row_pitch + v] = __ldg(src + (((n * a.T + ts) * a.H + hs) * (long long)a.W) * (C * ES) + v);
     }
   }
   __syncthreads();
@@ -929,7 +936,7 @@ preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restric
       const int wlim = (MODE == 4) ? (a.W - a.w0) : a.Wo;      // pixels available in the (cropped) row
       interior = xo >= 0 && xo < a.Wo && p0 >= 0 && p0 + MODE <= wlim;
     }
-    const uint8_t* seg0 = rows + (size_t)(rh * NPL * NR) * a.row_pitch + ((MODE >= 20) ? p0 : p0 + a.w0) * C;
+    const uint8_t* seg0 = rows + (size_t)(rh * NPL * NR) * a.row_pitch + ((MODE >= 20) ? p0 : p0 + a.w0) * (C * ES);
     if (interior) {
 #pragma unroll
       for (int k2 = 0; k2 < CL / 2; ++k2) {
@@ -941,7 +948,7 @@ preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restric
           float val = 0.f;
           if (k < KREAL) {
             const int sg = k / L, j = k - sg * L, c = j % C;      // compile-time after unrolling
-            val = u8_to_f32(seg0[(size_t)sg * a.row_pitch + j]);
+            val = src_to_f32(reinterpret_cast<const TS*>(seg0 + (size_t)sg * a.row_pitch) + j);
             if (!IDENT) val = (val - a.mean[c]) * a.scale[c];
           }
           f[e] = val;
@@ -970,7 +977,7 @@ preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restric
               ok = p0 + px >= 0 && p0 + px < wlim;
             }
             if (ok) {
-              val = u8_to_f32(seg0[(size_t)sg * a.row_pitch + j]);
+              val = src_to_f32(reinterpret_cast<const TS*>(seg0 + (size_t)sg * a.row_pitch) + j);
               if (!IDENT) val = (val - a.mean[c]) * a.scale[c];
             }
           }
@@ -986,9 +993,9 @@ preprocess_rows_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restric
   }
 }
 
-template <int MODE, int C, int CL>
-static int preprocess_rows_launch(const uint8_t* src, void* out, int n, PreRowArgs a, cudaStream_t st) {
-  a.row_bytes = a.W * C;
+template <int MODE, int C, int CL, typename TS>
+static int preprocess_rows_launch_t(const TS* src, void* out, int n, PreRowArgs a, cudaStream_t st) {
+  a.row_bytes = a.W * C * (int)sizeof(TS);
   a.row_pitch = (a.row_bytes + 15) & ~15;
   a.aligned = (a.row_bytes % 16 == 0) && (((uintptr_t)src) % 16 == 0);
   constexpr int NPL = (MODE == 21) ? 2 : 1, NR = (MODE >= 20) ? 2 : 1;
@@ -1007,16 +1014,31 @@ static int preprocess_rows_launch(const uint8_t* src, void* out, int n, PreRowAr
   bool ident = true;          // the reference's behaviour (train.py:466-478): raw 0..255, no mean / scale
   for (int c = 0; c < C; ++c) ident = ident && a.mean[c] == 0.f && a.scale[c] == 1.f;
   if (ident)
-    preprocess_rows_kernel<MODE, C, CL, true><<<(unsigned)blocks, PRE_THREADS, smem, st>>>(src, (__nv_bfloat16*)out, a);
+    preprocess_rows_kernel<MODE, C, CL, true, TS><<<(unsigned)blocks, PRE_THREADS, smem, st>>>(src, (__nv_bfloat16*)out, a);
   else
-    preprocess_rows_kernel<MODE, C, CL, false><<<(unsigned)blocks, PRE_THREADS, smem, st>>>(src, (__nv_bfloat16*)out, a);
+    preprocess_rows_kernel<MODE, C, CL, false, TS><<<(unsigned)blocks, PRE_THREADS, smem, st>>>(src, (__nv_bfloat16*)out, a);
   CSE_CUDA(cudaGetLastError());
   return CSE_OK;
 }
 
+// src_f32: the clip holds float32 values (on-the-fly Farneback flow) instead of uint8 frames.  Only the 1- / 2-channel
+// space-to-depth stems are instantiated for it (a flow volume has 2 channels).
+template <int MODE, int C, int CL>
+static int preprocess_rows_launch(const uint8_t* src, void* out, int n, const PreRowArgs& a, cudaStream_t st, bool src_f32) {
+  if (!src_f32) return preprocess_rows_launch_t<MODE, C, CL, uint8_t>(src, out, n, a, st);
+  if constexpr (MODE >= 20 && C <= 2) {
+    return preprocess_rows_launch_t<MODE, C, CL, float>(reinterpret_cast<const float*>(src), out, n, a, st);
+  } else {
+    set_error("preprocess: float32 clips are supported for the 1- / 2-channel space-to-depth stems only");
+    return CSE_ERR_INVALID;
+  }
+}
+
 int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int t0, int h0, int w0,
                       int To, int Ho, int Wo, const float* mean, const float* scale, void* out,
-                      int out_dt, int out_ld, cudaStream_t st, int wpitch, int wpad, int unroll_w, int s2d) {
+                      int out_dt, int out_ld, cudaStream_t st, int wpitch, int wpad, int unroll_w, int s2d, int src_dt) {
+  CSE_REQUIRE(src_dt == CSE_U8 || src_dt == CSE_F32, "preprocess: source dtype %d must be u8 or f32", src_dt);
+  const bool src_f32 = src_dt == CSE_F32;
   if (s2d) {
     // s2d = 1: To,Ho,Wo = T, ceil(H/2), ceil(W/2); s2d = 2: ceil(T/2), ceil(H/2), ceil(W/2) - the space-to-depth grid
     const int cells = s2d == 2 ? 8 : 4;
@@ -1034,7 +1056,7 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
       a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
       a.scale[c] = (scale && c < C) ? scale[c] : 1.f;
     }
-#define S2D_CASE(M_, C_, CL_) return preprocess_rows_launch<M_, C_, CL_>(src, out, n, a, st)
+#define S2D_CASE(M_, C_, CL_) return preprocess_rows_launch<M_, C_, CL_>(src, out, n, a, st, src_f32)
     if (s2d == 2) {
       if (C == 1 && out_ld == 8) S2D_CASE(21, 1, 8);
       if (C == 2 && out_ld == 16) S2D_CASE(21, 2, 16);
@@ -1066,7 +1088,7 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
       a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
       a.scale[c] = (scale && c < C) ? scale[c] : 1.f;
     }
-#define UNR_CASE(NB_, C_) return preprocess_rows_launch<NB_, C_, 16>(src, out, n, a, st)
+#define UNR_CASE(NB_, C_) return preprocess_rows_launch<NB_, C_, 16>(src, out, n, a, st, src_f32)
     if (unroll_w == 4) {
       switch (C) { case 1: UNR_CASE(4, 1); case 2: UNR_CASE(4, 2); case 3: UNR_CASE(4, 3); default: UNR_CASE(4, 4); }
     } else {
@@ -1092,7 +1114,11 @@ int launch_preprocess(const uint8_t* src, int n, int T, int H, int W, int C, int
   if (total == 0) return CSE_OK;
   unsigned blocks = (unsigned)((total + 255) / 256);
   using bf = __nv_bfloat16;
-#define PRE_CASE(TT, CO) preprocess_kernel<TT, CO><<<blocks, 256, 0, st>>>(src, (TT*)out, total, a)
+#define PRE_CASE(TT, CO)                                                                                          \
+  do {                                                                                                            \
+    if (src_f32) preprocess_kernel<TT, CO, float><<<blocks, 256, 0, st>>>((const float*)src, (TT*)out, total, a); \
+    else preprocess_kernel<TT, CO, uint8_t><<<blocks, 256, 0, st>>>(src, (TT*)out, total, a);                     \
+  } while (0)
   if (out_dt == CSE_BF16) {
     switch (out_ld) {
       case 8: PRE_CASE(bf, 8); break;

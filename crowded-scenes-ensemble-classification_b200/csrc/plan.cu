@@ -130,6 +130,9 @@ int cse_plan_add_op(cse_plan* p, const cse_op* op) {
   CSE_REQUIRE(p && op, "plan_add_op: NULL argument");
   if (p->finalized) { set_error("plan_add_op: plan already finalized"); return CSE_ERR_STATE; }
   CSE_REQUIRE(op->kind >= CSE_OP_PREPROCESS && op->kind <= CSE_OP_SOFTMAX, "plan_add_op: unknown kind %d", op->kind);
+  if (op->kind == CSE_OP_PREPROCESS)
+    CSE_REQUIRE(op->in_dtype == CSE_U8 || op->in_dtype == CSE_F32,
+                "plan_add_op: PREPROCESS in_dtype must be CSE_U8 (decoded frames) or CSE_F32 (float flow), got %d", op->in_dtype);
   if (op->kind == CSE_OP_CONV3D)
     CSE_REQUIRE(op->engine == CSE_ENGINE_DIRECT || op->engine == CSE_ENGINE_TCGEN05,
                 "plan_add_op: conv engine must be DIRECT or TCGEN05 (got %d)", op->engine);
@@ -240,7 +243,7 @@ static int run_op(cse_plan* p, PlanOp& po, const uint8_t* rgb, const uint8_t* fl
       return launch_preprocess(src, n, o.src_dims[0], o.src_dims[1], o.src_dims[2], o.src_dims[3], o.crop[0],
                                o.crop[1], o.crop[2], o.out_dims[0], o.out_dims[1], o.out_dims[2], o.pre_mean,
                                o.pre_scale, wsp(o.out0_off), o.out_dtype, o.out_ld, st, o.out_wpitch, o.out_wpad, o.pre_unroll_w,
-                               o.pre_s2d);
+                               o.pre_s2d, o.in_dtype);
     }
     case CSE_OP_CONV3D: {
       Epilogue ep;

@@ -454,13 +454,16 @@ class _NoMembers:
         return inputs[0].shape[0]
 
 
-def _load_members(model_type, member_paths, input_shape, nb_classes, batch):
+def _load_members(model_type, member_paths, input_shape, nb_classes, batch, optical_flow_status="TVL1_precomputed"):
     """All members of one test fold on this GPU, sharing one activation workspace."""
     from .ensemble_runtime import DeviceEnsemble
     from .graph import build_model_graph
     g = build_model_graph(model_type, tuple(input_shape), nb_classes)
     weight_sets = [zoo.load_member_weights(g, p) for p in member_paths]
-    return DeviceEnsemble(g, weight_sets, precision=zoo.DEFAULTS["precision"], max_batch=batch, micro_batch=batch)
+    kw = {}
+    if model_type == "TWOSTREAM_I3D" and optical_flow_status == "FarneBack_onTheFly":
+        kw["input_dtypes"] = ("u8", "f32")        # the on-the-fly flow is a float32 volume (train.py:294-332)
+    return DeviceEnsemble(g, weight_sets, precision=zoo.DEFAULTS["precision"], max_batch=batch, micro_batch=batch, **kw)
 
 
 def _predict_members(ens, generator, n_clips, dist_state, chunk, owned=None, m_total=None, workers=1):
@@ -547,7 +550,8 @@ def store_probabilities(trained_models_folder, results_folder, involved_sets, ba
             # member-sharded partition: this rank loads and runs only its own members on all clips
             owned = shard_members([1.0] * len(member_paths), dist_state[2])
         local_paths = member_paths if owned is None else [member_paths[m] for m in owned[rank]]
-        ens = _load_members(model_type, local_paths, sample_input.shape, nb_classes, chunk) if local_paths else None
+        ens = _load_members(model_type, local_paths, sample_input.shape, nb_classes, chunk,
+                            optical_flow_status) if local_paths else None
         if ens is None:         # more ranks than members: nothing to run here, but take part in the gather
             ens = _NoMembers(nb_classes)
         probs = _predict_members(ens, generator, generator.n, dist_state, chunk, owned, len(member_paths),

@@ -96,6 +96,7 @@ class DevOp:
     brick: Tuple[int, int, int, int] = (0, 0, 0, 0)
     halo: int = 0
     pair_pool: int = 0
+    src_dtype: int = 2            # PREPROCESS: dtype of the external clip (rt.U8 frames / rt.F32 on-the-fly flow)
     out_split: int = 0            # fused sibling 1x1x1 convs: columns >= out_split go to out1, >= out_split2 to out2
     out_split2: int = 0
     out2: Optional[TRef] = None
@@ -158,6 +159,7 @@ class Plan:
                 s.pool_zero = op.pool_zero
             if op.kind == rt.OP_PREPROCESS:
                 s.out_wpitch, s.out_wpad, s.pre_unroll_w, s.pre_s2d = o0.wpitch, o0.wpad, o0.unroll_w, o0.s2d
+                s.in_dtype = op.src_dtype
             if op.in1 is not None:
                 s.in1_ld, s.in1_off = op.in1.ld, op.in1.byte_off()
             else:
@@ -353,8 +355,13 @@ class Lowerer:
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
                  stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True,
                  balance_n: bool = True, pair_pool: bool = True, persist_input: bool = False,
-                 fuse_siblings: bool = True, s2d_depth: bool = True):
+                 fuse_siblings: bool = True, s2d_depth: bool = True, input_dtypes=None):
         self.s2d_depth = s2d_depth
+        # dtype of every external input: "u8" (decoded frames - the default) or "f32" (the dense flow of the
+        # FarneBack_onTheFly TwoStream variant, train.py:294-332, evaluate_ensemble.py:1365-1386)
+        self.input_dtypes = tuple(input_dtypes) if input_dtypes else tuple("u8" for _ in g.inputs)
+        if len(self.input_dtypes) != len(g.inputs) or any(d not in ("u8", "f32") for d in self.input_dtypes):
+            raise ValueError("input_dtypes must hold 'u8' / 'f32' for each of the %d inputs" % len(g.inputs))
         self.keep_all = keep_all
         self.fuse_siblings = fuse_siblings
         self.persist_input = persist_input
@@ -494,6 +501,7 @@ class Lowerer:
     def _input(self, node: Node):
         t, h, w, c = node.out_shape
         idx = self.g.inputs.index(node.name)
+        src_dt = rt.F32 if self.input_dtypes[idx] == "f32" else rt.U8
         crop = self.crop
         if crop is not None:
             t0, h0, w0, to, ho, wo = crop
@@ -502,7 +510,7 @@ class Lowerer:
         wpitch = wpad = 0
         cons = self.consumers[node.name]
         first = self.g.nodes[cons[0]] if len(cons) == 1 else None
-        if (self.use_tc and self.packed_stem and first is not None and first.op == "conv3d" and c <= 8
+        if (self.use_tc and self.packed_stem and src_dt == rt.U8 and first is not None and first.op == "conv3d" and c <= 8
                 and first.attrs["k"] == (3, 3, 3) and first.attrs["s"] == (1, 1, 1)
                 and first.attrs["padding"] == "same" and first.attrs["filters"] % 8 == 0 and c <= 4):
             # packed stem: the 3 kw taps of a pixel become one contiguous 32-wide K chunk
@@ -515,7 +523,7 @@ class Lowerer:
                 out = TRef(b, 0, c, 16, (t, h, w // 2), self.act, 0, 0, 4)
                 mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
                 scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
-                self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
+                self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx, src_dtype=src_dt,
                                 src_dims=(t, h, w, c), pre_mean=mean, pre_scale=scale, layers=(node.name,)))
                 self.val[node.name] = out
                 return
@@ -524,7 +532,7 @@ class Lowerer:
                 out = TRef(b, 0, c, 16, (t, h, w), self.act, 0, 0, 3)
                 mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
                 scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
-                self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
+                self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx, src_dtype=src_dt,
                                 src_dims=(t, h, w, c), pre_mean=mean, pre_scale=scale, layers=(node.name,)))
                 self.val[node.name] = out
                 return
@@ -532,7 +540,7 @@ class Lowerer:
         if (self.use_tc and self.s2d_stem and first is not None and first.op == "conv3d" and c <= 4
                 and first.attrs["k"] == (7, 7, 7) and first.attrs["s"] == (2, 2, 2)
                 and first.attrs["padding"] == "same" and first.attrs["filters"] % 8 == 0
-                and first.attrs["filters"] >= 16):
+                and first.attrs["filters"] >= 16 and (src_dt == rt.U8 or c <= 2)):
             # stride-2 7x7x7 stem (I3D Conv3d_1a_7x7 train.py:1026, R3D stem :1481): the pre-processing
             # kernel writes 2x2 space-to-depth cells over (H, W); rows are padded on the left by the
             # number of cells the 'same' padding reaches into and on the right so that the 4-cell
@@ -559,7 +567,7 @@ class Lowerer:
             else:
                 b = self.new_buf(node.name, (t, h2, wpitch), cell, self.act)
                 out = TRef(b, 0, cell, cell, (t, h2, w2), self.act, wpitch, wpad, 0, 1, c)
-            self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
+            self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx, src_dtype=src_dt,
                             src_dims=(t, h, w, c), pre_mean=mean, pre_scale=scale, layers=(node.name,)))
             self.val[node.name] = out
             return
@@ -567,7 +575,7 @@ class Lowerer:
         out = TRef(b, 0, c, ld, (t, h, w), self.act, wpitch, wpad)
         mean = tuple(self.mean) + (0.0,) * (4 - len(self.mean)) if self.mean is not None else (0.0,) * 4
         scale = tuple(self.scale) + (1.0,) * (4 - len(self.scale)) if self.scale is not None else (1.0,) * 4
-        self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx,
+        self.emit(DevOp(rt.OP_PREPROCESS, node.name, None, None, out, ext_input=idx, src_dtype=src_dt,
                         src_dims=(t, h, w, c), pre_mean=mean, pre_scale=scale, layers=(node.name,)))
         self.val[node.name] = out
 

@@ -33,6 +33,8 @@ class Member:
         self.precision = precision
         self.max_batch = int(max_batch)
         self.plan: Plan = lower(graph, weights, precision, self.max_batch, **lower_kw)
+        self.input_dtypes = tuple(lower_kw.get("input_dtypes") or ("u8",) * len(graph.inputs))
+        self._weights, self._lower_kw, self._variants = weights, dict(lower_kw), {}
         self.nb_classes = self.plan.nb_classes
         self.input_shapes = [graph.shape(n) for n in graph.inputs]
         with torch.cuda.device(self.device):
@@ -91,9 +93,10 @@ class Member:
         n = inputs_u8[0].shape[0]
         if n > self.max_batch:
             raise ValueError("batch %d exceeds max_batch %d" % (n, self.max_batch))
-        for x, shp in zip(inputs_u8, self.input_shapes):
-            if not (x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous()):
-                raise ValueError("inputs must be contiguous uint8 CUDA tensors")
+        for x, shp, dt in zip(inputs_u8, self.input_shapes, self.input_dtypes):
+            want = torch.uint8 if dt == "u8" else torch.float32
+            if not (x.is_cuda and x.dtype == want and x.is_contiguous()):
+                raise ValueError("inputs must be contiguous %s CUDA tensors" % ("uint8" if dt == "u8" else "float32"))
             if tuple(x.shape[1:]) != tuple(shp) or x.shape[0] != n:
                 raise ValueError("input shape %r does not match model input %r" % (tuple(x.shape), (n,) + tuple(shp)))
         if logits_out is None:
@@ -135,21 +138,37 @@ class Member:
     @staticmethod
     def _as_u8(x):
         if hasattr(x, "is_cuda"):              # torch tensor: clips assembled on the GPU (clips.ClipSequence(device=...))
-            if not (x.is_cuda and str(x.dtype) == "torch.uint8"):
-                raise ValueError("tensor clips must be uint8 CUDA tensors")
+            if not (x.is_cuda and str(x.dtype) in ("torch.uint8", "torch.float32")):
+                raise ValueError("tensor clips must be uint8 (frames) or float32 (on-the-fly flow) CUDA tensors")
             return x.contiguous()
         a = np.asarray(x)
         if a.dtype == np.uint8:
             return np.ascontiguousarray(a)
         r = np.rint(a)
         if not np.array_equal(r, a) or r.min() < 0 or r.max() > 255:
-            raise ValueError("clips must hold integer values 0..255 (decoded frames); got non-integer data")
+            if a.dtype in (np.float32, np.float64):
+                return np.ascontiguousarray(a, dtype=np.float32)     # dense optical flow (train.py:294-332): stays float
+            raise ValueError("clips must hold integer values 0..255 (decoded frames) or float32 flow; got %s" % a.dtype)
         return np.ascontiguousarray(r.astype(np.uint8))
+
+    def _for_inputs(self, xs):
+        """The member lowered for the dtypes of these inputs: decoded frames are uint8 (1 byte per value on the way to
+        the GPU), the FarneBack_onTheFly flow is float32.  A member is lowered for uint8 inputs unless told otherwise
+        (input_dtypes); the float variant shares graph and weights and is built on first use."""
+        dts = tuple("f32" if ("float" in str(v.dtype)) else "u8" for v in xs)
+        if dts == self.input_dtypes:
+            return self
+        if dts not in self._variants:
+            kw = dict(self._lower_kw, input_dtypes=dts)
+            self._variants[dts] = Member(self.graph, self._weights, precision=self.precision, max_batch=self.max_batch,
+                                         device=self.device, **kw)
+        return self._variants[dts]
 
     def predict(self, x, batch_size: Optional[int] = None, return_logits: bool = False):
         """x: NDHWC array (or [rgb, flow]) -> float32 [N, nb_classes] probabilities."""
         torch = self.torch
         xs = [self._as_u8(v) for v in (x if isinstance(x, (list, tuple)) else [x])]
+        me = self._for_inputs(xs)
         n = xs[0].shape[0]
         bs = min(batch_size or self.max_batch, self.max_batch)
         probs = np.empty((n, self.nb_classes), np.float32)
@@ -158,7 +177,7 @@ class Member:
             for i in range(0, n, bs):
                 dev = [v[i:i + bs].to(self.device).contiguous() if hasattr(v, "is_cuda")
                        else torch.from_numpy(v[i:i + bs]).to(self.device, non_blocking=False) for v in xs]
-                lg, pr = self.forward_device(dev)
+                lg, pr = me.forward_device(dev)
                 probs[i:i + bs] = pr.cpu().numpy()
                 logits[i:i + bs] = lg.cpu().numpy()
         return (probs, logits) if return_logits else probs

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcse_b200.so")
 
 # enums (include/cse.h)
+ABI_VERSION = 2
 F32, BF16, U8 = 0, 1, 2
 ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 OP_PREPROCESS, OP_CONV3D, OP_MAXPOOL3D, OP_AVGPOOL3D, OP_AFFINE, OP_ADD, OP_SOFTMAX = 1, 2, 3, 4, 5, 6, 7
@@ -84,8 +85,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cse_assemble_clip.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)
-    if lib.cse_abi_version() != 1:
-        raise CseError("ABI version mismatch: library %d, binding 1" % lib.cse_abi_version())
+    if lib.cse_abi_version() != ABI_VERSION:
+        raise CseError("ABI version mismatch: library %d, binding %d" % (lib.cse_abi_version(), ABI_VERSION))
     _lib = lib
     # experiments: CSE_TUNE="pair_min_tiles=0,twin_min_tiles=2" is applied ONCE here (never read on the launch path)
     for item in filter(None, os.environ.get("CSE_TUNE", "").split(",")):

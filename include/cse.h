@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CSE_ABI_VERSION 1
+#define CSE_ABI_VERSION 2
 
 typedef enum {
   CSE_OK = 0,
@@ -63,7 +63,9 @@ typedef enum {
 typedef struct cse_op {
   int32_t kind;              /* cse_op_kind */
   int32_t engine;            /* cse_engine (CONV3D only) */
-  int32_t in_dtype;          /* cse_dtype of in0 / in1 */
+  int32_t in_dtype;          /* cse_dtype of in0 / in1; PREPROCESS: dtype of the external clip - CSE_U8 (decoded frames, the
+                                default of every reference path) or CSE_F32 (dense flow of the FarneBack_onTheFly TwoStream
+                                variant, train.py:294-332, values are not integers) */
   int32_t out_dtype;         /* cse_dtype of out0 / out1 */
   int32_t w_dtype;           /* cse_dtype of the packed kernel */
   int32_t in_dims[4];        /* D,H,W,C of in0 per clip */
@@ -136,7 +138,8 @@ int  cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes,
                        const void* d_weights, size_t weight_bytes,
                        int64_t logits_off, int64_t probs_off);
 /* Runs the member on n <= max_batch clips.  d_rgb_u8 / d_flow_u8: uint8 NDHWC clips (flow may be
- * NULL for single-stream members).  d_logits / d_probs: fp32 [n, nb_classes] (either may be NULL). */
+ * NULL for single-stream members; it points to float32 values when the flow PREPROCESS op was declared with
+ * in_dtype = CSE_F32).  d_logits / d_probs: fp32 [n, nb_classes] (either may be NULL). */
 int  cse_plan_run(cse_plan* p, const uint8_t* d_rgb_u8, const uint8_t* d_flow_u8, int n,
                   float* d_logits, float* d_probs, void* stream);
 /* Same, starting at op `first_op`.  Members of one fold ensemble share the architecture, the

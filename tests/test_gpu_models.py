@@ -87,6 +87,32 @@ def test_twostream_matches_oracle():
     assert rel_err(l16, exp_logits.numpy()) <= 1e-2
 
 
+def test_twostream_float_flow_matches_oracle():
+    """FarneBack_onTheFly TwoStream variant (train.py:294-332; SPECIALCASE of the global list,
+    evaluate_ensemble.py:1365-1386): the flow tower takes a float32 volume (sub-pixel displacements, not bytes).  The
+    member lowered for ("u8", "f32") inputs against the oracle on the same values: fp32 <= 1e-4, bf16 <= 1e-2; a
+    member lowered for uint8 inputs switches to the float variant on its own when it is handed float flow."""
+    shape = (20, 96, 96, 0)
+    g = G.build_model_graph("TWOSTREAM_I3D", shape, 11)
+    w = synthetic_weights(g, seed=103, nontrivial=True)
+    rng = np.random.default_rng(8)
+    rgb = clips(1, 2, (20, 96, 96, 3))
+    flow = (rng.standard_normal((2, 20, 96, 96, 2)) * 3.0).astype(np.float32)
+    exp_logits, _ = OM.forward("TWOSTREAM_I3D", w, [rgb, flow], torch.float64)
+    exp_logits = exp_logits.numpy()
+    m32 = Member(g, w, precision="fp32", max_batch=2, input_dtypes=("u8", "f32"))
+    _, l32 = m32.predict([rgb, flow], return_logits=True)
+    assert rel_err(l32, exp_logits) <= 1e-4
+    del m32
+    m16 = Member(g, w, precision="bf16", max_batch=2)              # lowered for uint8 flow ...
+    _, l16 = m16.predict([rgb, flow], return_logits=True)          # ... builds its float-flow variant here
+    assert rel_err(l16, exp_logits) <= 1e-2
+    assert list(m16._variants) == [("u8", "f32")]
+    # integer-valued float flow (what a TV-L1 gray clip stored as float32 is) still takes the uint8 path
+    _, l8 = m16.predict([rgb, clips(2, 2, (20, 96, 96, 2)).astype(np.float32)], return_logits=True)
+    assert list(m16._variants) == [("u8", "f32")] and np.isfinite(l8).all()
+
+
 def test_batch_size_invariance_and_generator():
     """The reference runs batch 1 (evaluate_ensemble.py:1032-1040); batching must not change results."""
     shape = (16, 48, 48, 3)

@@ -65,7 +65,7 @@ def clips(seed, n, shape):
 # --------------------------------------------------------------------------- library
 def test_library_and_device():
     lib = rt.load_library()
-    assert lib.cse_abi_version() == 1
+    assert lib.cse_abi_version() == rt.ABI_VERSION == 2
     sm, mj, mn = rt.device_info()
     assert sm > 0 and mj == 10, "expected a Blackwell (sm_100) device, got cc %d.%d" % (mj, mn)
 

@@ -200,7 +200,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib = rt.load_library()                      # raises if the library is not built: no CPU fallback
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.cse_abi_version() == 1
+    assert lib.cse_abi_version() == rt.ABI_VERSION
 
 
 def test_cse_op_struct_matches_header_layout():
