@@ -98,6 +98,7 @@ struct ConvTcDesc {            // built once at plan finalize
   bool has_out1;
   int out_split, out_split2;   // fused sibling 1x1 convs: columns >= split go to out1, columns >= split2 to out2
   int pair_pool;               // pair-packed stem with the (1,2,2) max-pool done in registers
+  int groups;                  // epilogue groups of 4 warps (2; 4 for the pair-packed stem)
   int bs_group;                // shared-B h-halo layout: tiles per weight stage (0 = not available)
   int bs_stages, bs_nslots, bs_slots;
   uint32_t bs_b_region, bs_b_stage, bs_stage_region;

@@ -72,6 +72,7 @@ struct ConvTcArgs {
   int twin;                        // twin-tile mode: two M tiles share every B stage (4 TMEM accumulators of bn <= 128 columns)
   int pair_pool;                   // pair-packed stem: GEMM row = 2 output pixels (N = 2*Cout), (1,2,2) max-pool in registers
   int step1[5], step2[5];          // gridDim.x and 2*gridDim.x as mixed-radix digits (nt, tw, th, td, tn)
+  int stepE[5];                    // (epilogue groups)*gridDim.x: the stride of one epilogue group's tile walk
   Epilogue ep;
 };
 
@@ -100,8 +101,10 @@ struct TileIter {
 
 // KC = channels per pipeline stage (16 -> SWIZZLE_32B, 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B)
 // EC = output channels per epilogue chunk = TMA-store box width (16/32/64, same swizzle family)
-template <int KC, int EC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NG = epilogue groups of 4 warps (one TMEM accumulator each): 2 everywhere, 4 for the pair-packed C3D stem whose tile
+// is 9 short MMAs (576 cycles) against a ~2000-cycle pooled epilogue - four groups drain four accumulators in turn.
+template <int KC, int EC, int NG = 2>
+__global__ void __launch_bounds__(64 + 128 * NG, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1,
                const __grid_constant__ CUtensorMap tmap_o2,
@@ -115,7 +118,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // mbarriers: see the BAR_* offsets
   __shared__ __align__(8) uint64_t bars[BAR_COUNT];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_par[2][4][256];                   // per epilogue group: scale0, shift0, scale1, shift1
+  __shared__ __align__(16) float s_par[NG][4][256];                  // per epilogue group: scale0, shift0, scale1, shift1
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -303,7 +306,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     auto dlo = [](uint32_t saddr) -> uint32_t { return ((saddr >> 4) & 0x3FFFu) | 0x10000u; };   // start address + LBO = 1
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     int buf = 0;
     if (a.b_resident) {
       mbar_wait(bar_base + BAR_B_RESIDENT, 0u);
@@ -384,11 +386,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
-    for (int tile = (a.twin || a.bshare) ? a.num_tiles : blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      const uint32_t aph = buf ? acc_phase1 : acc_phase0;
+    uint32_t it = 0;                   // the CTA's it-th tile lives in accumulator it % nbuf (2 x 256 or 4 x 128 columns)
+    for (int tile = (a.twin || a.bshare) ? a.num_tiles : blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t nbm = (uint32_t)a.nbuf - 1u;
+      buf = (int)(it & nbm);
+      const uint32_t aph = (it / (uint32_t)a.nbuf) & 1u;
       mbar_wait(bar_base + BAR_TMEM_EMPTY + 8u * buf, aph ^ 1u);                   // tmem_empty[buf]
       tc_fence_after();
-      const uint32_t d_tmem = (uint32_t)buf * 256u;                       // TMEM base is 0 (asserted)
+      const uint32_t d_tmem = (uint32_t)buf * a.acc_cols;                 // TMEM base is 0 (asserted)
       if (a.halo == 2) {
         const int nst = a.kd * a.kchunks;
         const uint32_t a_fh = ((uint32_t)a.b_w * ROW_BYTES) >> 4;          // one brick row of pixels
@@ -412,8 +417,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (st == nst - 1) tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * buf);
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
-        if (buf) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
-        buf ^= 1;
         continue;
       }
       if (a.halo) {
@@ -433,8 +436,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_commit(leader, bar_base + BAR_EMPTY + 8u * stage);
         tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * buf);
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
-        if (buf) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
-        buf ^= 1;
         continue;
       }
       for (int ks = 0; ks < ksteps; ++ks) {
@@ -446,8 +447,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (ks == ksteps - 1) tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * buf);   // tmem_full[buf]
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       }
-      if (buf) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
-      buf ^= 1;
     }
   } else {
     // =============================== epilogue ===================================
@@ -518,11 +517,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int slot = 0;
     int last_nt = -1;
     TileIter ti;
-    for (ti.init(a, blockIdx.x + grp * gridDim.x); ti.tile < a.num_tiles; ti.advance(a, a.step2, 2 * gridDim.x)) {
+    for (ti.init(a, blockIdx.x + grp * gridDim.x); ti.tile < a.num_tiles; ti.advance(a, a.stepE, NG * gridDim.x)) {
       const int buf = (int)(seq & bmask);
       const uint32_t acc_phase = (seq / (uint32_t)a.nbuf) & 1u;
       const uint32_t buf_col = (uint32_t)buf * a.acc_cols;
-      seq += 2u;
+      seq += (uint32_t)NG;
       const int nt = ti.nt;
       const int ow0 = ti.tw * a.b_w, oh0 = ti.th * a.b_h, od0 = ti.td * a.b_d, on0 = ti.tn * a.b_n;
       const int col_base = nt * a.bn;
@@ -612,6 +611,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++slot == a.nslots) slot = 0;
         continue;
       }
+      if constexpr (NG == 2)          // (the 4-group instantiation only serves the pair-packed stem above)
       for (int c0 = 0; c0 < a.bn; c0 += EC) {
         // the staging slot we are about to overwrite must have been read by its TMA store
         if (store_thread) {
@@ -800,6 +800,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ----------------------------------------------------------------------------- host side
+// Tile-count thresholds of the shared-B / twin / CTA-pair modes and the epilogue groups of the pair-packed stem; -1 = the
+// built-in default.  Set through cse_tune() (tests force the modes on small shapes); never read from the environment on
+// the launch path.
+struct TcTune { int bshare_min_tiles = -1, twin_min_tiles = -1, pair_min_tiles = -1, stem_groups = -1; };
+static TcTune tc_tune;
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -1021,13 +1027,16 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   // keeps >= 4 stages (3 for the widest tiles); a TMA store only releases its slot once it has
   // read it, so more slots = more stores in flight
   d->slot_bytes = (uint32_t)slot;
+  // epilogue groups: 2; the pair-packed C3D stem runs 4 (tile = 9 short MMAs, the pooled epilogue is the long pole)
+  d->groups = (pair_pool && tc_tune.stem_groups != 2) ? 4 : 2;
+  const size_t groups = (size_t)d->groups;
   auto layout = [&](size_t stage_sz, int* out_stages, int* out_nslots, size_t* out_staging) -> bool {
     const int want_stages = (stage_sz >= 48 * 1024) ? 3 : 4;
     int stages = 0, nslots = 0;
     size_t staging = 0;
     for (int ns = 4; ns >= 1; --ns) {
-      staging = slot * ns * 2;
-      if (staging + resident + 2 * stage_sz > 214 * 1024) continue;
+      staging = slot * ns * groups;
+      if (staging + resident + 2 * stage_sz > (214 - 8 * (groups - 2) / 2) * 1024) continue;   // s_par grows with the groups
       stages = (int)((214 * 1024 - staging - resident) / stage_sz);
       nslots = ns;
       if (stages >= want_stages) break;
@@ -1117,14 +1126,15 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   return CSE_OK;
 }
 
-template <int KC, int EC>
+template <int KC, int EC, int NG = 2>
 static int launch_tc_t(const ConvTcDesc& d, const ConvTcArgs& args, int grid, size_t smem_bytes, cudaStream_t st) {
   static PerDeviceOnce once;
   if (once.need()) {
-    CSE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));
+    CSE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, EC, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (217 - 8 * (NG - 2) / 2) * 1024));
     once.mark();
   }
-  conv_tc_kernel<KC, EC><<<grid, TC_THREADS, smem_bytes, st>>>(d.tmap_a, d.tmap_b, d.tmap_o0, d.tmap_o1, d.tmap_o2, args);
+  conv_tc_kernel<KC, EC, NG><<<grid, 64 + 128 * NG, smem_bytes, st>>>(d.tmap_a, d.tmap_b, d.tmap_o0, d.tmap_o1, d.tmap_o2, args);
   CSE_CUDA(cudaGetLastError());
   return CSE_OK;
 }
@@ -1138,14 +1148,11 @@ static int launch_tc_kc(const ConvTcDesc& d, const ConvTcArgs& a, int grid, size
   }
 }
 
-// Tile-count thresholds of the shared-B / twin modes; -1 = the built-in default.  Set through cse_tune() (tests force
-// the modes on small shapes); never read from the environment on the launch path.
-struct TcTune { int bshare_min_tiles = -1, twin_min_tiles = -1, pair_min_tiles = -1; };
-static TcTune tc_tune;
 int conv_tc_tune(const char* key, int value) {
   if (!strcmp(key, "bshare_min_tiles")) { tc_tune.bshare_min_tiles = value; return CSE_OK; }
   if (!strcmp(key, "twin_min_tiles")) { tc_tune.twin_min_tiles = value; return CSE_OK; }
   if (!strcmp(key, "pair_min_tiles")) { tc_tune.pair_min_tiles = value; return CSE_OK; }
+  if (!strcmp(key, "stem_groups")) { tc_tune.stem_groups = value; return CSE_OK; }     // read at plan finalize
   return CSE_ERR_INVALID;
 }
 
@@ -1186,6 +1193,7 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   size_t smem_bytes = d.smem_bytes;
   a.twin = 0;
   a.bshare = 0; a.b_slots = 2; a.b_stage = 0; a.nbuf = 2; a.acc_cols = 256;
+  if (d.groups == 4) { a.nbuf = 4; a.acc_cols = 128; }        // pair-packed stem: four 128-column accumulators
   const int bs_min = tc_tune.bshare_min_tiles >= 0 ? tc_tune.bshare_min_tiles : 8 * sm_count;
   if (d.bs_group && bs_min > 0 && a.num_tiles >= bs_min) {
     a.bshare = d.bs_group; a.b_slots = d.bs_slots;
@@ -1206,12 +1214,16 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   }
   {
     const int radix[4] = {a.n_tiles_n, a.tiles_w, a.tiles_h, a.tiles_d};
-    for (int which = 0; which < 3; ++which) {
-      int v = grid * (which == 2 ? (a.bshare ? a.bshare : 1) : which + 1);
-      int* st = which == 2 ? a.stepG : (which ? a.step2 : a.step1);
+    for (int which = 0; which < 4; ++which) {
+      int v = grid * (which == 3 ? d.groups : (which == 2 ? (a.bshare ? a.bshare : 1) : which + 1));
+      int* st = which == 3 ? a.stepE : (which == 2 ? a.stepG : (which ? a.step2 : a.step1));
       for (int i = 0; i < 4; ++i) { st[i] = v % radix[i]; v /= radix[i]; }
       st[4] = v;
     }
+  }
+  if (d.groups == 4) {
+    CSE_REQUIRE(d.pair_pool && d.kc == 16 && d.ec == 64, "conv_tc: four epilogue groups are only built for the pair-packed stem");
+    return launch_tc_t<16, 64, 4>(d, a, grid, smem_bytes, st);
   }
   switch (d.kc) {
     case 64: return launch_tc_kc<64>(d, a, grid, smem_bytes, st);
