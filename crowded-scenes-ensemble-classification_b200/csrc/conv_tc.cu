@@ -101,8 +101,8 @@ struct TileIter {
 
 // KC = channels per pipeline stage (16 -> SWIZZLE_32B, 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B)
 // EC = output channels per epilogue chunk = TMA-store box width (16/32/64, same swizzle family)
-// NG = epilogue groups of 4 warps (one TMEM accumulator each): 2 everywhere, 4 for the pair-packed C3D stem whose tile
-// is 9 short MMAs (576 cycles) against a ~2000-cycle pooled epilogue - four groups drain four accumulators in turn.
+// NG = epilogue groups of 4 warps (one TMEM accumulator each): 2 everywhere; a 4-group instantiation exists for the
+// pair-packed C3D stem (four 128-column accumulators drained in turn; opt-in, see conv_tc_build).
 template <int KC, int EC, int NG = 2>
 __global__ void __launch_bounds__(64 + 128 * NG, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -1027,8 +1027,10 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   // keeps >= 4 stages (3 for the widest tiles); a TMA store only releases its slot once it has
   // read it, so more slots = more stores in flight
   d->slot_bytes = (uint32_t)slot;
-  // epilogue groups: 2; the pair-packed C3D stem runs 4 (tile = 9 short MMAs, the pooled epilogue is the long pole)
-  d->groups = (pair_pool && tc_tune.stem_groups != 2) ? 4 : 2;
+  // epilogue groups: 2.  The pair-packed C3D stem can run 4 (cse_tune("stem_groups", 4)); measured no gain (conv1 5.99
+  // vs 6.00 ms per 4 x 256 clips): the tile's 128 x 128 fp32 accumulator (64 KB) leaves TMEM at ~64 B/clk = 1024 cycles
+  // against 576 cycles of MMA, and MMA accumulation and tcgen05.ld share the TMEM port - conv1 is TMEM-drain bound.
+  d->groups = (pair_pool && tc_tune.stem_groups == 4) ? 4 : 2;
   const size_t groups = (size_t)d->groups;
   auto layout = [&](size_t stage_sz, int* out_stages, int* out_nslots, size_t* out_staging) -> bool {
     const int want_stages = (stage_sz >= 48 * 1024) ? 3 : 4;
