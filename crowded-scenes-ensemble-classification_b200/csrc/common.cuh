@@ -99,6 +99,10 @@ struct ConvTcDesc {            // built once at plan finalize
   int out_split, out_split2;   // fused sibling 1x1 convs: columns >= split go to out1, columns >= split2 to out2
   int pair_pool;               // pair-packed stem with the (1,2,2) max-pool done in registers
   int groups;                  // epilogue groups of 4 warps (2; 4 for the pair-packed stem)
+  int ksplit;                  // split-K factor (1 = none); partial = fp32 [ksplit][part_rows][part_ld] in the workspace
+  float* partial;
+  int part_ld;
+  long long part_rows;
   int bs_group;                // shared-B h-halo layout: tiles per weight stage (0 = not available)
   int bs_stages, bs_nslots, bs_slots;
   uint32_t bs_b_region, bs_b_stage, bs_stage_region;
@@ -127,7 +131,8 @@ struct ConvTcDesc {            // built once at plan finalize
 };
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
                   int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
-                  const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_split2, void* out2, int out2_ld);
+                  const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_split2, void* out2, int out2_ld,
+                  int ksplit = 1, void* partial = nullptr, size_t partial_bytes = 0);
 int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);
 int launch_conv_tc_pair(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count, cudaStream_t st);   // conv_tc2.cu
 

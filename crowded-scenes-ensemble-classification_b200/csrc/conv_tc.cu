@@ -73,6 +73,14 @@ struct ConvTcArgs {
   int pair_pool;                   // pair-packed stem: GEMM row = 2 output pixels (N = 2*Cout), (1,2,2) max-pool in registers
   int step1[5], step2[5];          // gridDim.x and 2*gridDim.x as mixed-radix digits (nt, tw, th, td, tn)
   int stepE[5];                    // (epilogue groups)*gridDim.x: the stride of one epilogue group's tile walk
+  // split-K (generic mode, layers with fewer tiles than SMs): the N-tile digit of the tile walk carries the K split too
+  // (n_tiles_n = real N tiles x ksplit, nt = digit / ksplit, split = digit % ksplit); every split accumulates
+  // ksteps_per k-steps and stores its fp32 accumulator tile to partial[split][m_row][col]; splitk_reduce_kernel sums the
+  // splits in order and applies the epilogue
+  int ksplit, ksteps_per;
+  float* partial;
+  int part_ld;
+  long long part_rows;
   Epilogue ep;
 };
 
@@ -281,6 +289,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         continue;
       }
+      if (a.ksplit > 1) {
+        // this work item = k-steps [k0, k1) of the tile's K loop (flattened tap-major, chunk-minor like the weights)
+        const int bcol_s = (nt / a.ksplit) * a.bn;
+        const int k0 = (nt % a.ksplit) * a.ksteps_per, k1 = min(k0 + a.ksteps_per, ksteps);
+        for (int kidx = k0; kidx < k1; ++kidx) {
+          const int ch = kidx % a.kchunks;
+          int tap = kidx / a.kchunks;
+          const int fw = tap % a.kw; tap /= a.kw;
+          const int fh = tap % a.kh;
+          const int fd = tap / a.kh;
+          mbar_wait(bar_base + BAR_EMPTY + 8u * stage, phase ^ 1u);
+          const uint32_t fb = bar_base + 8u * stage;
+          mbar_expect_tx_p(leader, fb, a.a_bytes + a.b_bytes);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          tma_load_5d(leader, sa, &tmap_a, fb, ch * KC, iw0 + fw, ih0 + fh, id0 + fd, n0);
+          tma_load_2d(leader, sa + A_STAGE, &tmap_b, fb, kidx * KC, bcol_s);
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+        continue;
+      }
       int kcoord = 0;
       for (int fd = 0; fd < a.kd; ++fd)
         for (int fh = 0; fh < a.kh; ++fh)
@@ -438,13 +466,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         continue;
       }
-      for (int ks = 0; ks < ksteps; ++ks) {
+      int nks = ksteps;
+      if (a.ksplit > 1) {                       // split-K: this item's share of the K loop (N-tile digit % ksplit)
+        const int k0 = ((tile % a.n_tiles_n) % a.ksplit) * a.ksteps_per;
+        nks = min(a.ksteps_per, ksteps - k0);
+      }
+      for (int ks = 0; ks < nks; ++ks) {
         mbar_wait(bar_base + 8u * stage, phase);                           // full[stage]
         tc_fence_after();
         const uint32_t sa = smem_base + stage * stage_bytes;
         tc_mma_k<KC / 16>(leader, d_tmem, dlo(sa), dlo(sa + A_STAGE), desc_hi32, idesc, ks > 0 ? 1u : 0u);
         tc_commit(leader, bar_base + BAR_EMPTY + 8u * stage);                    // frees the smem stage when the MMAs retire
-        if (ks == ksteps - 1) tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * buf);   // tmem_full[buf]
+        if (ks == nks - 1) tc_commit(leader, bar_base + BAR_TMEM_FULL + 8u * buf);   // tmem_full[buf]
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -550,6 +583,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(bar_base + BAR_TMEM_FULL + 8u * buf, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + buf_col;
+      if (a.ksplit > 1) {
+        // split-K: raw fp32 accumulator rows -> partial[split][m_tile * 128 + row][N tile columns]
+        const int split = nt % a.ksplit, ntile = nt / a.ksplit;
+        const long long m_tile = (((long long)ti.tn * a.tiles_d + ti.td) * a.tiles_h + ti.th) * a.tiles_w + ti.tw;
+        float* dst = a.partial + ((long long)split * a.part_rows + m_tile * TC_BM + row) * a.part_ld + ntile * a.bn;
+        for (int c0 = 0; c0 < a.bn; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(t_row + (uint32_t)c0, r);
+          tc_wait_ld();
+          if (c0 + 16 >= a.bn) {
+            tc_fence_before();
+            mbar_arrive(bar_base + BAR_TMEM_EMPTY + 8u * buf);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(dst + c0 + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        }
+        continue;
+      }
       if (EC == 64 && a.pair_pool) {
         // Pair-packed stem + MaxPooling3D (1,2,2): row = (h, pixel pair), columns [0,64) = left pixel,
         // [64,128) = right pixel.  max over the pair in registers, + bias, (ReLU) -> bf16, max with the
@@ -799,6 +851,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+// Split-K tail: out[m, c] = epilogue(sum over splits, in order, of partial[split][m][c]).  One thread per (output row, 8
+// columns); rows are decoded back to NDHWC pixels through the brick tiling of the main kernel.
+struct SplitKReduceArgs {
+  const float* partial;
+  int ksplit, part_ld;
+  long long part_rows;
+  int Do, Ho, Wo, Co;
+  int b_n, b_d, b_h, b_w, tiles_d, tiles_h, tiles_w, n_batch;
+  int out_ld;
+  Epilogue ep;
+};
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(SplitKReduceArgs a) {
+  const int cv = (a.Co + 7) / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.part_rows * cv) return;
+  const int c0 = (int)(idx % cv) * 8;
+  const long long m = idx / cv;
+  const int row = (int)(m % TC_BM);
+  long long mt = m / TC_BM;
+  const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
+  const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
+  const int td = (int)(mt % a.tiles_d);
+  const int tn = (int)(mt / a.tiles_d);
+  const int rw = row % a.b_w, rh = (row / a.b_w) % a.b_h, rd = (row / (a.b_w * a.b_h)) % a.b_d, rn = row / (a.b_w * a.b_h * a.b_d);
+  const int ow = tw * a.b_w + rw, oh = th * a.b_h + rh, od = td * a.b_d + rd, on = tn * a.b_n + rn;
+  if (rn >= a.b_n || ow >= a.Wo || oh >= a.Ho || od >= a.Do || on >= a.n_batch) return;
+  float y[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = 0.f;
+  const float* p = a.partial + m * a.part_ld + c0;
+  for (int sidx = 0; sidx < a.ksplit; ++sidx, p += a.part_rows * a.part_ld) {
+    const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+    y[0] += v0.x; y[1] += v0.y; y[2] += v0.z; y[3] += v0.w; y[4] += v1.x; y[5] += v1.y; y[6] += v1.z; y[7] += v1.w;
+  }
+  const long long pix = (((long long)on * a.Do + od) * a.Ho + oh) * a.Wo + ow;
+  const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(a.ep.res);
+  __align__(16) __nv_bfloat16 o0[8], o1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = min(c0 + j, a.Co - 1);
+    float v = a.ep.scale0 ? fmaf(y[j], __ldg(a.ep.scale0 + c), a.ep.shift0 ? __ldg(a.ep.shift0 + c) : 0.f)
+                          : y[j] + (a.ep.shift0 ? __ldg(a.ep.shift0 + c) : 0.f);
+    if (res) v += __bfloat162float(res[pix * a.ep.res_ld + c]);
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    if (a.ep.relu0) h = __hmax(h, __float2bfloat16_rn(0.f));
+    o0[j] = h;
+    if (a.ep.out1) {
+      __nv_bfloat16 h1 = __float2bfloat16_rn(fmaf(v, a.ep.scale1 ? __ldg(a.ep.scale1 + c) : 1.f, a.ep.shift1 ? __ldg(a.ep.shift1 + c) : 0.f));
+      if (a.ep.relu1) h1 = __hmax(h1, __float2bfloat16_rn(0.f));
+      o1[j] = h1;
+    }
+  }
+  // Co is a multiple of 8 (conv_tc_build): whole 16-byte vectors
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.ep.out0) + pix * a.out_ld + c0) = *reinterpret_cast<const uint4*>(o0);
+  if (a.ep.out1)
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.ep.out1) + pix * a.ep.out1_ld + c0) = *reinterpret_cast<const uint4*>(o1);
+}
+
 // ----------------------------------------------------------------------------- host side
 // Tile-count thresholds of the shared-B / twin / CTA-pair modes and the epilogue groups of the pair-packed stem; -1 = the
 // built-in default.  Set through cse_tune() (tests force the modes on small shapes); never read from the environment on
@@ -853,7 +965,8 @@ static int encode_out_map(PFN_encodeTiled enc, CUtensorMap* m, void* out, int ld
 
 int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out0, void* out1, int out1_ld,
                   int max_batch, const WinGeom& g, int kc, int bn, const int brick[4], int halo, const int pool[3],
-                  const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_split2, void* out2, int out2_ld) {
+                  const int pool_dims[3], int pool_zero, int pair_pool, int out_split, int out_split2, void* out2, int out2_ld,
+                  int ksplit, void* partial, size_t partial_bytes) {
   CSE_REQUIRE(kc == 16 || kc == 32 || kc == 64, "conv_tc: kc=%d must be 16/32/64", kc);
   CSE_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "conv_tc: bn=%d must be a multiple of 16 in [16,256]", bn);
   CSE_REQUIRE(g.Ci % 8 == 0 && g.in_ld % 8 == 0, "conv_tc: Cin=%d / ld=%d must be multiples of 8", g.Ci, g.in_ld);
@@ -870,6 +983,7 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   if (!enc) return CSE_ERR_CUDA;
 
   d->g = g; d->kc = kc; d->bn = bn; d->max_batch = max_batch;
+  d->ksplit = 1; d->partial = nullptr;
   d->n_tiles_n = ceil_div(g.Co, bn);
   d->kchunks = ceil_div(g.Ci, kc);
   for (int i = 0; i < 4; ++i) d->brick[i] = brick[i];
@@ -1091,6 +1205,21 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
         d->bs_smem_bytes = a_stage * st + nb_ * b_stage + stg + 1024;
       }
   }
+  if (ksplit > 1) {
+    // split-K: generic mode only, plain tensors (no fused pool / sibling split / pair-packed stem)
+    const int ksteps = taps * d->kchunks;
+    CSE_REQUIRE(halo == 0 && !pooled && out_split == 0 && !pair_pool && ksplit <= 16 && ksplit <= ksteps && partial != nullptr &&
+                    ((uintptr_t)partial % 16) == 0,
+                "conv_tc: split-K (%d) needs the generic mode, plain outputs and a 16-byte aligned fp32 partial buffer", ksplit);
+    const long long m_tiles = (long long)ceil_div(max_batch, brick[0]) * d->tiles_d * d->tiles_h * d->tiles_w;
+    d->part_rows = m_tiles * TC_BM;
+    d->part_ld = d->n_tiles_n * bn;
+    CSE_REQUIRE((size_t)ksplit * d->part_rows * d->part_ld * sizeof(float) <= partial_bytes,
+                "conv_tc: split-K partial buffer of %zu bytes is too small", partial_bytes);
+    d->ksplit = ksplit;
+    d->partial = reinterpret_cast<float*>(partial);
+    d->twin_ok = 0;
+  }
   // CTA-pair layout (conv_tc2.cu): h-halo mode, single N tile, no pool / second output / split: every CTA of a
   // 2-CTA cluster stages its own A box and HALF of the weight taps (bn/2 rows each)
   d->pair_ok = 0;
@@ -1179,8 +1308,11 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
   a.tiles_d = d.tiles_d; a.tiles_h = d.tiles_h; a.tiles_w = d.tiles_w;
   a.n_batch = n;
   const long long m_tiles = (long long)ceil_div(n, d.brick[0]) * d.tiles_d * d.tiles_h * d.tiles_w;
-  CSE_REQUIRE(m_tiles * d.n_tiles_n < (1LL << 31), "conv_tc: too many tiles");
-  a.num_tiles = (int)(m_tiles * d.n_tiles_n);
+  CSE_REQUIRE(m_tiles * d.n_tiles_n * d.ksplit < (1LL << 31), "conv_tc: too many tiles");
+  a.ksplit = d.ksplit; a.partial = d.partial; a.part_ld = d.part_ld; a.part_rows = d.part_rows;
+  a.ksteps_per = ceil_div(g.kd * g.kh * g.kw * d.kchunks, d.ksplit);
+  if (d.ksplit > 1) a.n_tiles_n = d.n_tiles_n * d.ksplit;        // the N-tile digit of the tile walk carries the split
+  a.num_tiles = (int)(m_tiles * a.n_tiles_n);
   a.stages = d.stages;
   a.a_bytes = d.a_bytes; a.b_bytes = d.b_bytes;
   a.a_stage = d.a_stage; a.stage_bytes = d.stage_bytes;
@@ -1227,11 +1359,26 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
     CSE_REQUIRE(d.pair_pool && d.kc == 16 && d.ec == 64, "conv_tc: four epilogue groups are only built for the pair-packed stem");
     return launch_tc_t<16, 64, 4>(d, a, grid, smem_bytes, st);
   }
+  int rc;
   switch (d.kc) {
-    case 64: return launch_tc_kc<64>(d, a, grid, smem_bytes, st);
-    case 32: return launch_tc_kc<32>(d, a, grid, smem_bytes, st);
-    default: return launch_tc_kc<16>(d, a, grid, smem_bytes, st);
+    case 64: rc = launch_tc_kc<64>(d, a, grid, smem_bytes, st); break;
+    case 32: rc = launch_tc_kc<32>(d, a, grid, smem_bytes, st); break;
+    default: rc = launch_tc_kc<16>(d, a, grid, smem_bytes, st); break;
   }
+  if (rc || d.ksplit <= 1) return rc;
+  SplitKReduceArgs r;
+  r.partial = d.partial; r.ksplit = d.ksplit; r.part_ld = d.part_ld; r.part_rows = d.part_rows;
+  r.Do = g.Do; r.Ho = g.Ho; r.Wo = g.Wo; r.Co = g.Co;
+  r.b_n = d.brick[0]; r.b_d = d.brick[1]; r.b_h = d.brick[2]; r.b_w = d.brick[3];
+  r.tiles_d = d.tiles_d; r.tiles_h = d.tiles_h; r.tiles_w = d.tiles_w; r.n_batch = n;
+  r.out_ld = g.out_ld; r.ep = ep;
+  const long long rows = m_tiles * TC_BM;           // rows of the tiles this launch ran (n <= max_batch)
+  r.part_rows = d.part_rows;
+  const long long items = rows * ((g.Co + 7) / 8);
+  SplitKReduceArgs rr = r;
+  splitk_reduce_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(rr);
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
 }
 
 }  // namespace cse

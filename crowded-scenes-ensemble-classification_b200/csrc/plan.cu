@@ -214,10 +214,16 @@ int cse_plan_finalize(cse_plan* p, void* d_workspace, size_t workspace_bytes, co
         const long long ktot = (long long)g.kd * g.kh * g.kw * kchunks * o.kc;   // same element count in every packing
         const long long rows = (long long)ceil_div(g.Co, o.bn > 0 ? o.bn : 16) * o.bn;
         if ((rc = check_span(p, o.w_off, ktot * rows, CSE_BF16, "tc weights", true))) return rc;
+        if (o.ksplit > 1) {
+          CSE_REQUIRE(o.part_off >= 0 && o.part_bytes > 0, "op %zu: split-K without a partial buffer", i);
+          if ((rc = check_span(p, o.part_off, o.part_bytes, CSE_U8, "split-K partials", false))) return rc;
+        }
         rc = conv_tc_build(&po.tc, p->ws + o.in0_off, p->wts + o.w_off, p->ws + o.out0_off,
                            o.out1_off >= 0 ? p->ws + o.out1_off : nullptr, o.out1_ld, nb, g, o.kc, o.bn, o.brick,
                            o.tc_halo, o.pool_k, o.pool_dims, o.pool_zero, o.tc_pair_pool, o.out_split, o.out_split2,
-                           o.out_split2 > 0 ? p->ws + o.out2_off : nullptr, o.out2_ld);
+                           o.out_split2 > 0 ? p->ws + o.out2_off : nullptr, o.out2_ld,
+                           o.ksplit > 1 ? o.ksplit : 1, (o.ksplit > 1 && o.part_off >= 0) ? p->ws + o.part_off : nullptr,
+                           o.ksplit > 1 ? (size_t)o.part_bytes : 0);
         if (rc) return rc;
         po.has_tc = true;
       } else {

@@ -96,6 +96,8 @@ class DevOp:
     brick: Tuple[int, int, int, int] = (0, 0, 0, 0)
     halo: int = 0
     pair_pool: int = 0
+    ksplit: int = 1               # TCGEN05 split-K factor
+    part: Optional[Buf] = None    # fp32 partial tiles of a split-K conv (live during that op only)
     src_dtype: int = 2            # PREPROCESS: dtype of the external clip (rt.U8 frames / rt.F32 on-the-fly flow)
     out_split: int = 0            # fused sibling 1x1x1 convs: columns >= out_split go to out1, >= out_split2 to out2
     out_split2: int = 0
@@ -139,7 +141,7 @@ class Plan:
                 s.out_dims[:] = (1, 1, 1, op.softmax_C)
                 s.in_dtype = s.out_dtype = rt.F32
                 s.in0_off, s.out0_off = i0.byte_off(), o0.byte_off()
-                s.in1_off = s.out1_off = s.w_off = -1
+                s.in1_off = s.out1_off = s.w_off = s.part_off = -1
                 s.scale0_off = s.shift0_off = s.scale1_off = s.shift1_off = -1
                 out.append(s)
                 continue
@@ -186,6 +188,8 @@ class Plan:
             s.shift0_off = bo[op.shift0] if op.shift0 >= 0 else -1
             s.scale1_off = bo[op.scale1] if op.scale1 >= 0 else -1
             s.shift1_off = bo[op.shift1] if op.shift1 >= 0 else -1
+            s.ksplit, s.part_off, s.part_bytes = op.ksplit, (op.part.offset if op.part is not None else -1), \
+                (op.part.nbytes if op.part is not None else 0)
             out.append(s)
         return out
 
@@ -355,8 +359,9 @@ class Lowerer:
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
                  stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True,
                  balance_n: bool = True, pair_pool: bool = True, persist_input: bool = False,
-                 fuse_siblings: bool = True, s2d_depth: bool = True, input_dtypes=None):
+                 fuse_siblings: bool = True, s2d_depth: bool = True, input_dtypes=None, split_k: bool = True):
         self.s2d_depth = s2d_depth
+        self.split_k = split_k
         # dtype of every external input: "u8" (decoded frames - the default) or "f32" (the dense flow of the
         # FarneBack_onTheFly TwoStream variant, train.py:294-332, evaluate_ensemble.py:1365-1386)
         self.input_dtypes = tuple(input_dtypes) if input_dtypes else tuple("u8" for _ in g.inputs)
@@ -454,6 +459,8 @@ class Lowerer:
                 if r is not None:
                     r.buf.first = min(r.buf.first, idx)
                     r.buf.last = max(r.buf.last, idx)
+            if op.part is not None:
+                op.part.first = op.part.last = idx
         for r in (logits, probs):
             if r is not None:
                 r.buf.last = len(self.ops) + 1
@@ -621,6 +628,16 @@ class Lowerer:
             else:
                 op.brick = gen_brick
                 op.w_blob = self.blob(pack_tc_weights(kernel, kc, bn, n_tiles))
+                # split-K: a layer with far fewer tiles than SMs (small batches: C3D conv5a/5b at batch 8; the Dense
+                # layers, whose M is the batch) spreads the K loop of every tile over several CTAs; the fp32 partial
+                # tiles are summed in a fixed order by a second kernel.  Decided here, from max_batch - never from the
+                # batch actually run - so one member gives bit-identical results for every batch size.
+                ks = 1 if pool else self._split_k_factor(ci, kernel, out_dims)
+                if ks >= 2:
+                    op.ksplit = ks
+                    nbytes = ks * m_tiles * 128 * n_tiles * bn * 4
+                    op.part = Buf(name + ":splitk", _round_up(nbytes, ALIGN))
+                    self.bufs.append(op.part)
         else:
             op.engine = rt.ENGINE_DIRECT
             kflat = kernel.reshape(-1, co)
@@ -636,6 +653,22 @@ class Lowerer:
             op.scale1, op.shift1, op.relu1 = self.fblob(sc1), self.fblob(sh1), int(relu1)
         self.emit(op)
         return op
+
+    def _split_k_factor(self, ci: int, kernel, out_dims, mult=(1, 1, 1)) -> int:
+        """Split-K factor the generic tcgen05 path would use for this conv (1 = no split); see _conv_like."""
+        if not (self.split_k and self.use_tc):
+            return 1
+        kc = choose_kc(ci)
+        brick = choose_brick(self.nb, *out_dims, mult=mult)
+        m_tiles = (-(-self.nb // brick[0]) * -(-out_dims[0] // brick[1]) * -(-out_dims[1] // brick[2])
+                   * -(-out_dims[2] // brick[3]))
+        bn, n_tiles = choose_bn(kernel.shape[-1], m_tiles if self.balance_n else 0)
+        ksteps = kernel.shape[0] * kernel.shape[1] * kernel.shape[2] * -(-ci // kc)
+        tiles = m_tiles * n_tiles
+        if tiles * 2 > SM_COUNT or ksteps < 16:
+            return 1
+        ks = min(SM_COUNT // tiles, ksteps // 8, 8)
+        return ks if ks >= 2 else 1
 
     def _tc_ok(self, x: TRef, co: int, s, out_dtype: int, residual: Optional[TRef]) -> bool:
         return (self.use_tc and x.dtype == rt.BF16 and out_dtype == rt.BF16 and x.C % 8 == 0 and x.ld % 8 == 0
@@ -781,6 +814,8 @@ class Lowerer:
             return
         if x.wpitch or x.unroll_w or self._tc_ok(x, kernel.shape[-1], node.attrs["s"], self.act, None):
             fp = self._fusable_pool(final, out_dims)
+            if fp is not None and not (x.wpitch or x.unroll_w) and self._split_k_factor(x.C, kernel, out_dims) > 1:
+                fp = None       # a layer this small gains more from split-K than from the fused pool (tiny stand-alone pool)
             if fp is not None and final not in self.place:
                 pool = fp[:3]
                 layers = layers + fp[3]

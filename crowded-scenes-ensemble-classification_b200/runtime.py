@@ -43,6 +43,7 @@ class CseOp(C.Structure):
         ("in0_off", C.c_int64), ("in1_off", C.c_int64), ("out0_off", C.c_int64), ("out1_off", C.c_int64), ("out2_off", C.c_int64),
         ("w_off", C.c_int64), ("scale0_off", C.c_int64), ("shift0_off", C.c_int64),
         ("scale1_off", C.c_int64), ("shift1_off", C.c_int64),
+        ("part_off", C.c_int64), ("part_bytes", C.c_int64), ("ksplit", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

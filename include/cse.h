@@ -113,6 +113,12 @@ typedef struct cse_op {
   int64_t w_off;             /* weight-arena byte offsets (-1 = none) */
   int64_t scale0_off, shift0_off;   /* fp32 [Cout]: y = acc*scale0 + shift0 (+ in1); out0 = relu0?(y) */
   int64_t scale1_off, shift1_off;   /* fp32 [Cout]: out1 = relu1?(y*scale1 + shift1) */
+  int64_t part_off;          /* TCGEN05 split-K: workspace byte offset of the fp32 partial tiles (-1 = none) */
+  int64_t part_bytes;        /* size of that buffer */
+  int32_t ksplit;            /* TCGEN05: split the K loop of every tile over `ksplit` CTAs (layers with fewer tiles than SMs:
+                                small batches, the 1-2 row Dense layers); 0 / 1 = no split.  The splits are summed in order
+                                by a second kernel, so results do not depend on scheduling */
+  int32_t reserved0;
 } cse_op;
 
 typedef struct cse_plan cse_plan;   /* opaque: one ensemble member's forward pass on one GPU */

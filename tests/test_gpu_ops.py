@@ -392,6 +392,44 @@ def test_conv_tcgen05_stem_cta_pair(dhw, c, cout, nb, depth):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("dhw,cin,cout,k,nb,res", [((2, 7, 7), 512, 512, (3, 3, 3), 2, False), ((1, 4, 4), 256, 512, (3, 3, 3), 3, True),
+                                                   ((1, 1, 1), 4096, 4096, (1, 1, 1), 5, False), ((2, 7, 7), 96, 208, (3, 3, 3), 1, True)])
+def test_conv_tcgen05_split_k(dhw, cin, cout, k, nb, res):
+    """Split-K (layers with fewer tiles than SMs: C3D conv5 at small batches, the Dense layers, R3D stages 3-4): every
+    tile's K loop is spread over several CTAs, fp32 partial tiles are summed in order by splitk_reduce_kernel, which
+    also applies BN / ReLU / the residual add and the second output.  Against the oracle, and against the unsplit
+    lowering (same products, different fp32 summation order)."""
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, cin, (1, 1, 1), (1, 1, 1), "same", True, "relu", name="pre")
+        y = g.conv3d(x, cout, k, (1, 1, 1), "same", True, None, name="c")
+        if res:
+            sc = g.conv3d(x, cout, (1, 1, 1), (1, 1, 1), "same", True, None, name="sc")
+            y = g.add_([sc, y], name="add")
+        y = g.bn(y, scale=True, name="b")
+        g.relu(y, name="r")
+    outs = {}
+    for split in (True, False):
+        g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * 3, mean=[128.0] * 3, split_k=split)
+        op = [o for o in m.plan.ops if o.name == "c"][0]
+        assert op.engine == rt.ENGINE_TCGEN05 and (op.ksplit > 1) == split, (op.ksplit, op.bn, op.brick)
+        xs = clips(4, nb, dhw + (3,))
+        run(m, [xs])
+        outs[split] = m.read_tensor(m.plan.tensors["r"], nb)
+        if split:
+            xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], nb), dtype=T64)
+            kern, bias = w["c"]
+            y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (1, 1, 1), "same")
+            if res:
+                ks, bs = w["sc"]
+                y = y + bf16_round(O.conv3d(xin, bf16_round(ks), torch.as_tensor(bs, dtype=T64), (1, 1, 1), "same").numpy())
+            y = O.relu(O.batchnorm(y, *[torch.as_tensor(a, dtype=T64) for a in w["b"]])).numpy()
+            err = np.abs(outs[True] - y).max() / max(np.abs(y).max(), 1e-6)
+            assert err <= 2.0 ** -7, "rel err %g (ksplit=%d bn=%d brick=%s)" % (err, op.ksplit, op.bn, op.brick)
+        del m
+    assert np.abs(outs[True] - outs[False]).max() <= 2.0 ** -7 * np.abs(outs[False]).max()
+
+
 PAIR_POOL = [((4, 16, 16), 3, True), ((3, 12, 40), 3, True), ((5, 8, 24), 2, False), ((2, 34, 18), 3, True),
              ((3, 16, 112), 4, True)]
 
