@@ -1022,6 +1022,11 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
     CSE_REQUIRE(g.kw == 1 && g.sh == 1 && g.sw == 1 && brick[0] == 1 && brick[1] == 1 && brick[3] % 8 == 0 &&
                     g.kh * bn <= 256,
                 "conv_tc: h-halo mode needs kw=1, stride 1 in H/W, brick (1,1,h,w%%8==0), kh*bn<=256");
+  } else if (halo == 3) {
+    // h-halo with kw taps, CTA-pair kernel only (conv_tc2.cu): one stage per (fd, fw, chunk), the haloed box shifted by fw
+    CSE_REQUIRE(g.sh == 1 && g.sw == 1 && brick[0] == 1 && brick[1] == 1 && brick[3] % 8 == 0 && d->n_tiles_n == 1 &&
+                    bn <= 128 && !(pool && pool[0] > 0) && out_split == 0 && !pair_pool,
+                "conv_tc: pair h-halo mode needs stride 1 in H/W, brick (1,1,h,w%%8==0), a single N tile <= 128, no pool / split");
   } else {
     CSE_REQUIRE(halo == 0, "conv_tc: unknown halo mode %d", halo);
   }
@@ -1038,7 +1043,7 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
     cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(brick[3] * g.sw), (cuuint32_t)(brick[2] * g.sh),
                          (cuuint32_t)(brick[1] * g.sd), (cuuint32_t)brick[0]};
     if (halo == 1) { box[2] = (cuuint32_t)(brick[2] + g.kh - 1); box[3] = (cuuint32_t)(brick[1] + g.kd - 1); }
-    if (halo == 2) box[2] = (cuuint32_t)(brick[2] + g.kh - 1);
+    if (halo == 2 || halo == 3) box[2] = (cuuint32_t)(brick[2] + g.kh - 1);
     cuuint32_t estr[5] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, (cuuint32_t)g.sd, 1};
     CUresult r = enc(&d->tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1049,8 +1054,8 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
       return CSE_ERR_CUDA;
     }
   }
-  // B: [Cout_pad][Ktot] bf16, K-major
-  {
+  // B: [Cout_pad][Ktot] bf16, K-major (the pair-only mode loads B through tmap_bh, built below)
+  if (halo != 3) {
     // halo mode packs B as [n_tile][tap][bn][kc]: one box = the kh taps of one fd plane
     // h-halo mode packs B as [n_tile][fd][chunk][fh][bn][kc]: one box = the kh taps of one (fd, chunk)
     const long long ktot = halo ? kc : (long long)taps * d->kchunks * kc;
@@ -1113,7 +1118,7 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   size_t b_stage = (((size_t)bn * kc * 2) + 1023) & ~(size_t)1023;
   d->a_bytes = (uint32_t)(rows * kc * 2);
   d->b_bytes = (uint32_t)(bn * kc * 2);
-  if (halo == 2) {
+  if (halo == 2 || halo == 3) {
     const size_t halo_rows = (size_t)brick[3] * (brick[2] + g.kh - 1);
     d->a_bytes = (uint32_t)(halo_rows * kc * 2);
     d->b_bytes = (uint32_t)((size_t)g.kh * bn * kc * 2);
@@ -1163,7 +1168,8 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   };
   int stages = 0;
   size_t staging = 0;
-  CSE_REQUIRE(layout(stage, &stages, &d->nslots, &staging), "conv_tc: tile too large for shared memory");
+  const bool fits = layout(stage, &stages, &d->nslots, &staging);
+  CSE_REQUIRE(fits || halo == 3, "conv_tc: tile too large for shared memory");
   d->stages = stages;
   d->b_region = (uint32_t)(stage * stages);
   d->stage_region = (uint32_t)(stage * stages + resident);
@@ -1223,7 +1229,7 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   // CTA-pair layout (conv_tc2.cu): h-halo mode, single N tile, no pool / second output / split: every CTA of a
   // 2-CTA cluster stages its own A box and HALF of the weight taps (bn/2 rows each)
   d->pair_ok = 0;
-  if (halo == 2 && d->n_tiles_n == 1 && bn <= 128 && bn % 16 == 0 && (kc == 64 || kc == 32) && !pooled && out1 == nullptr &&
+  if ((halo == 2 || halo == 3) && d->n_tiles_n == 1 && bn <= 128 && bn % 16 == 0 && (kc == 64 || kc == 32) && !pooled &&
       out_split == 0 && !pair_pool && brick[0] == 1 && brick[1] == 1 &&
       (((size_t)(bn / 2) * kc * 2) % (kc == 64 ? 1024 : 512)) == 0) {
     cuuint64_t dims[2] = {(cuuint64_t)kc, (cuuint64_t)bn * taps * d->kchunks};
@@ -1252,6 +1258,10 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
       d->p2_stage_region = (uint32_t)(pstage * st_);
       d->p2_smem_bytes = pstage * st_ + stg + 1024;
     }
+  }
+  if (halo == 3) {
+    CSE_REQUIRE(d->pair_ok, "conv_tc: pair h-halo mode does not fit (kc=%d bn=%d brick %dx%d)", kc, bn, brick[2], brick[3]);
+    d->tmap_b = d->tmap_bh;
   }
   d->smem_bytes = stage * stages + resident + staging + 1024;   // + alignment slack
   return CSE_OK;
@@ -1296,7 +1306,7 @@ int launch_conv_tc(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_count,
     // CTA-pair (cta_group::2) path for the small-N h-halo layers when there are enough tiles to fill every SM pair
     const long long tiles = (long long)n * d.tiles_d * d.tiles_h * d.tiles_w;
     const int pair_min = tc_tune.pair_min_tiles >= 0 ? tc_tune.pair_min_tiles : 2 * sm_count;
-    if (d.pair_ok && pair_min > 0 && tiles >= pair_min && ep.res == nullptr && ep.out1 == nullptr)
+    if (d.pair_ok && (d.halo == 3 || (pair_min > 0 && tiles >= pair_min)))
       return launch_conv_tc_pair(d, n, ep, sm_count, st);
   }
   ConvTcArgs a;

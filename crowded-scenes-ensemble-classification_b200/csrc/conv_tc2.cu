@@ -29,7 +29,7 @@ constexpr int P2_BAR_COUNT = (int)(P2_BAR_TMEM_EMPTY + 16u) / 8;
 
 struct ConvTc2Args {
   int Do, Ho, Wo, Co;
-  int kd, kh, sd, pd, ph, pw;
+  int kd, kh, kw, sd, pd, ph, pw;
   int kchunks, bn;
   int b_h, b_w, tiles_d, tiles_h, tiles_w;
   int n_batch, num_tiles;
@@ -42,6 +42,11 @@ struct ConvTc2Args {
   const float* scale0;
   const float* shift0;
   int relu0;
+  // residual add / second BN-ReLU output (pre-activation ResNet blocks, train.py:1346, 1278)
+  const float* scale1;
+  const float* shift1;
+  const void* res;
+  int res_ld, has_out1, relu1;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -118,7 +123,8 @@ __device__ __forceinline__ void tc2_mma_tap(uint32_t pred, uint32_t d_tmem, uint
 template <int KC, int EC>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh,
-                    const __grid_constant__ CUtensorMap tmap_o, const ConvTc2Args a) {
+                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o1,
+                    const ConvTc2Args a) {
   constexpr uint32_t ROW_BYTES = KC * 2;
   constexpr uint32_t SBO = 8 * ROW_BYTES;
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
@@ -127,7 +133,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[P2_BAR_COUNT];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_par[2][256];                  // scale0, shift0 (single N tile: loaded once)
+  __shared__ __align__(16) float s_par[4][256];                  // scale0, shift0, scale1, shift1 (single N tile: loaded once)
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -154,6 +160,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int c = min(i, a.Co - 1);
     s_par[0][i] = a.scale0 ? __ldg(a.scale0 + c) : 1.f;
     s_par[1][i] = a.shift0 ? __ldg(a.shift0 + c) : 0.f;
+    s_par[2][i] = a.scale1 ? __ldg(a.scale1 + c) : 1.f;
+    s_par[3][i] = a.shift1 ? __ldg(a.shift1 + c) : 0.f;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
@@ -169,7 +177,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __trap();
   }
 
-  const int nst = a.kd * a.kchunks;   // pipeline stages per tile
+  const int nst = a.kd * a.kw * a.kchunks;   // pipeline stages per tile: one per (fd, fw, channel chunk)
   auto decode = [&](int tile, int& tw, int& th, int& td, int& tn) {
     int mt = tile;
     tw = mt % a.tiles_w; mt /= a.tiles_w;
@@ -190,17 +198,18 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       decode(tile, tw, th, td, tn);
       const int iw0 = tw * a.b_w - a.pw, ih0 = th * a.b_h - a.ph, id0 = td * a.sd - a.pd;
       for (int fd = 0; fd < a.kd; ++fd)
-        for (int ch = 0; ch < a.kchunks; ++ch) {
-          mbar_wait(bar_base + P2_BAR_EMPTY + 8u * stage, phase ^ 1u);
-          const uint32_t fb = mapa_shared(bar_base + 8u * stage, 0u);   // the LEADER's full[stage]
-          if (rank == 0) mbar_expect_tx_p(leader, bar_base + 8u * stage, 2u * (a.a_bytes + a.bh_bytes));
-          const uint32_t sa = smem_base + stage * a.stage_bytes;
-          tma2_load_5d(leader, sa, &tmap_a, fb, ch * KC, iw0, ih0, id0 + fd, tn);
-          const int row0 = (fd * a.kchunks + ch) * a.kh * a.bn + (int)(rank * half_rows);
-          for (int fh = 0; fh < a.kh; ++fh)
-            tma2_load_2d(leader, sa + a.a_stage + fh * tap_bytes, &tmap_bh, fb, 0, row0 + fh * a.bn);
-          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
-        }
+        for (int fw = 0; fw < a.kw; ++fw)                     // kw > 1: the same haloed box, shifted by the W tap
+          for (int ch = 0; ch < a.kchunks; ++ch) {
+            mbar_wait(bar_base + P2_BAR_EMPTY + 8u * stage, phase ^ 1u);
+            const uint32_t fb = mapa_shared(bar_base + 8u * stage, 0u);   // the LEADER's full[stage]
+            if (rank == 0) mbar_expect_tx_p(leader, bar_base + 8u * stage, 2u * (a.a_bytes + a.bh_bytes));
+            const uint32_t sa = smem_base + stage * a.stage_bytes;
+            tma2_load_5d(leader, sa, &tmap_a, fb, ch * KC, iw0 + fw, ih0, id0 + fd, tn);
+            const int row0 = ((fd * a.kw + fw) * a.kchunks + ch) * a.kh * a.bn + (int)(rank * half_rows);
+            for (int fh = 0; fh < a.kh; ++fh)
+              tma2_load_2d(leader, sa + a.a_stage + fh * tap_bytes, &tmap_bh, fb, 0, row0 + fh * a.bn);
+            if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+          }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) ===============================
@@ -246,6 +255,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t swz = (EC == 64) ? (row & 7) : (EC == 32 ? ((row >> 1) & 3) : ((row >> 2) & 1));
     const bool has_scale0 = a.scale0 != nullptr;
     const bool relu0 = a.relu0 != 0;
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(a.res);
+    const bool fast = res == nullptr && !a.has_out1;
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     const uint32_t my_stg = smem_base + a.stage_region + (uint32_t)grp * (uint32_t)a.nslots * a.slot_bytes;
     const uint32_t bar_id = 1u + (uint32_t)grp;
     const uint32_t buf = (uint32_t)grp;                       // group g drains the pair's tiles g, g + 2, ... = buffer g
@@ -282,17 +294,64 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         const uint32_t s0 = my_stg + (uint32_t)slot * a.slot_bytes + (uint32_t)row * (EC * 2);
-        if (has_scale0) {
-          if (relu0) epi_chunk_fast<EC, true, true>(r, s_par, c0, s0, swz);
-          else epi_chunk_fast<EC, true, false>(r, s_par, c0, s0, swz);
+        if (fast) {
+          if (has_scale0) {
+            if (relu0) epi_chunk_fast<EC, true, true>(r, s_par, c0, s0, swz);
+            else epi_chunk_fast<EC, true, false>(r, s_par, c0, s0, swz);
+          } else {
+            if (relu0) epi_chunk_fast<EC, false, true>(r, s_par, c0, s0, swz);
+            else epi_chunk_fast<EC, false, false>(r, s_par, c0, s0, swz);
+          }
         } else {
-          if (relu0) epi_chunk_fast<EC, false, true>(r, s_par, c0, s0, swz);
-          else epi_chunk_fast<EC, false, false>(r, s_par, c0, s0, swz);
+          // residual add (+ second output y*scale1 + shift1 -> ReLU): the two tensors of a pre-activation ResNet block
+          const int ow = ow0 + (row % a.b_w), oh = oh0 + (row / a.b_w);
+          const bool use_res = res != nullptr && valid && row < a.b_h * a.b_w && ow < a.Wo && oh < a.Ho;
+          const long long pix = (((long long)tn * a.Do + td) * a.Ho + oh) * a.Wo + ow;
+#pragma unroll
+          for (int g8 = 0; g8 < EC / 8; ++g8) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float acc = __uint_as_float(r[g8 * 8 + j]);
+              y[j] = has_scale0 ? fmaf(acc, s_par[0][c0 + g8 * 8 + j], s_par[1][c0 + g8 * 8 + j]) : acc + s_par[1][c0 + g8 * 8 + j];
+            }
+            const int col = c0 + g8 * 8;
+            if (use_res && col < a.Co) {
+              const uint4 q0 = *reinterpret_cast<const uint4*>(res + pix * a.res_ld + col);
+              const __nv_bfloat16* e0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] += __bfloat162float(e0[j]);
+            }
+            uint32_t p[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+              if (relu0) h = __hmax2(h, zero2);
+              p[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + (((uint32_t)g8 ^ swz) << 4)), "r"(p[0]), "r"(p[1]),
+                         "r"(p[2]), "r"(p[3]) : "memory");
+            if (a.has_out1) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(
+                    fmaf(y[2 * j], s_par[2][c0 + g8 * 8 + 2 * j], s_par[3][c0 + g8 * 8 + 2 * j]),
+                    fmaf(y[2 * j + 1], s_par[2][c0 + g8 * 8 + 2 * j + 1], s_par[3][c0 + g8 * 8 + 2 * j + 1]));
+                if (a.relu1) h = __hmax2(h, zero2);
+                p[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + STG_BYTES + (((uint32_t)g8 ^ swz) << 4)), "r"(p[0]),
+                           "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
+            }
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (store_thread) {
-          if (valid && c0 < a.Co) tma_store_5d(&tmap_o, my_stg + (uint32_t)slot * a.slot_bytes, c0, ow0, oh0, td, tn);
+          if (valid && c0 < a.Co) {
+            tma_store_5d(&tmap_o, my_stg + (uint32_t)slot * a.slot_bytes, c0, ow0, oh0, td, tn);
+            if (a.has_out1) tma_store_5d(&tmap_o1, my_stg + (uint32_t)slot * a.slot_bytes + STG_BYTES, c0, ow0, oh0, td, tn);
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (++slot == a.nslots) slot = 0;
@@ -330,7 +389,7 @@ static int launch_pair_t(const ConvTcDesc& d, const ConvTc2Args& args, int grid,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CSE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<KC, EC>, d.tmap_a, d.tmap_bh, d.tmap_o0, args));
+  CSE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<KC, EC>, d.tmap_a, d.tmap_bh, d.tmap_o0, d.tmap_o1, args));
   return CSE_OK;
 }
 
@@ -338,7 +397,7 @@ int launch_conv_tc_pair(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_c
   const WinGeom& g = d.g;
   ConvTc2Args a;
   a.Do = g.Do; a.Ho = g.Ho; a.Wo = g.Wo; a.Co = g.Co;
-  a.kd = g.kd; a.kh = g.kh; a.sd = g.sd; a.pd = g.pd; a.ph = g.ph; a.pw = g.pw;
+  a.kd = g.kd; a.kh = g.kh; a.kw = g.kw; a.sd = g.sd; a.pd = g.pd; a.ph = g.ph; a.pw = g.pw;
   a.kchunks = d.kchunks; a.bn = d.bn;
   a.b_h = d.brick[2]; a.b_w = d.brick[3];
   a.tiles_d = d.tiles_d; a.tiles_h = d.tiles_h; a.tiles_w = d.tiles_w;
@@ -351,6 +410,8 @@ int launch_conv_tc_pair(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_c
   a.a_stage = d.a_stage; a.stage_bytes = d.p2_stage_bytes; a.stage_region = d.p2_stage_region;
   a.nslots = d.p2_nslots; a.slot_bytes = d.slot_bytes;
   a.scale0 = ep.scale0; a.shift0 = ep.shift0; a.relu0 = ep.relu0;
+  a.scale1 = ep.scale1; a.shift1 = ep.shift1; a.res = ep.res; a.res_ld = ep.res_ld;
+  a.has_out1 = ep.out1 != nullptr ? 1 : 0; a.relu1 = ep.relu1;
   const int pairs = (a.num_tiles + 1) / 2;
   int grid = 2 * (pairs < sm_count / 2 ? pairs : sm_count / 2);
   if (d.kc == 64) {

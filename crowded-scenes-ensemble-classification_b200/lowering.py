@@ -315,15 +315,27 @@ def pack_tc_weights_halo(kernel: np.ndarray, kc: int, bn: int, n_tiles: int) -> 
 
 
 def pack_tc_weights_hhalo(kernel: np.ndarray, kc: int, bn: int, n_tiles: int) -> np.ndarray:
-    """Keras [kd,kh,1,Ci,Co] -> [n_tile][fd][chunk][fh][bn][kc] bf16 bits (h-halo mode: the kh taps of one
-    (fd, channel chunk) are consecutive row blocks of one 2-D tensor with kc columns)."""
+    """Keras [kd,kh,kw,Ci,Co] -> [n_tile][fd][fw][chunk][fh][bn][kc] bf16 bits (h-halo modes: the kh taps of one
+    (fd, fw, channel chunk) are consecutive row blocks of one 2-D tensor with kc columns; kw = 1 for tc_halo = 2)."""
     kd, kh, kw, ci, co = kernel.shape
-    assert kw == 1
     nch = -(-ci // kc)
-    w = np.zeros((n_tiles * bn, kd, kh, nch * kc), np.float32)
-    w[:co, :, :, :ci] = kernel[:, :, 0, :, :].transpose(3, 0, 1, 2)
-    w = w.reshape(n_tiles, bn, kd, kh, nch, kc).transpose(0, 2, 4, 3, 1, 5)
+    w = np.zeros((n_tiles * bn, kd, kh, kw, nch * kc), np.float32)
+    w[:co, :, :, :, :ci] = kernel.transpose(4, 0, 1, 2, 3)
+    w = w.reshape(n_tiles, bn, kd, kh, kw, nch, kc).transpose(0, 2, 4, 5, 3, 1, 6)
     return to_bf16_bits(np.ascontiguousarray(w).reshape(-1, kc))
+
+
+def choose_brick_pair_halo(ho: int, wo: int, kh: int):
+    """Brick (1,1,h,w), w % 8 == 0, for the CTA-pair h-halo conv: fewest 128-row tiles per plane first (the layer is
+    MMA-bound there), then the fewest rows loaded.  -> (brick, fraction of the MMA rows that are real outputs)."""
+    best, best_key = None, None
+    for bw in range(8, min(_round_up(wo, 8), 128) + 1, 8):
+        for bh in range(1, 128 // bw + 1):
+            tiles = -(-ho // bh) * -(-wo // bw)
+            key = (tiles, tiles * (bh + kh - 1) * bw)
+            if best_key is None or key < best_key:
+                best, best_key = (1, 1, bh, bw), key
+    return best, ho * wo / float(best_key[0] * 128)
 
 
 def choose_brick_hhalo(ho: int, wo: int, kh: int) -> Tuple[int, int, int, int]:
@@ -359,8 +371,10 @@ class Lowerer:
                  crop=None, mean=None, scale=None, keep_all: bool = False, packed_stem: bool = True,
                  stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True,
                  balance_n: bool = True, pair_pool: bool = True, persist_input: bool = False,
-                 fuse_siblings: bool = True, s2d_depth: bool = True, input_dtypes=None, split_k: bool = True):
+                 fuse_siblings: bool = True, s2d_depth: bool = True, input_dtypes=None, split_k: bool = True,
+                 pair_halo: bool = True):
         self.s2d_depth = s2d_depth
+        self.pair_halo = pair_halo
         self.split_k = split_k
         # dtype of every external input: "u8" (decoded frames - the default) or "f32" (the dense flow of the
         # FarneBack_onTheFly TwoStream variant, train.py:294-332, evaluate_ensemble.py:1365-1386)
@@ -615,7 +629,19 @@ class Lowerer:
             bn, n_tiles = choose_bn(co, m_tiles if self.balance_n else 0)
             op.engine, op.w_dtype, op.kc, op.bn = rt.ENGINE_TCGEN05, rt.BF16, kc, bn
             hw_brick = choose_brick_hw(out_dims[1], out_dims[2], mult) if halo is True or halo == 1 else None
-            if (halo == 2 and kernel.shape[2] == 1 and tuple(s[1:]) == (1, 1) and kernel.shape[1] * bn <= 256
+            ph_brick, ph_eff = choose_brick_pair_halo(out_dims[1], out_dims[2], kernel.shape[1])
+            if (self.pair_halo and not halo and not pool and kernel.shape[2] > 1 and tuple(s[1:]) == (1, 1) and kc == 64
+                    and n_tiles == 1 and bn <= 128 and bn % 16 == 0 and (ph_eff >= 0.8 or self.pair_halo == "always")
+                    and (self.pair_halo == "always" or
+                         self.nb * out_dims[0] * -(-out_dims[1] // ph_brick[2]) * -(-out_dims[2] // ph_brick[3]) >= 2 * SM_COUNT)):
+                # 3x3x3 / stride-1 conv with a small single N tile and 64-channel chunks (R3D stage 1, C3D conv2): in the
+                # generic mode every tap re-loads its 16 KB A tile, and with N <= 128 that L2 -> shared-memory stream,
+                # not the MMA, sets the pace (R3D stage 1: 750 TFLOP/s).  CTA-pair h-halo mode: one haloed box per
+                # (fd, fw) feeds the kh taps, each CTA loads half of the weight rows, MMAs are 256 x N x 16.
+                op.halo = 3
+                op.brick = ph_brick
+                op.w_blob = self.blob(pack_tc_weights_hhalo(kernel, kc, bn, n_tiles))
+            elif (halo == 2 and kernel.shape[2] == 1 and tuple(s[1:]) == (1, 1) and kernel.shape[1] * bn <= 256
                     and (bn * kc * 2) % 1024 == 0 and not pool):
                 op.halo = 2
                 op.brick = choose_brick_hhalo(out_dims[1], out_dims[2], kernel.shape[1])

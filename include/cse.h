@@ -93,7 +93,9 @@ typedef struct cse_op {
   int32_t pool_dims[3];      /* D,H,W of the pooled output */
   int32_t pool_zero;         /* 1 = positions beyond the conv output count as 0 (ZeroPadding3D in front of the pool) */
   int32_t tc_halo;           /* TCGEN05: 1 = (kd,kh)-halo'd A brick, weights packed [n_tile][tap][bn][kc] (packed stem);
-                                2 = kh-halo'd A brick, one stage per (fd, chunk), weights [n_tile][fd][chunk][fh][bn][kc] */
+                                2 = kh-halo'd A brick, one stage per (fd, chunk), weights [n_tile][fd][chunk][fh][bn][kc];
+                                3 = the same with kw taps (one stage per (fd, fw, chunk), box shifted by fw), weights
+                                [fd][fw][chunk][fh][bn][kc], single N tile <= 128: CTA-pair (cta_group::2) kernel only */
   int32_t tc_pair_pool;      /* TCGEN05 pair-packed stem (C3D conv1 + pool1, train.py:1230-1233): in0 = pair-unrolled clip
                                 [n,T,H,W/2,16], GEMM row = 2 neighbouring output pixels, out_dims = D,H,W/2,2*Cout, weights
                                 [2*Cout][taps*16]; MaxPooling3D (1,2,2) is done in registers, pool_k = (1,2,1) in this

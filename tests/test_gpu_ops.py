@@ -430,6 +430,49 @@ def test_conv_tcgen05_split_k(dhw, cin, cout, k, nb, res):
     assert np.abs(outs[True] - outs[False]).max() <= 2.0 ** -7 * np.abs(outs[False]).max()
 
 
+@pytest.mark.parametrize("dhw,cin,cout,nb,res", [((4, 28, 28), 64, 64, 2, True), ((3, 12, 20), 64, 128, 3, False),
+                                                 ((2, 9, 13), 128, 64, 2, True), ((5, 16, 16), 64, 32, 1, True)])
+def test_conv_tcgen05_pair_halo_3x3x3(dhw, cin, cout, nb, res):
+    """3x3x3 / stride-1 convs with one small N tile on the CTA-pair kernel (tc_halo = 3: one haloed A box per (fd, fw)
+    feeds the kh taps, every CTA loads half of the weight rows, 256 x N x 16 MMAs) incl. the residual add + second
+    BN-ReLU output of the pre-activation ResNet blocks (R3D stage 1, train.py:1368-1393).  Ragged bricks, odd tile
+    counts, 1 and 2 channel chunks.  Against the oracle and against the generic lowering."""
+    def build(g):
+        x = g.input(dhw + (3,), name="in")
+        x = g.conv3d(x, cin, (1, 1, 1), (1, 1, 1), "same", True, "relu", name="pre")
+        y = g.conv3d(x, cout, (3, 3, 3), (1, 1, 1), "same", True, None, name="c")
+        if res:
+            sc = g.conv3d(x, cout, (1, 1, 1), (1, 1, 1), "same", True, None, name="sc")
+            y = g.add_([sc, y], name="add")
+        y = g.bn(y, scale=True, name="b")
+        g.relu(y, name="r")
+    outs = {}
+    xs = clips(4, nb, dhw + (3,))
+    for mode in ("always", False):
+        g, w, m = make_member(build, "bf16", nb, scale=[1 / 64.0] * 3, mean=[128.0] * 3, pair_halo=mode, split_k=False, balance_n=False)
+        op = [o for o in m.plan.ops if o.name == "c"][0]
+        assert op.engine == rt.ENGINE_TCGEN05 and op.halo == (3 if mode else 0), (op.halo, op.kc, op.bn)
+        run(m, [xs])
+        outs[mode] = m.read_tensor(m.plan.tensors["r"], nb)
+        if res:
+            outs[(mode, "add")] = m.read_tensor(m.plan.tensors["add"], nb)
+        if mode:
+            xin = torch.as_tensor(m.read_tensor(m.plan.tensors["pre"], nb), dtype=T64)
+            kern, bias = w["c"]
+            y = O.conv3d(xin, bf16_round(kern), torch.as_tensor(bias, dtype=T64), (1, 1, 1), "same")
+            if res:
+                ks, bs = w["sc"]
+                y = y + bf16_round(O.conv3d(xin, bf16_round(ks), torch.as_tensor(bs, dtype=T64), (1, 1, 1), "same").numpy())
+            y = O.relu(O.batchnorm(y, *[torch.as_tensor(a, dtype=T64) for a in w["b"]])).numpy()
+            err = np.abs(outs[mode] - y).max() / max(np.abs(y).max(), 1e-6)
+            assert err <= 2.0 ** -7, "rel err %g (bn=%d brick=%s)" % (err, op.bn, op.brick)
+        del m
+    # same products, same K order per tile (fd, fh, fw, chunk vs fd, fw, chunk, fh differ) -> equal up to fp32 summation order
+    assert np.abs(outs["always"] - outs[False]).max() <= 2.0 ** -7 * np.abs(outs[False]).max()
+    if res:
+        assert np.abs(outs[("always", "add")] - outs[(False, "add")]).max() <= 2.0 ** -7 * np.abs(outs[(False, "add")]).max()
+
+
 PAIR_POOL = [((4, 16, 16), 3, True), ((3, 12, 40), 3, True), ((5, 8, 24), 2, False), ((2, 34, 18), 3, True),
              ((3, 16, 112), 4, True)]
 
