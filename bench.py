@@ -267,7 +267,7 @@ def measure(name, args, steps, warmup, headline):
     host = [[torch.randint(0, 256, (batch,) + tuple(g.shape(n)), dtype=torch.uint8, generator=gen).pin_memory()
              for n in g.inputs] for g in graphs]
     dev_in = [[h.cuda() for h in hs] for hs in host]
-    in_bytes = sum(h.numel() for hs in host for h in hs)
+    in_bytes = ens.upload_bytes(host)          # unit-sharded steps upload only the clip ranges of this rank's units
     stream = torch.cuda.current_stream()
 
     def barrier():

@@ -303,6 +303,31 @@ class HeteroEnsemble:
         self._graphs.clear()
         self._seen_once.clear()
 
+    def upload_ranges(self):
+        """Unit-sharded step: per group, the merged clip ranges [(lo, hi)] this rank's units read (None = everything)."""
+        if getattr(self, "_unit_plan", None) is None:
+            return None
+        out = []
+        for ranges in self._unit_plan:
+            merged = []
+            for (lo, hi), _ in sorted(ranges):
+                if merged and lo <= merged[-1][1]:
+                    merged[-1] = (merged[-1][0], max(merged[-1][1], hi))
+                else:
+                    merged.append((lo, hi))
+            out.append(merged)
+        return out
+
+    def upload_bytes(self, host_group_inputs) -> int:
+        """Bytes one stream_host step copies host -> device (all inputs, or the owned clip ranges of a unit-sharded step)."""
+        needed = self.upload_ranges()
+        total = 0
+        for gi, hs in enumerate(host_group_inputs):
+            for h in hs:
+                per_clip = h[0].numel() * h.element_size()
+                total += per_clip * (h.shape[0] if needed is None else sum(hi - lo for lo, hi in needed[gi]))
+        return total
+
     def predict_units(self, group_inputs, collective: bool = True):
         """group_inputs as in predict_device (all n clips; only the owned ranges are read)."""
         n = group_inputs[0][0].shape[0]
@@ -357,14 +382,21 @@ class HeteroEnsemble:
             p = self._pipeline(first, depth)
             copy = p["copy"]
 
+            needed = self.upload_ranges()      # unit-sharded step: only the clip ranges this rank runs
+            self._last_upload_bytes = self.upload_bytes(first)
+
             def upload(k, batch):
                 with torch.cuda.stream(copy):
                     if p["used"][k]:
                         copy.wait_event(p["free"][k])     # the compute that read this buffer set has finished
                     p["start"][k].record(copy)
-                    for ds, hs in zip(p["bufs"][k], batch):
+                    for gi, (ds, hs) in enumerate(zip(p["bufs"][k], batch)):
                         for d, h in zip(ds, hs):
-                            d.copy_(h, non_blocking=True)
+                            if needed is None:
+                                d.copy_(h, non_blocking=True)
+                            else:
+                                for lo, hi in needed[gi]:
+                                    d[lo:hi].copy_(h[lo:hi], non_blocking=True)
                     p["ready"][k].record(copy)
 
             queue = []                     # buffer sets uploaded and not yet computed, in order
@@ -390,7 +422,8 @@ class HeteroEnsemble:
         if p is None or not any(p["used"]):
             return None
         ms = [p["start"][k].elapsed_time(p["ready"][k]) for k in range(p["depth"]) if p["used"][k]]
-        return p["bytes"] / (min(ms) / 1e3) / 1e9 if ms and min(ms) > 0 else None
+        nbytes = getattr(self, "_last_upload_bytes", None) or p["bytes"]
+        return nbytes / (min(ms) / 1e3) / 1e9 if ms and min(ms) > 0 else None
 
     def profile_ops(self, group_inputs, iters: int = 2):
         out = []
