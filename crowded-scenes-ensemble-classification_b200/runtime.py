@@ -23,7 +23,11 @@ EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_tune", "
            "cse_plan_finalize", "cse_plan_run", "cse_plan_run_from", "cse_plan_num_input_ops", "cse_plan_run_range",
            "cse_plan_num_ops",
            "cse_plan_last_launches", "cse_plan_destroy", "cse_preprocess", "cse_vote", "cse_vote_search",
-           "cse_assemble_clip"]
+           "cse_assemble_clip",
+           "cse_model_create", "cse_model_set_option", "cse_model_num_layers", "cse_model_layer_info", "cse_model_tensor_info",
+           "cse_model_set_weight", "cse_model_lower", "cse_model_num_ops", "cse_model_get_op", "cse_model_workspace_bytes",
+           "cse_model_weight_bytes", "cse_model_copy_weight_arena", "cse_model_logits_offset", "cse_model_probs_offset",
+           "cse_model_finalize", "cse_model_forward", "cse_model_forward_shared_input", "cse_model_destroy"]
 
 
 class CseOp(C.Structure):
@@ -84,6 +88,29 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cse_vote.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.cse_vote_search.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.cse_assemble_clip.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
+    lib.cse_model_create.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32, i32, i32, i32, i32]
+    lib.cse_model_set_option.argtypes = [vp, C.c_char_p, i32]
+    lib.cse_model_num_layers.argtypes = [vp]
+    lib.cse_model_layer_info.argtypes = [vp, i32, C.c_char_p, i32, C.POINTER(C.c_int)]
+    lib.cse_model_tensor_info.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(C.c_int), C.c_char_p, i32]
+    lib.cse_model_set_weight.argtypes = [vp, i32, i32, vp, C.POINTER(i64), i32]
+    lib.cse_model_lower.argtypes = [vp]
+    lib.cse_model_num_ops.argtypes = [vp]
+    lib.cse_model_get_op.argtypes = [vp, i32, C.POINTER(CseOp)]
+    lib.cse_model_workspace_bytes.argtypes = [vp]
+    lib.cse_model_workspace_bytes.restype = C.c_size_t
+    lib.cse_model_weight_bytes.argtypes = [vp]
+    lib.cse_model_weight_bytes.restype = C.c_size_t
+    lib.cse_model_copy_weight_arena.argtypes = [vp, vp, C.c_size_t]
+    lib.cse_model_logits_offset.argtypes = [vp]
+    lib.cse_model_logits_offset.restype = i64
+    lib.cse_model_probs_offset.argtypes = [vp]
+    lib.cse_model_probs_offset.restype = i64
+    lib.cse_model_finalize.argtypes = [vp, vp, C.c_size_t]
+    lib.cse_model_forward.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.cse_model_forward_shared_input.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.cse_model_destroy.argtypes = [vp]
+    lib.cse_model_destroy.restype = None
     for name in EXPORTS:
         getattr(lib, name)
     if lib.cse_abi_version() != ABI_VERSION:
@@ -199,3 +226,103 @@ def assemble_clip(frames_u8, t: int, h: int, w: int, out=None):
     assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == shape
     check(lib.cse_assemble_clip(frames_u8.data_ptr(), n, hs, ws, c, out.data_ptr(), t, h, w, current_stream_ptr()))
     return out
+
+
+# --------------------------------------------------------------------------- #
+# native member model (cse_model_*): graph construction + lowering inside the library
+# --------------------------------------------------------------------------- #
+class NativeModel:
+    """Thin handle on a ``cse_model``: what a non-Python binder does - name the architecture, hand over the Keras weight
+    tensors in ``model.layers`` order, finalize, forward.  (The Python product path lowers in ``lowering.py``;
+    ``tests/test_model_api.py`` holds both lowerings to byte-identical plans.)"""
+
+    def __init__(self, model_type: str, shape, nb_classes: int = 11, precision: str = "bf16", max_batch: int = 8,
+                 persist_input: bool = False, flow_input_f32: bool = False):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        t, h, w = (int(v) for v in shape[:3])
+        check(self.lib.cse_model_create(C.byref(self.handle), model_type.encode(), t, h, w, int(nb_classes),
+                                        BF16 if precision == "bf16" else F32, int(max_batch)))
+        self.nb_classes, self.max_batch = int(nb_classes), int(max_batch)
+        if persist_input:
+            check(self.lib.cse_model_set_option(self.handle, b"persist_input", 1))
+        if flow_input_f32:
+            check(self.lib.cse_model_set_option(self.handle, b"flow_input_f32", 1))
+
+    def layers(self):
+        """[(layer name, [(tensor name, shape), ...])] of the weighted layers in Keras model.layers order."""
+        out = []
+        for i in range(self.lib.cse_model_num_layers(self.handle)):
+            name = C.create_string_buffer(256)
+            nt = C.c_int()
+            check(self.lib.cse_model_layer_info(self.handle, i, name, 256, C.byref(nt)))
+            tensors = []
+            for j in range(nt.value):
+                dims = (C.c_int64 * 5)()
+                nd = C.c_int()
+                tn = C.create_string_buffer(256)
+                check(self.lib.cse_model_tensor_info(self.handle, i, j, dims, C.byref(nd), tn, 256))
+                tensors.append((tn.value.decode(), tuple(dims[k] for k in range(nd.value))))
+            out.append((name.value.decode(), tensors))
+        return out
+
+    def set_weights(self, weights):
+        """weights: {keras layer name: [arrays in Keras order]} (what hdf5.read_keras_weights + assign_positional give)."""
+        import numpy as np
+        for i, (lname, tensors) in enumerate(self.layers()):
+            arrs = weights[lname]
+            if len(arrs) != len(tensors):
+                raise CseError("layer %s: %d tensors expected, %d given" % (lname, len(tensors), len(arrs)))
+            for j, a in enumerate(arrs):
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                dims = (C.c_int64 * a.ndim)(*a.shape)
+                check(self.lib.cse_model_set_weight(self.handle, i, j, a.ctypes.data, dims, a.ndim))
+
+    def lower(self):
+        check(self.lib.cse_model_lower(self.handle))
+
+    def ops(self):
+        out = []
+        for i in range(self.lib.cse_model_num_ops(self.handle)):
+            s = CseOp()
+            check(self.lib.cse_model_get_op(self.handle, i, C.byref(s)))
+            out.append(s)
+        return out
+
+    def weight_arena(self):
+        import numpy as np
+        n = self.lib.cse_model_weight_bytes(self.handle)
+        buf = np.empty(n, np.uint8)
+        check(self.lib.cse_model_copy_weight_arena(self.handle, buf.ctypes.data, n))
+        return buf
+
+    def workspace_bytes(self) -> int:
+        return int(self.lib.cse_model_workspace_bytes(self.handle))
+
+    def finalize(self, shared_workspace=None):
+        require_cuda()
+        if shared_workspace is None:
+            check(self.lib.cse_model_finalize(self.handle, None, 0))
+        else:
+            ptr = (shared_workspace.data_ptr() + 1023) // 1024 * 1024
+            check(self.lib.cse_model_finalize(self.handle, ptr, shared_workspace.numel() - (ptr - shared_workspace.data_ptr())))
+            self._keep = shared_workspace
+
+    def forward(self, rgb, flow=None, shared_input: bool = False):
+        """rgb / flow: contiguous CUDA tensors [n,T,H,W,C] -> (logits, probs) fp32 CUDA tensors [n, nb_classes]."""
+        torch = require_cuda()
+        n = rgb.shape[0]
+        logits = torch.empty((n, self.nb_classes), dtype=torch.float32, device=rgb.device)
+        probs = torch.empty_like(logits)
+        fn = self.lib.cse_model_forward_shared_input if shared_input else self.lib.cse_model_forward
+        check(fn(self.handle, rgb.data_ptr(), flow.data_ptr() if flow is not None else None, n, logits.data_ptr(),
+                 probs.data_ptr(), current_stream_ptr()))
+        return logits, probs
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.cse_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

@@ -165,6 +165,48 @@ int  cse_plan_num_ops(const cse_plan* p);
 int  cse_plan_last_launches(const cse_plan* p);
 void cse_plan_destroy(cse_plan* p);
 
+/* ---- member model: graph construction and lowering inside the library --------------------------- */
+/* The same replacement of evaluate_load_model + predict_generator (train.py:1712-1772, evaluate_ensemble.py:1053-1056)
+ * one level up: the caller names the architecture and hands over the Keras weight tensors; fusion, engine / tile choice,
+ * BatchNormalization folding, weight re-packing and buffer planning happen in the library (csrc/model*.{h,cu}), so a
+ * binding in any language needs none of it.
+ *   model_type : "C3D" | "I3D" | "TWOSTREAM_I3D" | "R3D_18" | "R3D_34" | "R3D_50" | "R3D_101" | "R3D_152"  (train.py:1712-1772)
+ *   T, H, W    : clip geometry (define_input, train.py:1566-1616: 16x112x112 for C3D / R3D, 20x224x224 for I3D / TwoStream)
+ *   dtype      : CSE_BF16 = tcgen05 tensor-core path, CSE_F32 = CUDA-core reference-precision path
+ * Layers are addressed the way model.load_weights(path) (by_name = False) pairs them: index into the weighted layers in
+ * Keras' model.layers order, tensors within a layer in Keras order (Conv3D / Dense: kernel, bias; BatchNormalization:
+ * [gamma,] beta, moving_mean, moving_variance), host fp32 in Keras layout ([kd,kh,kw,Cin,Cout], [in,out]). */
+typedef struct cse_model cse_model;
+int  cse_model_create(cse_model** out, const char* model_type, int T, int H, int W, int nb_classes, int dtype, int max_batch);
+/* options before lowering: "persist_input" = 1 keeps the pre-processed clip alive after a forward pass (members of one
+ * fold share it, cse_model_forward_shared_input); "flow_input_f32" = 1: the flow clip is float32 (FarneBack_onTheFly) */
+int  cse_model_set_option(cse_model* m, const char* key, int value);
+int  cse_model_num_layers(const cse_model* m);
+int  cse_model_layer_info(const cse_model* m, int layer, char* name, int name_cap, int* n_tensors);
+int  cse_model_tensor_info(const cse_model* m, int layer, int tensor, int64_t* dims /*[5]*/, int* ndim, char* name, int name_cap);
+int  cse_model_set_weight(cse_model* m, int layer, int tensor, const float* host, const int64_t* dims, int ndim);
+/* Host-only lowering (no device needed): after it the plan can be inspected. */
+int  cse_model_lower(cse_model* m);
+int  cse_model_num_ops(const cse_model* m);
+int  cse_model_get_op(const cse_model* m, int i, cse_op* out);
+size_t cse_model_workspace_bytes(const cse_model* m);
+size_t cse_model_weight_bytes(const cse_model* m);
+int  cse_model_copy_weight_arena(const cse_model* m, void* host_dst, size_t cap);
+int64_t cse_model_logits_offset(const cse_model* m);
+int64_t cse_model_probs_offset(const cse_model* m);
+/* Lowers if needed, uploads the packed weights, allocates the workspace (or binds d_shared_workspace - members that run
+ * back to back on one stream may share one activation arena of max(cse_model_workspace_bytes) bytes, 1024-byte aligned) and
+ * builds the plan.  No allocation happens after this call. */
+int  cse_model_finalize(cse_model* m, void* d_shared_workspace, size_t shared_workspace_bytes);
+/* n <= max_batch clips: d_rgb uint8 [n,T,H,W,3]; d_flow uint8 (or float32) [n,T,H,W,2] for the two-stream model, else NULL.
+ * d_logits / d_probs: fp32 [n, nb_classes], either may be NULL.  Asynchronous on `stream`. */
+int  cse_model_forward(cse_model* m, const void* d_rgb, const void* d_flow, int n, float* d_logits, float* d_probs, void* stream);
+/* Same, skipping the pre-processing ops: the clip tensor written by the previous member of the fold (same architecture,
+ * same shared workspace, "persist_input") is reused. */
+int  cse_model_forward_shared_input(cse_model* m, const void* d_rgb, const void* d_flow, int n, float* d_logits, float* d_probs,
+                                    void* stream);
+void cse_model_destroy(cse_model* m);
+
 /* ---- stand-alone kernels ------------------------------------------------------------------- */
 /* Clip pre-processing, replaces the uint8 -> float32 store of train.py:466-478.  Reference
  * behaviour = crop none, mean 0, scale 1 (raw BGR 0..255).  Output channels c >= C are zero. */
