@@ -108,6 +108,28 @@ int cse_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   return CSE_OK;
 }
 
+int cse_malloc(void** d_ptr, size_t bytes) {
+  CSE_REQUIRE(d_ptr != nullptr, "malloc: NULL argument");
+  CSE_CUDA(cudaMalloc(d_ptr, bytes));
+  return CSE_OK;
+}
+int cse_free(void* d_ptr) {
+  CSE_CUDA(cudaFree(d_ptr));
+  return CSE_OK;
+}
+int cse_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream) {
+  CSE_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return CSE_OK;
+}
+int cse_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream) {
+  CSE_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return CSE_OK;
+}
+int cse_stream_synchronize(void* stream) {
+  CSE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return CSE_OK;
+}
+
 int cse_tune(const char* key, int value) {
   CSE_REQUIRE(key != nullptr, "tune: NULL key");
   int rc = conv_tc_tune(key, value);

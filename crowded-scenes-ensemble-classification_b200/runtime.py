@@ -19,7 +19,8 @@ ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 OP_PREPROCESS, OP_CONV3D, OP_MAXPOOL3D, OP_AVGPOOL3D, OP_AFFINE, OP_ADD, OP_SOFTMAX = 1, 2, 3, 4, 5, 6, 7
 OP_NAMES = {1: "preprocess", 2: "conv3d", 3: "maxpool3d", 4: "avgpool3d", 5: "affine", 6: "add", 7: "softmax"}
 
-EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_tune", "cse_plan_create", "cse_plan_add_op",
+EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_tune",
+           "cse_malloc", "cse_free", "cse_memcpy_h2d", "cse_memcpy_d2h", "cse_stream_synchronize", "cse_plan_create", "cse_plan_add_op",
            "cse_plan_finalize", "cse_plan_run", "cse_plan_run_from", "cse_plan_num_input_ops", "cse_plan_run_range",
            "cse_plan_num_ops",
            "cse_plan_last_launches", "cse_plan_destroy", "cse_preprocess", "cse_vote", "cse_vote_search",
@@ -72,6 +73,11 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cse_last_error.restype = C.c_char_p
     lib.cse_device_info.argtypes = [C.POINTER(C.c_int)] * 3
     lib.cse_tune.argtypes = [C.c_char_p, i32]
+    lib.cse_malloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.cse_free.argtypes = [vp]
+    lib.cse_memcpy_h2d.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.cse_memcpy_d2h.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.cse_stream_synchronize.argtypes = [vp]
     lib.cse_plan_create.argtypes = [C.POINTER(vp), i32, i32]
     lib.cse_plan_add_op.argtypes = [vp, C.POINTER(CseOp)]
     lib.cse_plan_finalize.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i64, i64]

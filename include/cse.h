@@ -136,6 +136,13 @@ int         cse_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * -1 = built-in default).  Unknown key -> CSE_ERR_INVALID. */
 int         cse_tune(const char* key, int value);
 
+/* ---- device memory helpers (for hosts that do not link the CUDA runtime themselves: plain C, ctypes, JNI ...) --- */
+int  cse_malloc(void** d_ptr, size_t bytes);                      /* cudaMalloc */
+int  cse_free(void* d_ptr);
+int  cse_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);    /* asynchronous on `stream` */
+int  cse_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+int  cse_stream_synchronize(void* stream);                        /* NULL = the default stream */
+
 /* ---- member plan: replaces evaluate_load_model + predict_generator ------------------------ */
 /* (train.py:1712-1772, evaluate_ensemble.py:1053-1056) */
 int  cse_plan_create(cse_plan** out, int max_batch, int nb_classes);

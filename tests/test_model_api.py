@@ -99,3 +99,18 @@ def test_native_model_forward_matches_member(mt, shape, n):
     ref2, _ = Member(g, w2, precision="bf16", max_batch=n).forward_device([x])
     torch.cuda.synchronize()
     assert torch.equal(l2, ref2)
+
+
+@pytest.mark.gpu
+def test_plain_c_host_builds_and_runs(tmp_path):
+    """tools/c_abi_demo.c: a plain C program (no Python, no torch, no CUDA headers) builds a 2-member C3D ensemble through
+    cse_model_* / cse_vote and checks the vote on the host."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "crowded-scenes-ensemble-classification_b200")
+    exe = str(tmp_path / "c_abi_demo")
+    subprocess.run(["gcc", "-O2", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "tools", "c_abi_demo.c"),
+                    "-L", libdir, "-lcse_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "c_abi_demo ok" in out.stdout, out.stdout + out.stderr
