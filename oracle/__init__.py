@@ -11,5 +11,7 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
   reference ships no tests / vectors / weights.
 * ``vote`` - numpy restatement of the soft vote + CSV text round trip.  PINNED against
   vectors produced by the reference's own functions (tools/make_golden_vote.py).
-* ``vote_c/`` - the same vote in plain C (compiled by ``__graft_entry__.build()``).
+* ``resize`` - numpy restatement of select_frames + OpenCV's 8-bit INTER_LINEAR resize.  PINNED against cv2 itself
+  and against the reference's own clip loaders (tools/make_golden_clips.py).
+* ``bench.py`` additionally uses ``vote`` for the post-timing self-check of the predictions it timed.
 """
