@@ -185,3 +185,62 @@ def test_global_ensemble(dataset, monkeypatch):
     for i in range(FOLDS):
         merged = os.path.join(ds["root"], "Results", "global_ensemble_probabilities_%s_TestFold%d_%dfolds.csv" % (mlist[0], i, FOLDS))
         assert os.path.isfile(merged)
+
+
+# --------------------------------------------------------------------------- Combine_ensembles under two ranks
+def _combine_worker(rank, world, port, root, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.chdir(root)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ordered = E.combine_ensembles(FOLDS, os.path.join(root, "Trained_models/"), ["C3D_SCRATCH", "R3D_18_SCRATCH", "I3D_PRETRAINED"],
+                                      os.path.join(root, "Results"))
+        with open(os.path.join(out_dir, "rank%d.txt" % rank), "w") as f:
+            f.write(repr([(tuple(k), round(float(v), 9)) for k, v in ordered.items()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_combine_ensembles_two_ranks(tmp_path):
+    """Combine_ensembles (evaluate_ensemble.py:1298-1326) under torchrun-style ranks: every rank must walk the 2^n - 1
+    model subsets in the same order (they meet in barriers; rank 0 alone writes the merged CSVs the others read).  The
+    member probabilities are cached CSVs (the reference's resume-by-file-name, :180-216), so only the lookup / merge /
+    vote path runs; both ranks share cuda:0 for the vote kernel."""
+    import socket
+    import torch.multiprocessing as mp
+    root = str(tmp_path)
+    rng = np.random.default_rng(3)
+    n_clips = 9
+    labels = [int(v) for v in rng.integers(0, NCLS, n_clips)]
+    for mt, tc in (("C3D", "_SCRATCH"), ("R3D_18", "_SCRATCH"), ("I3D", "_PRETRAINED")):
+        name, sub = E.get_ModelsNameAndTrainedModelsSubfolder(FOLDS, os.path.join(root, "Trained_models/"), mt, tc, "unbalanced",
+                                                              "TVL1_precomputed", "non_augmented", 0)
+        rows = []
+        for i in range(FOLDS):
+            d = os.path.join(sub, "TestSplit%d" % i)
+            os.makedirs(d)
+            pd.DataFrame([["clip%d" % k, "", "", labels[k]] for k in range(n_clips)],
+                         columns=["rgbclips_path", "x_axis_flowclips_path", "y_axis_flowclips_path", "class"]).to_csv(
+                os.path.join(d, "test.csv"))
+            for j in [k for k in range(FOLDS) if k != i]:
+                logits = rng.standard_normal((n_clips, NCLS)).astype(np.float32)
+                p = (np.exp(logits) / np.exp(logits).sum(1, keepdims=True)).astype(np.float32)
+                rows.append([os.path.join(d, "%s_split_test%d_val%d_weights" % (name, i, j)), E.convert_array2listofarrays(p)])
+        os.makedirs(os.path.join(root, "Results"), exist_ok=True)
+        pd.DataFrame(rows, columns=["path", "probabilities"]).to_csv(
+            os.path.join(root, "Results", "test_predicted_probabilities_%s.csv" % name))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_combine_worker, args=(2, port, root, root), nprocs=2, join=True)
+    a, b = (open(os.path.join(root, "rank%d.txt" % r)).read() for r in range(2))
+    assert a == b and a.count("(") >= 7          # 2^3 - 1 subsets, identical order and accuracies on both ranks
+    merged = [f for f in os.listdir(os.path.join(root, "Results")) if f.startswith("global_ensemble_summed_prediction_results_")]
+    assert len(merged) == 7
+    for f in merged:
+        for cell in pd.read_csv(os.path.join(root, "Results", f))["predictions"]:
+            assert len(ast.literal_eval(cell)) == n_clips
