@@ -213,8 +213,8 @@ def test_combine_ensembles_two_ranks(tmp_path):
     import torch.multiprocessing as mp
     root = str(tmp_path)
     rng = np.random.default_rng(3)
-    n_clips = 9
-    labels = [int(v) for v in rng.integers(0, NCLS, n_clips)]
+    n_clips = NCLS + 2          # nb_classes = len(set(test_data['class'])) (evaluate_ensemble.py:1028): every class occurs
+    labels = [int(v) for v in rng.permutation(NCLS)] + [3, 7]
     for mt, tc in (("C3D", "_SCRATCH"), ("R3D_18", "_SCRATCH"), ("I3D", "_PRETRAINED")):
         name, sub = E.get_ModelsNameAndTrainedModelsSubfolder(FOLDS, os.path.join(root, "Trained_models/"), mt, tc, "unbalanced",
                                                               "TVL1_precomputed", "non_augmented", 0)
