@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcse_b200.so")
-SOURCES = ["plan.cu", "ops.cu", "conv_tc.cu", "conv_tc2.cu", "vote.cu", "ingest.cu", "model.cu"]
+SOURCES = ["plan.cu", "ops.cu", "conv_tc.cu", "conv_tc2.cu", "vote.cu", "ingest.cu", "flow.cu", "model.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
               "-cudart", "static"]

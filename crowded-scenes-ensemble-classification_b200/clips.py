@@ -149,10 +149,38 @@ def farneback_flow_clip(frames: Sequence[np.ndarray], t: int, h: int, w: int) ->
     return out
 
 
-def load_farneback_twostream_clip(path: str, t: int, h: int, w: int):
-    """-> (uint8 [T,H,W,3] BGR, float32 [T,H,W,2] flow) of one video, decoded once."""
+def farneback_flow_clip_device(frames: Sequence[np.ndarray], t: int, h: int, w: int, device, frames_dev=None):
+    """farneback_flow_clip on the GPU -> float32 CUDA tensor [T,H,W,2].  The decoded frames are uploaded once (or taken
+    from `frames_dev`, uint8 [F,Hs,Ws,3]); frame scaling and gray conversion are bit-exact with cv2 (cse_resize_u8,
+    cse_bgr2gray, in the extractor's order: first frame resize -> gray, later frames gray -> resize), the flow of all
+    consecutive pairs is one cse_farneback call (bit-identical to oracle/farneback.py, within 1e-4 pixel of cv2 - its
+    SIMD summation order is not reproducible), select_frames is a strided slice, the final resize is cse_resize_linear_f32
+    (bit-exact with cv2.resize on floats)."""
+    import torch
+    from . import runtime as rt
+    if frames_dev is None:
+        frames_dev = torch.from_numpy(np.ascontiguousarray(np.stack(frames))).to(device)
+    if frames_dev.dim() != 4 or frames_dev.shape[-1] != 3 or frames_dev.shape[0] < 2:
+        raise ValueError("the Farneback extractor needs >= 2 BGR frames, got %r" % (tuple(frames_dev.shape),))
+    factor = 224 / max(frames_dev.shape[1:])
+    with torch.cuda.device(frames_dev.device):
+        first = rt.bgr2gray(rt.resize_u8(frames_dev[:1].contiguous(), fx=factor, fy=factor))
+        rest = rt.resize_u8(rt.bgr2gray(frames_dev[1:].contiguous()), fx=factor, fy=factor)
+        flows = rt.farneback(torch.cat([first, rest]))                      # [F-1,h',w',2]
+        step = max(1, flows.shape[0] // t)
+        sel = flows[::step][:t].contiguous()
+        if sel.shape[0] != t:
+            raise ValueError("flow clip has %d fields, expected %d" % (sel.shape[0], t))
+        return rt.resize_linear_f32(sel, h, w)
+
+
+def load_farneback_twostream_clip(path: str, t: int, h: int, w: int, device=None):
+    """-> (uint8 [T,H,W,3] BGR, float32 [T,H,W,2] flow) of one video, decoded once; with `device` both are CUDA tensors
+    and the flow is computed on that GPU."""
     frames = decode_frames(path)
-    return _assemble(frames, t, h, w), farneback_flow_clip(frames, t, h, w)
+    if device is None:
+        return _assemble(frames, t, h, w), farneback_flow_clip(frames, t, h, w)
+    return _assemble(frames, t, h, w, device), farneback_flow_clip_device(frames, t, h, w, device)
 
 
 class ClipSequence:
@@ -163,7 +191,8 @@ class ClipSequence:
                  augmentation_frequency=0, shuffle=False, device=None):
         """device: None = clips are assembled on the CPU and returned as numpy arrays (the reference's
         behaviour); a CUDA device = frames are resized on that GPU and x is returned as uint8 CUDA
-        tensors, which Member.predict / predict_generator take directly."""
+        tensors, which Member.predict / predict_generator take directly (FarneBack_onTheFly: the flow is computed on
+        that GPU too, cse_farneback, and returned as a float32 CUDA tensor)."""
         if shuffle or augmentation_status != "non_augmented":
             raise ValueError("evaluation clips are ordered and non-augmented")
         if optical_flow_status not in ("TVL1_precomputed", "FarneBack_onTheFly"):
@@ -194,8 +223,10 @@ class ClipSequence:
         for i in idx:
             frames = decode_frames(vd["rgbclips_path"].values[i])
             item = {"rgb": _select(frames, t)}
-            if self.farneback:                    # dense flow in the loader thread, like the reference's workers
+            if self.farneback and self.device is None:   # dense flow in the loader thread, like the reference's workers
                 item["flow"] = farneback_flow_clip(frames, t, self.input_shape[1], self.input_shape[2])
+            elif self.farneback:                          # computed on the GPU in assemble()
+                item["frames"] = frames
             elif self.model_type == "TWOSTREAM_I3D":
                 item["fx"] = _select(decode_frames(vd["x_axis_flowclips_path"].values[i], gray=True), t)
                 item["fy"] = _select(decode_frames(vd["y_axis_flowclips_path"].values[i], gray=True), t)
@@ -213,11 +244,9 @@ class ClipSequence:
         if tuple(rgb.shape[1:]) != (t, h, w, 3):
             raise ValueError("clips decode to %r, expected %r" % (tuple(rgb.shape[1:]), (t, h, w, 3)))
         if self.farneback:
-            flow = np.stack([r["flow"] for r in raw])
             if self.device is not None:
-                import torch
-                flow = torch.from_numpy(flow).to(self.device)
-            return [rgb, flow]
+                return [rgb, stack([farneback_flow_clip_device(r["frames"], t, h, w, self.device) for r in raw])]
+            return [rgb, np.stack([r["flow"] for r in raw])]
         if self.model_type == "TWOSTREAM_I3D":
             flow = stack([last(_finish(r["fx"], t, h, w, self.device), _finish(r["fy"], t, h, w, self.device))
                           for r in raw])

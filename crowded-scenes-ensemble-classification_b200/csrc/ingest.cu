@@ -76,3 +76,27 @@ extern "C" int cse_assemble_clip(const uint8_t* d_frames, int n_frames, int Hs, 
   CSE_CUDA(cudaGetLastError());
   return CSE_OK;
 }
+
+// cv2.resize(img, (W, H)) (fx = fy = 0) or cv2.resize(img, None, fx=fx, fy=fy) (W, H = cvRound(size * factor), taps from
+// 1 / factor - OpenCV uses the factor as given) for n uint8 images [n,Hs,Ws,C] -> [n,H,W,C]; the Farneback extractor's
+// frame scaling (train.py:300-312)
+extern "C" int cse_resize_u8(const uint8_t* d_src, int n, int Hs, int Ws, int C, uint8_t* d_dst, int H, int W, double fx, double fy,
+                             void* stream) {
+  CSE_REQUIRE(d_src && d_dst && n >= 1 && n <= 65535 && Hs >= 1 && Ws >= 1 && H >= 1 && H <= 65535 && W >= 1, "resize_u8: bad arguments");
+  CSE_REQUIRE(C >= 1 && C <= 4, "resize_u8: C=%d channels (1..4 supported)", C);
+  CSE_REQUIRE((fx > 0) == (fy > 0), "resize_u8: give both factors or neither");
+  if (fx > 0)
+    CSE_REQUIRE(W == (int)nearbyint(Ws * fx) && H == (int)nearbyint(Hs * fy), "resize_u8: %dx%d is not cvRound(%dx%d * (%g, %g))", H, W, Hs, Ws,
+                fy, fx);
+  const double scale_x = 1.0 / (fx > 0 ? fx : (double)W / (double)Ws), scale_y = 1.0 / (fy > 0 ? fy : (double)H / (double)Hs);
+  const dim3 grid((unsigned)((W + 127) / 128), (unsigned)H, (unsigned)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C) {
+    case 1: assemble_clip_kernel<1><<<grid, 128, 0, st>>>(d_src, 1, Hs, Ws, d_dst, H, W, scale_x, scale_y); break;
+    case 2: assemble_clip_kernel<2><<<grid, 128, 0, st>>>(d_src, 1, Hs, Ws, d_dst, H, W, scale_x, scale_y); break;
+    case 3: assemble_clip_kernel<3><<<grid, 128, 0, st>>>(d_src, 1, Hs, Ws, d_dst, H, W, scale_x, scale_y); break;
+    default: assemble_clip_kernel<4><<<grid, 128, 0, st>>>(d_src, 1, Hs, Ws, d_dst, H, W, scale_x, scale_y); break;
+  }
+  CSE_CUDA(cudaGetLastError());
+  return CSE_OK;
+}

@@ -24,7 +24,8 @@ EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_tune",
            "cse_plan_finalize", "cse_plan_run", "cse_plan_run_from", "cse_plan_num_input_ops", "cse_plan_run_range",
            "cse_plan_num_ops",
            "cse_plan_last_launches", "cse_plan_destroy", "cse_preprocess", "cse_vote", "cse_vote_search",
-           "cse_assemble_clip",
+           "cse_assemble_clip", "cse_resize_u8", "cse_bgr2gray", "cse_farneback_workspace_bytes", "cse_farneback",
+           "cse_resize_linear_f32",
            "cse_model_create", "cse_model_set_option", "cse_model_num_layers", "cse_model_layer_info", "cse_model_tensor_info",
            "cse_model_set_weight", "cse_model_lower", "cse_model_num_ops", "cse_model_get_op", "cse_model_workspace_bytes",
            "cse_model_weight_bytes", "cse_model_copy_weight_arena", "cse_model_logits_offset", "cse_model_probs_offset",
@@ -94,6 +95,12 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cse_vote.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.cse_vote_search.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.cse_assemble_clip.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
+    lib.cse_resize_u8.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, C.c_double, C.c_double, vp]
+    lib.cse_bgr2gray.argtypes = [vp, vp, C.c_longlong, vp]
+    lib.cse_farneback_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.cse_farneback_workspace_bytes.restype = C.c_size_t
+    lib.cse_farneback.argtypes = [vp, i32, i32, i32, C.c_double, i32, i32, i32, i32, C.c_double, vp, vp, C.c_size_t, vp]
+    lib.cse_resize_linear_f32.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp]
     lib.cse_model_create.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32, i32, i32, i32, i32]
     lib.cse_model_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.cse_model_num_layers.argtypes = [vp]
@@ -231,6 +238,59 @@ def assemble_clip(frames_u8, t: int, h: int, w: int, out=None):
         out = torch.empty(shape, dtype=torch.uint8, device=frames_u8.device)
     assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == shape
     check(lib.cse_assemble_clip(frames_u8.data_ptr(), n, hs, ws, c, out.data_ptr(), t, h, w, current_stream_ptr()))
+    return out
+
+
+def resize_u8(images_u8, h: int = None, w: int = None, fx: float = None, fy: float = None):
+    """uint8 device tensor [n, Hs, Ws(, C)] -> [n, h, w(, C)]: cv2.resize(img, (w, h)), or with fx / fy
+    cv2.resize(img, None, fx=fx, fy=fy) (size = cvRound(size * factor)), bit-exact with OpenCV's 8-bit INTER_LINEAR."""
+    torch = require_cuda()
+    lib = load_library()
+    assert images_u8.is_cuda and images_u8.dtype == torch.uint8 and images_u8.is_contiguous() and images_u8.dim() in (3, 4)
+    n, hs, ws = images_u8.shape[:3]
+    c = images_u8.shape[3] if images_u8.dim() == 4 else 1
+    if fx is not None:
+        h, w = round(hs * fy), round(ws * fx)          # cvRound: half to even, like Python's round
+    out = torch.empty((n, h, w) + ((c,) if images_u8.dim() == 4 else ()), dtype=torch.uint8, device=images_u8.device)
+    check(lib.cse_resize_u8(images_u8.data_ptr(), n, hs, ws, c, out.data_ptr(), h, w, float(fx or 0.0), float(fy or 0.0),
+                            current_stream_ptr()))
+    return out
+
+
+def bgr2gray(images_u8):
+    """uint8 device tensor [..., 3] (BGR) -> [...]: cv2.cvtColor(COLOR_BGR2GRAY), bit-exact."""
+    torch = require_cuda()
+    lib = load_library()
+    assert images_u8.is_cuda and images_u8.dtype == torch.uint8 and images_u8.is_contiguous() and images_u8.shape[-1] == 3
+    out = torch.empty(images_u8.shape[:-1], dtype=torch.uint8, device=images_u8.device)
+    check(lib.cse_bgr2gray(images_u8.data_ptr(), out.data_ptr(), out.numel(), current_stream_ptr()))
+    return out
+
+
+def farneback(gray_u8, pyr_scale=0.5, levels=5, winsize=11, iterations=5, poly_n=5, poly_sigma=1.1):
+    """uint8 device tensor [F, H, W] of gray frames -> float32 [F - 1, H, W, 2]: cv2.calcOpticalFlowFarneback between
+    consecutive frames (defaults = the reference's call, train.py:320-322)."""
+    torch = require_cuda()
+    lib = load_library()
+    assert gray_u8.is_cuda and gray_u8.dtype == torch.uint8 and gray_u8.is_contiguous() and gray_u8.dim() == 3
+    f, h, w = gray_u8.shape
+    flow = torch.empty((f - 1, h, w, 2), dtype=torch.float32, device=gray_u8.device)
+    nbytes = lib.cse_farneback_workspace_bytes(f, h, w)
+    work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=gray_u8.device)
+    check(lib.cse_farneback(gray_u8.data_ptr(), f, h, w, float(pyr_scale), int(levels), int(winsize), int(iterations), int(poly_n),
+                            float(poly_sigma), flow.data_ptr(), work.data_ptr(), work.numel() * 8, current_stream_ptr()))
+    return flow
+
+
+def resize_linear_f32(images_f32, h: int, w: int):
+    """float32 device tensor [n, Hs, Ws(, C)] -> [n, h, w(, C)]: cv2.resize(img, (w, h)) on CV_32F, bit-exact."""
+    torch = require_cuda()
+    lib = load_library()
+    assert images_f32.is_cuda and images_f32.dtype == torch.float32 and images_f32.is_contiguous() and images_f32.dim() in (3, 4)
+    n, hs, ws = images_f32.shape[:3]
+    c = images_f32.shape[3] if images_f32.dim() == 4 else 1
+    out = torch.empty((n, h, w) + ((c,) if images_f32.dim() == 4 else ()), dtype=torch.float32, device=images_f32.device)
+    check(lib.cse_resize_linear_f32(images_f32.data_ptr(), n, hs, ws, c, out.data_ptr(), h, w, current_stream_ptr()))
     return out
 
 

@@ -244,6 +244,27 @@ int  cse_vote_search(const double* d_probs /*[M,N,C]*/, const double* d_weights 
 int  cse_assemble_clip(const uint8_t* d_frames, int n_frames, int Hs, int Ws, int C,
                        uint8_t* d_clip, int T, int H, int W, void* stream);
 
+/* ---- on-the-fly dense optical flow: replaces opticalflow_FarneBack_extractor (train.py:294-332) ---- */
+/* cv2.resize on CV_8U images [n,Hs,Ws,C] -> [n,H,W,C], bit-identical: fx = fy = 0 is cv2.resize(img, (W, H));
+ * fx, fy > 0 is cv2.resize(img, None, fx=, fy=) (the caller passes H = cvRound(Hs * fy), W = cvRound(Ws * fx); the
+ * taps come from 1 / factor, as OpenCV computes them) - the extractor's frame scaling (train.py:300-312). */
+int  cse_resize_u8(const uint8_t* d_src, int n, int Hs, int Ws, int C, uint8_t* d_dst, int H, int W,
+                   double fx, double fy, void* stream);
+/* cv2.cvtColor(COLOR_BGR2GRAY) on CV_8U, bit-identical: `pixels` BGR triples -> gray bytes. */
+int  cse_bgr2gray(const uint8_t* d_bgr, uint8_t* d_gray, long long pixels, void* stream);
+/* cv2.calcOpticalFlowFarneback(prev, next, None, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags=0)
+ * between every pair of CONSECUTIVE frames of d_gray uint8 [n_frames,H,W] -> d_flow fp32 [n_frames-1,H,W,2] (dx, dy).
+ * Bit-identical to oracle/farneback.py (the restatement of OpenCV's algorithm), which agrees with cv2 itself to
+ * <= 1e-4 pixel (cv2's SIMD / IPP summation order is not reproducible).  d_work: cse_farneback_workspace_bytes(),
+ * 8-byte aligned.  The reference calls it with (0.5, 5, 11, 5, 5, 1.1). */
+size_t cse_farneback_workspace_bytes(int n_frames, int H, int W);
+int  cse_farneback(const uint8_t* d_gray, int n_frames, int H, int W, double pyr_scale, int levels, int winsize,
+                   int iterations, int poly_n, double poly_sigma, float* d_flow, void* d_work, size_t work_bytes,
+                   void* stream);
+/* cv2.resize on CV_32F images [n,Hs,Ws,C] -> [n,H,W,C] (INTER_LINEAR), bit-identical: the flow fields resized to the
+ * network's input size (get_twostream_videoclip, train.py:223-239). */
+int  cse_resize_linear_f32(const float* d_src, int n, int Hs, int Ws, int C, float* d_dst, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

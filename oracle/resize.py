@@ -34,9 +34,10 @@ def select_frame_indices(n_frames: int, frames_per_video: int):
     return list(range(0, n_frames, step))[:frames_per_video]
 
 
-def linear_taps(src: int, dst: int, horizontal: bool):
-    """-> (i0, i1, w0, w1): source indices and int16 fixed-point weights of every destination index."""
-    scale = 1.0 / (float(dst) / float(src))
+def linear_taps(src: int, dst: int, horizontal: bool, inv_scale: float = None):
+    """-> (i0, i1, w0, w1): source indices and int16 fixed-point weights of every destination index.  `inv_scale` is
+    the fx / fy of cv2.resize(img, None, fx=, fy=), which OpenCV uses as given instead of dst / src."""
+    scale = 1.0 / (float(dst) / float(src) if inv_scale is None else float(inv_scale))
     d = np.arange(dst, dtype=np.float64)
     f = ((d + 0.5) * scale - 0.5).astype(np.float32)
     s = np.floor(f).astype(np.int64)
@@ -53,14 +54,17 @@ def linear_taps(src: int, dst: int, horizontal: bool):
     return i0, i1, w0, w1
 
 
-def resize_linear_u8(img: np.ndarray, width: int, height: int) -> np.ndarray:
-    """cv2.resize(img, (width, height)) for uint8 [H,W] or [H,W,C] images, bit for bit."""
+def resize_linear_u8(img: np.ndarray, width: int = None, height: int = None, fx: float = None, fy: float = None) -> np.ndarray:
+    """cv2.resize(img, (width, height)), or cv2.resize(img, None, fx=fx, fy=fy) (output size = cvRound(size * factor),
+    taps from 1 / factor), for uint8 [H,W] or [H,W,C] images, bit for bit."""
     img = np.asarray(img)
     if img.dtype != np.uint8:
         raise TypeError("uint8 frames only")
     hs, ws = img.shape[:2]
-    x0, x1, ax0, ax1 = linear_taps(ws, width, True)
-    y0, y1, by0, by1 = linear_taps(hs, height, False)
+    if fx is not None:
+        width, height = int(np.rint(ws * fx)), int(np.rint(hs * fy))
+    x0, x1, ax0, ax1 = linear_taps(ws, width, True, fx)
+    y0, y1, by0, by1 = linear_taps(hs, height, False, fy)
     im = img.astype(np.int64).reshape(hs, ws, -1)
     rows = im[:, x0] * ax0[None, :, None] + im[:, x1] * ax1[None, :, None]
     r0, r1 = rows[y0], rows[y1]
