@@ -18,6 +18,7 @@ outside the accelerated path: clips can equally be pre-decoded ``.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence
 
 import numpy as np
@@ -204,6 +205,8 @@ class ClipSequence:
         self.num_classes = num_classes
         self.batch_size = int(batch_size)
         self.device = device
+        # CSE_CPU_FLOW=1 keeps the reference's own OpenCV flow (bit-identical to its extractor) with GPU clip assembly
+        self.flow_on_device = device is not None and os.environ.get("CSE_CPU_FLOW", "0") != "1"
         self.n = int(video_data.count().iloc[0]) if hasattr(video_data.count(), "iloc") else int(video_data.count()[0])
 
     def __len__(self):
@@ -223,7 +226,7 @@ class ClipSequence:
         for i in idx:
             frames = decode_frames(vd["rgbclips_path"].values[i])
             item = {"rgb": _select(frames, t)}
-            if self.farneback and self.device is None:   # dense flow in the loader thread, like the reference's workers
+            if self.farneback and not self.flow_on_device:   # dense flow in the loader thread, like the reference's workers
                 item["flow"] = farneback_flow_clip(frames, t, self.input_shape[1], self.input_shape[2])
             elif self.farneback:                          # computed on the GPU in assemble()
                 item["frames"] = frames
@@ -244,9 +247,13 @@ class ClipSequence:
         if tuple(rgb.shape[1:]) != (t, h, w, 3):
             raise ValueError("clips decode to %r, expected %r" % (tuple(rgb.shape[1:]), (t, h, w, 3)))
         if self.farneback:
-            if self.device is not None:
+            if self.flow_on_device:
                 return [rgb, stack([farneback_flow_clip_device(r["frames"], t, h, w, self.device) for r in raw])]
-            return [rgb, np.stack([r["flow"] for r in raw])]
+            flow = np.stack([r["flow"] for r in raw])
+            if self.device is not None:
+                import torch
+                flow = torch.from_numpy(flow).to(self.device)
+            return [rgb, flow]
         if self.model_type == "TWOSTREAM_I3D":
             flow = stack([last(_finish(r["fx"], t, h, w, self.device), _finish(r["fy"], t, h, w, self.device))
                           for r in raw])

@@ -226,6 +226,82 @@ __global__ void fb_box_h_solve_kernel(const double* __restrict__ vsum_, long lon
   flow[1] = (float)__dmul_rn(__dsub_rn(__dmul_rn(g22, h1), __dmul_rn(g12, h2)), idet);
 }
 
+// The two box sums and the solve in ONE pass over M for the reference's window (HALF = winsize / 2 = 5): a CTA owns a
+// 32 x 16 tile of flow vectors.  One thread per (column, channel) of the tile plus halo loads its 26 rows of M straight
+// into registers (coalesced: a row of the haloed tile is 210 consecutive floats; edge-replicated) and forms the 16 column
+// sums with a register window, so every M value is fetched once instead of 11 times; the row sums are formed the same way
+// per (row, channel, half row) from shared memory, then one thread per pixel scales and solves.  Each window is still
+// summed directly in double in the order r = -HALF .. HALF, so the result is bit-identical to the two generic kernels
+// above (which remain for other window sizes).  FP64-pipe work: 352 DADD per thread-column; the shared arrays are
+// padded (213 / 165 doubles per row) so that the 64-bit accesses of a half-warp fall into distinct banks.
+constexpr int FB_TW = 32, FB_TH = 16;
+template <int HALF>
+__global__ void __launch_bounds__(256)
+fb_box_solve_tile_kernel(const float* __restrict__ M_, long long Mstride, float* __restrict__ flow_, long long fstride, int H, int W, double scale) {
+  constexpr int WIN = 2 * HALF + 1, CW = (FB_TW + 2 * HALF) * 5, RH = FB_TH + 2 * HALF, VLD = CW + 3, SLD = FB_TW * 5 + 5;
+  constexpr int SEG = FB_TW / 2;
+  static_assert(CW <= 256 && FB_TH * 5 * 2 <= 256, "one thread per column-channel / per (row, channel, half row)");
+  __shared__ double V[FB_TH * VLD];                      // column sums [FB_TH][(FB_TW + 2 HALF) * 5]
+  __shared__ double S[FB_TH * SLD];                      // window sums [FB_TH][FB_TW * 5]
+  const int tid = threadIdx.x;
+  const int tiles_x = (W + FB_TW - 1) / FB_TW;
+  const int x0 = (blockIdx.x % tiles_x) * FB_TW, y0 = (blockIdx.x / tiles_x) * FB_TH;
+  if (tid < CW) {
+    const int tx = tid / 5, c = tid - tx * 5;
+    const float* src = M_ + blockIdx.y * Mstride + (long long)clampi(x0 + tx - HALF, 0, W - 1) * 5 + c;
+    float in[RH];
+#pragma unroll
+    for (int ty = 0; ty < RH; ++ty) in[ty] = src[(long long)clampi(y0 + ty - HALF, 0, H - 1) * W * 5];
+    double w[WIN];                                        // widened once on entry: conversions are a slow pipe
+#pragma unroll
+    for (int r = 0; r < WIN - 1; ++r) w[r + 1] = (double)in[r];
+#pragma unroll
+    for (int yo = 0; yo < FB_TH; ++yo) {
+#pragma unroll
+      for (int r = 0; r < WIN - 1; ++r) w[r] = w[r + 1];
+      w[WIN - 1] = (double)in[yo + WIN - 1];
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < WIN; ++r) s = __dadd_rn(s, w[r]);
+      V[yo * VLD + tid] = s;
+    }
+  }
+  __syncthreads();
+  if (tid < FB_TH * 5 * 2) {
+    const int c = tid % 5, ty = (tid / 5) % FB_TH, seg = tid / (5 * FB_TH);
+    const double* v = V + ty * VLD + seg * SEG * 5 + c;
+    double* out = S + ty * SLD + seg * SEG * 5 + c;
+    double w[WIN];
+#pragma unroll
+    for (int r = 0; r < WIN - 1; ++r) w[r + 1] = v[r * 5];
+#pragma unroll
+    for (int xo = 0; xo < SEG; ++xo) {
+#pragma unroll
+      for (int r = 0; r < WIN - 1; ++r) w[r] = w[r + 1];
+      w[WIN - 1] = v[(xo + WIN - 1) * 5];
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < WIN; ++r) s = __dadd_rn(s, w[r]);
+      out[xo * 5] = s;
+    }
+  }
+  __syncthreads();
+  float* flow = flow_ + blockIdx.y * fstride;
+#pragma unroll
+  for (int p = tid; p < FB_TH * FB_TW; p += 256) {
+    const int ty = p / FB_TW, tx = p % FB_TW, gy = y0 + ty, gx = x0 + tx;
+    if (gy >= H || gx >= W) continue;
+    const double* v = S + ty * SLD + tx * 5;
+    const double g11 = __dmul_rn(v[0], scale), g12 = __dmul_rn(v[1], scale), g22 = __dmul_rn(v[2], scale), h1 = __dmul_rn(v[3], scale),
+                 h2 = __dmul_rn(v[4], scale);
+    const double idet = __ddiv_rn(1.0, __dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3));
+    float2 o;
+    o.x = (float)__dmul_rn(__dsub_rn(__dmul_rn(g11, h2), __dmul_rn(g12, h1)), idet);
+    o.y = (float)__dmul_rn(__dsub_rn(__dmul_rn(g22, h1), __dmul_rn(g12, h2)), idet);
+    *reinterpret_cast<float2*>(flow + ((long long)gy * W + gx) * 2) = o;
+  }
+}
+
 // cv2.cvtColor(BGR2GRAY) on CV_8U: 15-bit fixed point (B 3735, G 19235, R 9798), round to nearest
 __global__ void fb_bgr2gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -375,8 +451,13 @@ int cse_farneback(const uint8_t* d_gray, int n_frames, int H, int W, double pyr_
     const int m = winsize / 2;
     const double scale = 1.0 / ((double)winsize * winsize);
     for (int it = 0; it < iterations; ++it) {
-      fb_box_v_kernel<<<dim3(fb_blocks(lpx * 5), P), FB_THREADS, 0, st>>>(M, lpx * 5, vsum, lpx * 5, L.h, L.w, m);
-      fb_box_h_solve_kernel<<<dim3(fb_blocks(lpx), P), FB_THREADS, 0, st>>>(vsum, lpx * 5, flow, lpx * 2, L.h, L.w, m, scale);
+      if (m == 5) {
+        const unsigned tiles = (unsigned)(((L.w + FB_TW - 1) / FB_TW) * ((L.h + FB_TH - 1) / FB_TH));
+        fb_box_solve_tile_kernel<5><<<dim3(tiles, P), 256, 0, st>>>(M, lpx * 5, flow, lpx * 2, L.h, L.w, scale);
+      } else {
+        fb_box_v_kernel<<<dim3(fb_blocks(lpx * 5), P), FB_THREADS, 0, st>>>(M, lpx * 5, vsum, lpx * 5, L.h, L.w, m);
+        fb_box_h_solve_kernel<<<dim3(fb_blocks(lpx), P), FB_THREADS, 0, st>>>(vsum, lpx * 5, flow, lpx * 2, L.h, L.w, m, scale);
+      }
       if (it < iterations - 1)
         fb_update_matrices_kernel<<<dim3(fb_blocks(lpx), P), FB_THREADS, 0, st>>>(R, lpx * 5, flow, lpx * 2, M, lpx * 5, L.h, L.w);
     }
