@@ -4,7 +4,10 @@ N synthetic MJPG videos on disk -> ClipSequence (cv2 decode, select_frames, resi
 GPU) -> 4-member C3D DeviceEnsemble -> probabilities, for several `workers` settings.  Shows where the
 time goes once the network itself runs at thousands of clips/s (decode is next).
 
-Usage: python tools/bench_ingest.py [--clips 96] [--size 320x240] [--frames 48]"""
+--flow: the FarneBack_onTheFly TwoStream-I3D variant instead (T = 20, 224 x 224, 4 members): the dense flow of every
+video computed by the loader threads with OpenCV like the reference (CSE_CPU_FLOW=1) or on the GPU (cse_farneback).
+
+Usage: python tools/bench_ingest.py [--clips 96] [--size 320x240] [--frames 48] [--flow]"""
 import argparse
 import os
 import sys
@@ -22,6 +25,7 @@ def main():
     ap.add_argument("--clips", type=int, default=96)
     ap.add_argument("--size", default="320x240")
     ap.add_argument("--frames", type=int, default=48)
+    ap.add_argument("--flow", action="store_true")
     args = ap.parse_args()
     import cv2
     import pandas as pd
@@ -44,6 +48,8 @@ def main():
         vw.release()
         paths.append(p)
     data = pd.DataFrame({"rgbclips_path": paths, "class": [k % 11 for k in range(args.clips)]})
+    if args.flow:
+        return flow_mode(args, paths, w, h)
     shape = (16, 112, 112, 3)
     g = G.build_model_graph("C3D", shape, 11)
     ens = DeviceEnsemble(g, [synthetic_weights(g, seed=100 + j) for j in range(4)], max_batch=32, micro_batch=32)
@@ -71,6 +77,36 @@ def main():
     print("decode only, one thread: %.1f clips/s" % dec)
     for k, v in out.items():
         print("%-28s %8.1f clips/s" % (k, v))
+
+
+def flow_mode(args, paths, w, h):
+    import pandas as pd
+    import torch
+    from cse_b200 import clips, ensemble as E, graph as G
+    from cse_b200.ensemble_runtime import DeviceEnsemble
+    from cse_b200.weights import synthetic_weights
+    data = pd.DataFrame({"rgbclips_path": paths, "x_axis_flowclips_path": [""] * len(paths), "y_axis_flowclips_path": [""] * len(paths),
+                         "class": [k % 11 for k in range(len(paths))]})
+    shape = (20, 224, 224, 0)
+    g = G.build_model_graph("TWOSTREAM_I3D", shape, 11)
+    ens = DeviceEnsemble(g, [synthetic_weights(g, seed=100 + j) for j in range(4)], max_batch=16, micro_batch=16, input_dtypes=("u8", "f32"))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out, probs = {}, {}
+    for flow, workers in (("cpu", 4), ("cpu", 16), ("gpu", 4), ("gpu", 16)):
+        os.environ["CSE_CPU_FLOW"] = "1" if flow == "cpu" else "0"
+        seq = clips.ClipSequence(data, "TWOSTREAM_I3D", shape, 11, batch_size=1, optical_flow_status="FarneBack_onTheFly", device=dev)
+        E._predict_members(ens, seq, min(4, seq.n), (None, 0, 1), 16, workers=workers)           # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        probs[flow] = E._predict_members(ens, seq, seq.n, (None, 0, 1), 16, workers=workers)
+        torch.cuda.synchronize()
+        out["flow=%s workers=%d" % (flow, workers)] = len(paths) / (time.perf_counter() - t0)
+    agree = float((probs["cpu"].sum(0).argmax(-1) == probs["gpu"].sum(0).argmax(-1)).mean())
+    print("videos: %d x %d frames of %dx%d MJPG -> TwoStream-I3D 20x224x224, 4 members, FarneBack_onTheFly; host cores: %d"
+          % (len(paths), args.frames, w, h, os.cpu_count()))
+    for k, v in out.items():
+        print("%-28s %8.1f clips/s" % (k, v))
+    print("max |p_gpu_flow - p_cpu_flow| = %.3g, soft-vote agreement %.4f" % (float(np.abs(probs["cpu"] - probs["gpu"]).max()), agree))
 
 
 if __name__ == "__main__":
