@@ -310,13 +310,28 @@ def measure(name, args, steps, warmup, headline):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
-        pred = step_resident()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    def time_resident():
+        """EXACTLY `steps` steps between two events; one more event per step only to tell a transient stall of the
+        box (host descheduled, a neighbour's NCCL bootstrap: one 2-GPU run showed a single 0.7 s gap in 20 steps of
+        65 ms) from the steady state: -> (last prediction, ms of the whole region, median ms of one step)."""
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record(stream)
+        for i in range(steps):
+            out = step_resident()
+            evs[i + 1].record(stream)
+        barrier()
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+        return out, evs[0].elapsed_time(evs[steps]), per[steps // 2]
+
+    pred, ms, med = time_resident()
+    remeasured = None
+    stalled = torch.tensor([1 if ms > 1.2 * med * steps else 0], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(stalled, op=dist.ReduceOp.MAX)
+    if int(stalled.item()):            # rejected and re-measured ONCE, like a throttled run; the second number stands
+        remeasured = {"first_ms_per_step": ms / steps, "median_step_ms": med, "why": "transient stall in the timed region"}
+        barrier()
+        pred, ms, med = time_resident()
     launches = ens.last_launches * steps
     clocks = sampler.stop() if sampler else None
     pred_resident = pred.cpu().numpy().copy()
@@ -416,7 +431,7 @@ def measure(name, args, steps, warmup, headline):
             "e2e": {"value": total_clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": batch * 4, "ms_per_step": ms_e2e / steps,
                     "h2d_copy_gbs": round(h2d_gbs, 1) if h2d_gbs else None, "pipeline_depth": 3},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "selfcheck": "ok",
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "selfcheck": "ok", "remeasured": remeasured,
         }
     del ens, dev_in, host
     import gc
@@ -450,7 +465,7 @@ def run_ours(args):
             r = measure(name, args, max(3, min(args.steps, 8)), 3, False)
             if r is not None:
                 extra.append({k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "selfcheck",
-                                                "gpu_launches")}
+                                                "gpu_launches", "remeasured")}
                              | {"workload": name, "config": r["config"],
                                 "roofline": {k: r["roofline"].get(k) for k in ("achieved", "peak", "unit", "frac", "kernel_share_of_step",
                                                                                "whole_step_model_tflops", "hbm_kernels", "top_ops", "note")}})
