@@ -325,11 +325,12 @@ def measure(name, args, steps, warmup, headline):
 
     pred, ms, med = time_resident()
     remeasured = None
-    stalled = torch.tensor([1 if ms > 1.2 * med * steps else 0], dtype=torch.int32, device="cuda")
+    stalled = torch.tensor([1.0 if ms > 1.2 * med * steps else 0.0, ms / steps, med], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(stalled, op=dist.ReduceOp.MAX)
-    if int(stalled.item()):            # rejected and re-measured ONCE, like a throttled run; the second number stands
-        remeasured = {"first_ms_per_step": ms / steps, "median_step_ms": med, "why": "transient stall in the timed region"}
+        dist.all_reduce(stalled, op=dist.ReduceOp.MAX)          # any rank's stall counts; the record holds the maxima over ranks
+    if float(stalled[0]) > 0:          # rejected and re-measured ONCE, like a throttled run; the second number stands
+        remeasured = {"first_ms_per_step": float(stalled[1]), "median_step_ms": float(stalled[2]),
+                      "why": "transient stall in the timed region (some rank: region > 1.2 x steps x its median step)"}
         barrier()
         pred, ms, med = time_resident()
     launches = ens.last_launches * steps
