@@ -1025,8 +1025,8 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   } else if (halo == 3) {
     // h-halo with kw taps, CTA-pair kernel only (conv_tc2.cu): one stage per (fd, fw, chunk), the haloed box shifted by fw
     CSE_REQUIRE(g.sh == 1 && g.sw == 1 && brick[0] == 1 && brick[1] == 1 && brick[3] % 8 == 0 && d->n_tiles_n == 1 &&
-                    bn <= 128 && !(pool && pool[0] > 0) && out_split == 0 && !pair_pool,
-                "conv_tc: pair h-halo mode needs stride 1 in H/W, brick (1,1,h,w%%8==0), a single N tile <= 128, no pool / split");
+                    bn <= 128 && !(pool && pool[0] > 0) && d->out_split2 == 0 && !pair_pool,
+                "conv_tc: pair h-halo mode needs stride 1 in H/W, brick (1,1,h,w%%8==0), a single N tile <= 128, no pool, at most one split");
   } else {
     CSE_REQUIRE(halo == 0, "conv_tc: unknown halo mode %d", halo);
   }
@@ -1230,7 +1230,7 @@ int conv_tc_build(ConvTcDesc* d, const void* in, const void* w_packed, void* out
   // 2-CTA cluster stages its own A box and HALF of the weight taps (bn/2 rows each)
   d->pair_ok = 0;
   if ((halo == 2 || halo == 3) && d->n_tiles_n == 1 && bn <= 128 && bn % 16 == 0 && (kc == 64 || kc == 32) && !pooled &&
-      out_split == 0 && !pair_pool && brick[0] == 1 && brick[1] == 1 &&
+      (out_split == 0 || (halo == 3 && d->out_split2 == 0)) && !pair_pool && brick[0] == 1 && brick[1] == 1 &&
       (((size_t)(bn / 2) * kc * 2) % (kc == 64 ? 1024 : 512)) == 0) {
     cuuint64_t dims[2] = {(cuuint64_t)kc, (cuuint64_t)bn * taps * d->kchunks};
     cuuint64_t strides[1] = {(cuuint64_t)kc * 2};

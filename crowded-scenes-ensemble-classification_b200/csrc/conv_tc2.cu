@@ -47,6 +47,7 @@ struct ConvTc2Args {
   const float* shift1;
   const void* res;
   int res_ld, has_out1, relu1;
+  int out_split;                   // > 0: columns >= out_split are stored through tmap_o1 (two members' stems in one GEMM)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -349,7 +350,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (store_thread) {
           if (valid && c0 < a.Co) {
-            tma_store_5d(&tmap_o, my_stg + (uint32_t)slot * a.slot_bytes, c0, ow0, oh0, td, tn);
+            if (a.out_split > 0 && c0 >= a.out_split) tma_store_5d(&tmap_o1, my_stg + (uint32_t)slot * a.slot_bytes, c0 - a.out_split, ow0, oh0, td, tn);
+            else tma_store_5d(&tmap_o, my_stg + (uint32_t)slot * a.slot_bytes, c0, ow0, oh0, td, tn);
             if (a.has_out1) tma_store_5d(&tmap_o1, my_stg + (uint32_t)slot * a.slot_bytes + STG_BYTES, c0, ow0, oh0, td, tn);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -412,6 +414,7 @@ int launch_conv_tc_pair(const ConvTcDesc& d, int n, const Epilogue& ep, int sm_c
   a.scale0 = ep.scale0; a.shift0 = ep.shift0; a.relu0 = ep.relu0;
   a.scale1 = ep.scale1; a.shift1 = ep.shift1; a.res = ep.res; a.res_ld = ep.res_ld;
   a.has_out1 = ep.out1 != nullptr ? 1 : 0; a.relu1 = ep.relu1;
+  a.out_split = d.out_split;
   const int pairs = (a.num_tiles + 1) / 2;
   int grid = 2 * (pairs < sm_count / 2 ? pairs : sm_count / 2);
   if (d.kc == 64) {

@@ -9,7 +9,7 @@ one [M, N, C] device buffer that the vote kernel reduces.  Members share one wor
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -32,11 +32,29 @@ class DeviceEnsemble:
         # all members share one workspace and one lowering, hence the offset of the pre-processed
         # clip tensor: it is written once per micro-batch by the first member and kept alive
         self.share_input = bool(lower_kw.pop("share_input", True)) and len(weight_sets) > 1
+        # fuse_stems: members 2k and 2k+1 read the same pre-processed clips, so their 64-filter 7x7x7 stems run as ONE
+        # tcgen05 GEMM with N = 128 (the N = 64 MMA is bound by the shared-memory operand port, not by the math):
+        # member 2k is lowered as the "lead" (its stem op carries the peer's stem weights and stores the peer's
+        # activations into a persistent buffer), member 2k+1 as the "follow" (no stem op; its first consumers read that
+        # buffer).  Results are bit-identical to the stand-alone members (same K order, per-column scale / shift).
+        from .lowering import Lowerer
+        plain = all(lower_kw.get(k, True) is True for k in ("tc", "s2d_stem", "stem_halo")) and "stem_role" not in lower_kw
+        self.fuse_stems = (bool(lower_kw.pop("fuse_stems", True)) and self.share_input and plain
+                           and Lowerer.stem_fusable(graph, precision))
         if self.share_input:
             lower_kw = dict(lower_kw, persist_input=True)
-        for w in weight_sets:
-            m = Member(graph, w, precision=precision, max_batch=self.micro_batch, device=device,
-                       workspace=shared, **lower_kw)
+        self._member_kw = dict(precision=precision, max_batch=self.micro_batch, device=device, **lower_kw)
+        self._weight_sets = list(weight_sets)
+        self._solo: Dict[int, Member] = {}
+        self.roles: List[Optional[str]] = []
+        for j, w in enumerate(weight_sets):
+            role_kw = {}
+            if self.fuse_stems and j % 2 == 0 and j + 1 < len(weight_sets):
+                role_kw = dict(stem_role="lead", stem_peer=weight_sets[j + 1])
+            elif self.fuse_stems and j % 2 == 1:
+                role_kw = dict(stem_role="follow")
+            self.roles.append(role_kw.get("stem_role"))
+            m = Member(graph, w, workspace=shared, **self._member_kw, **role_kw)
             shared = m.workspace
             self.members.append(m)
         self.device = self.members[0].device
@@ -82,15 +100,34 @@ class DeviceEnsemble:
             raise ValueError("clip range [%d, %d) exceeds max_batch %d" % (lo, lo + n, self.max_batch))
         launches = 0
         mb = self.micro_batch
+        ids = list(member_ids)
+        run = []          # a leader runs its fused plan only when its follower comes right after it; anyone else runs alone
+        for k, j in enumerate(ids):
+            paired = ((self.roles[j] == "lead" and k + 1 < len(ids) and ids[k + 1] == j + 1) or
+                      (self.roles[j] == "follow" and k > 0 and ids[k - 1] == j - 1))
+            run.append(self.members[j] if (paired or self.roles[j] is None) else self.solo_member(j))
         for i in range(0, n, mb):
             chunk = [x[i:i + mb] for x in inputs_u8]
-            for k, j in enumerate(member_ids):
-                m = self.members[j]
+            written = False              # the pre-processed clips of this chunk are in the shared workspace
+            for j, m in zip(ids, run):
+                shared = m.workspace is self.members[0].workspace
                 m.forward_device(chunk, self.logits[j, lo + i:lo + i + mb], self.probs[j, lo + i:lo + i + mb],
-                                 skip_input_ops=self.share_input and k > 0)
+                                 skip_input_ops=self.share_input and shared and written)
+                written = written or shared
                 launches += m.launches
         self.last_launches += launches
         return n
+
+    def solo_member(self, j: int) -> Member:
+        """Member j lowered stand-alone (its own stem op), for clip chunks its stem partner does not run on this GPU
+        (unit-sharded steps).  Built on first use - i.e. during warm-up, before any CUDA graph is captured - on the shared
+        workspace (the pre-processed clips sit at the same offset in every lowering of the ensemble)."""
+        if j not in self._solo:
+            try:
+                self._solo[j] = Member(self.graph, self._weight_sets[j], workspace=self.members[0].workspace, **self._member_kw)
+            except rt.CseError:          # a stand-alone plan that needs more room than the paired ones: its own arena,
+                self._solo[j] = Member(self.graph, self._weight_sets[j], **self._member_kw)      # its own pre-processing
+        return self._solo[j]
 
     def vote(self, n):
         probs = self.probs[:, :n].contiguous() if n != self.max_batch else self.probs
@@ -112,42 +149,49 @@ class DeviceEnsemble:
     # ---- profiling -------------------------------------------------------------- #
     def profile_ops(self, inputs_u8, iters: int = 2):
         """CUDA-event duration of every op launch (summed over members and micro-batches) for one
-        step; events are recorded on the stream the kernels are launched on."""
+        step; events are recorded on the stream the kernels are launched on.  Every member runs the ops of its own plan
+        (a stem leader's fused stem op counts the FLOPs of both members, its follower has no stem op); the rows are
+        keyed by op name in the order of member 0's plan."""
         torch = self.torch
         stream = torch.cuda.current_stream()
         n = inputs_u8[0].shape[0]
         mb = self.micro_batch
-        plan = self.members[0].plan
-        acc = [0.0] * len(plan.ops)
-        n_input_ops = 0
-        while n_input_ops < len(plan.ops) and plan.ops[n_input_ops].kind == rt.OP_PREPROCESS:
-            n_input_ops += 1
+        rows: Dict[str, dict] = {}
+        eng = {0: "", 1: "direct", 2: "tcgen05"}
+        for m in self.members:
+            for op in m.plan.ops:
+                key = op.name[:-5] if op.name.endswith("+peer") else op.name
+                rows.setdefault(key, {"name": key, "kind": rt.OP_NAMES[op.kind], "engine": eng[op.engine], "ms": 0.0,
+                                      "flops": 0.0, "bytes": 0.0})
         for it in range(iters + 1):
             evs = []
             for i in range(0, n, mb):
                 chunk = [x[i:i + mb] for x in inputs_u8]
-                for j, m in enumerate(self.members):
-                    for k in range(len(plan.ops)):
-                        if self.share_input and j > 0 and k < n_input_ops:
+                for jm, m in enumerate(self.members):
+                    for k, op in enumerate(m.plan.ops):
+                        if self.share_input and jm > 0 and op.kind == rt.OP_PREPROCESS:
                             continue            # pre-processed clips are shared with member 0
                         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         a.record(stream)
                         m.run_ops(chunk, k, k + 1)
                         b.record(stream)
-                        evs.append((k, a, b))
+                        evs.append((op, a, b))
             torch.cuda.synchronize()
             if it == 0:
                 continue            # warm-up pass
-            for k, a, b in evs:
-                acc[k] += a.elapsed_time(b)
-        out = []
-        eng = {0: "", 1: "direct", 2: "tcgen05"}
-        for k, op in enumerate(plan.ops):
-            shared = self.share_input and k < n_input_ops
-            out.append({"name": op.name, "kind": rt.OP_NAMES[op.kind], "engine": eng[op.engine],
-                        "ms": acc[k] / iters, "flops": op.flops * n * self.M,
-                        "bytes": _algorithmic_bytes(op) * n * (1 if shared else self.M)})
-        return out
+            for op, a, b in evs:
+                key = op.name[:-5] if op.name.endswith("+peer") else op.name
+                r = rows[key]
+                r["ms"] += a.elapsed_time(b) / iters
+        # algorithmic FLOPs / bytes of one step (n clips through every member), independent of the micro-batching
+        for jm, m in enumerate(self.members):
+            for op in m.plan.ops:
+                if self.share_input and jm > 0 and op.kind == rt.OP_PREPROCESS:
+                    continue
+                key = op.name[:-5] if op.name.endswith("+peer") else op.name
+                rows[key]["flops"] += op.flops * n
+                rows[key]["bytes"] += _algorithmic_bytes(op) * n
+        return list(rows.values())
 
 
 def _algorithmic_bytes(op) -> float:

@@ -372,7 +372,15 @@ class Lowerer:
                  stem_halo: bool = True, stem_unroll: bool = True, fuse_pool: bool = True, s2d_stem: bool = True,
                  balance_n: bool = True, pair_pool: bool = True, persist_input: bool = False,
                  fuse_siblings: bool = True, s2d_depth: bool = True, input_dtypes=None, split_k: bool = True,
-                 pair_halo: bool = True):
+                 pair_halo: bool = True, stem_role: Optional[str] = None, stem_peer=None):
+        # Two members of one ensemble read the same clips: their 7x7x7 stems can run as ONE GEMM with N = 2 x 64
+        # (DeviceEnsemble pairs members 2k / 2k+1).  "lead": this member's stem op carries the peer's stem weights
+        # (`stem_peer`, a weights dict) as columns 64..127 and stores them into a persistent peer buffer; "follow":
+        # this member has no stem op, its first consumers read that peer buffer (written by the leader just before).
+        if stem_role not in (None, "lead", "follow") or (stem_role == "lead") != (stem_peer is not None):
+            raise ValueError("stem_role is None, 'lead' (with stem_peer weights) or 'follow'")
+        self.stem_role, self.stem_peer = stem_role, stem_peer
+        self.persistent: List[Buf] = []
         self.s2d_depth = s2d_depth
         self.pair_halo = pair_halo
         self.split_k = split_k
@@ -482,7 +490,11 @@ class Lowerer:
             for op in self.ops:
                 if op.kind == rt.OP_PREPROCESS:
                     op.out0.buf.last = len(self.ops) + 1
-                    op.out0.buf.first = 0
+                    op.out0.buf.first = -2 if self.stem_role else 0
+        # peer stem buffers: placed right after the pre-processed clips (which every role of one ensemble places first,
+        # in the same order), before any plan-local buffer - the same offset in the leader's and the follower's plan
+        for b in self.persistent:
+            b.first, b.last = -1, len(self.ops) + 1
         if self.keep_all:           # tests: every intermediate stays readable after the run
             for b in self.bufs:
                 if b.last >= 0:
@@ -964,36 +976,90 @@ class Lowerer:
         pb = node.attrs["pads_before"]
         off_d, off_h, off_w = (p - 2 * ((p + 1) // 2) for p in pb)                 # 0 (pad even) or -1 (odd)
         depth = x.s2d == 2          # 2x2x2 cells: depth is regrouped like H and W (4 cell taps, stride 1)
-        k2 = np.zeros((4 if depth else 7, 4, 1, 4 * cell, co), np.float32)
-        for fd in range(k2.shape[0]):
-            for pd in range(2 if depth else 1):
-                td = 2 * fd + pd + off_d if depth else fd
-                if not 0 <= td < 7:
-                    continue
-                for fh in range(4):
-                    for ph in range(2):
-                        th = 2 * fh + ph + off_h
-                        if not 0 <= th < 7:
-                            continue
-                        for fw in range(4):
-                            for pw in range(2):
-                                tw = 2 * fw + pw + off_w
-                                if not 0 <= tw < 7:
-                                    continue
-                                c0 = fw * cell + ((pd * 2 + ph) * 2 + pw) * ci
-                                k2[fd, fh, 0, c0:c0 + ci, :] = kernel[td, th, tw, :, :]
+
+        def regroup(kern):
+            k2 = np.zeros((4 if depth else 7, 4, 1, 4 * cell, co), np.float32)
+            for fd in range(k2.shape[0]):
+                for pd in range(2 if depth else 1):
+                    td = 2 * fd + pd + off_d if depth else fd
+                    if not 0 <= td < 7:
+                        continue
+                    for fh in range(4):
+                        for ph in range(2):
+                            th = 2 * fh + ph + off_h
+                            if not 0 <= th < 7:
+                                continue
+                            for fw in range(4):
+                                for pw in range(2):
+                                    tw = 2 * fw + pw + off_w
+                                    if not 0 <= tw < 7:
+                                        continue
+                                    c0 = fw * cell + ((pd * 2 + ph) * 2 + pw) * ci
+                                    k2[fd, fh, 0, c0:c0 + ci, :] = kern[td, th, tw, :, :]
+            return k2
+
         view = TRef(x.buf, 0, 4 * cell, cell, x.dims, x.dtype, x.wpitch, x.wpad)
         if depth:
             k_, s_, pad_ = (4, 4, 1), (1, 1, 1), ((pb[0] + 1) // 2, (pb[1] + 1) // 2, 0)
         else:
             k_, s_, pad_ = (7, 4, 1), (2, 1, 1), (pb[0], (pb[1] + 1) // 2, 0)
-        op = self._conv_like(node.name, view, k2, bias, k_, s_, pad_, out_dims,
+        if self.stem_role is not None:
+            if not self.stem_fusable(self.g, self.precision) or not self.use_tc or not self.stem_halo:
+                raise RuntimeError("stem_role needs the bf16 tcgen05 path and a 64-filter 7x7x7 stem")
+            # the peer buffer exists in both roles and is placed before every plan-local buffer (lower()), so that the
+            # leader's store and the follower's loads agree on its address inside the shared workspace
+            pbuf = self.new_buf(final + ":peer", out_dims, co, self.act)
+            self.persistent.append(pbuf)
+            peer = TRef(pbuf, 0, co, co, tuple(out_dims), self.act)
+            if self.stem_role == "follow":
+                for l in layers:
+                    self.val[l] = peer
+                    self.done.add(l)
+                return
+            pw_ = self.stem_peer
+            pkernel = pw_[node.name][0]
+            pbias = pw_[node.name][1] if node.attrs["use_bias"] else None
+            bn_name = layers[1] if chain_bn is not None else None
+            folds = [fold_bn(bias, chain_bn[0] if chain_bn else None, chain_bn[1] if chain_bn else False, co),
+                     fold_bn(pbias, pw_[bn_name] if bn_name else None, chain_bn[1] if chain_bn else False, co)]
+            scale = np.concatenate([np.ones(co, np.float32) if f[0] is None else f[0] for f in folds])
+            shift = np.concatenate([np.zeros(co, np.float32) if f[1] is None else f[1] for f in folds])
+            kcat = np.concatenate([regroup(kernel), regroup(pkernel)], axis=-1)
+            o0 = self.out_ref(final, out_dims, co, self.act)
+            op = DevOp(rt.OP_CONV3D, node.name + "+peer", view, None, TRef(o0.buf, o0.coff, 2 * co, o0.ld, tuple(out_dims), self.act),
+                       peer, k=k_, s=s_, pad=pad_, relu0=int(relu), layers=tuple(layers), flops=2 * flops)
+            op.scale0, op.shift0 = self.fblob(scale), self.fblob(shift)
+            op.out_split = co
+            op.engine, op.w_dtype, op.kc, op.bn, op.halo = rt.ENGINE_TCGEN05, rt.BF16, choose_kc(view.C), 2 * co, 3
+            op.brick = choose_brick_hhalo(out_dims[1], out_dims[2], 4)
+            op.w_blob = self.blob(pack_tc_weights_hhalo(kcat, op.kc, op.bn, 1))
+            self.emit(op)
+            for l in layers:
+                self.val[l] = o0
+                self.done.add(l)
+            return
+        op = self._conv_like(node.name, view, regroup(kernel), bias, k_, s_, pad_, out_dims,
                              chain_bn, relu, final, layers, flops=flops, halo=2 if self.stem_halo else 0)
         if op.engine != rt.ENGINE_TCGEN05:
             raise RuntimeError("s2d stem must lower to the tcgen05 engine")
         for l in layers:
             self.val[l] = op.out0
             self.done.add(l)
+
+    @staticmethod
+    def stem_fusable(g: Graph, precision: str = "bf16") -> bool:
+        """True when every clip input of the graph feeds a 7x7x7 / stride-2 conv with 64 filters (I3D, TwoStream-I3D,
+        R3D): the stems DeviceEnsemble can run for two members at once."""
+        if precision != "bf16" or not g.inputs:
+            return False
+        for name in g.inputs:
+            cons = [n for n in g.nodes.values() if name in n.inputs]
+            if len(cons) != 1 or cons[0].op != "conv3d":
+                return False
+            a = cons[0].attrs
+            if tuple(a["k"]) != (7, 7, 7) or tuple(a["s"]) != (2, 2, 2) or a["filters"] != 64:
+                return False
+        return True
 
     def _fused_residual(self, node, add, x, kernel, bias, out_dims, flops):
         """residual conv + add (+ the next block's BN-ReLU as a second output)."""
