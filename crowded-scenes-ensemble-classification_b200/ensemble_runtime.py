@@ -341,7 +341,7 @@ class HeteroEnsemble:
             for m, lo, hi in my_units:
                 if m0 <= m < m0 + ens.M:
                     by_range.setdefault((lo, hi), []).append(m - m0)
-            plan.append(sorted(by_range.items()))
+            plan.append(sorted((r, sorted(ms)) for r, ms in by_range.items()))     # members ascending: stem pairs stay adjacent
             m0 += ens.M
         self._unit_plan, self.gather = plan, gather
         self._graphs.clear()

@@ -70,3 +70,44 @@ def test_s2d_stem_regrouping_equals_reference_conv(dhw, c, depth):
     np.testing.assert_allclose(got, exp, rtol=1e-9, atol=1e-6)
     # executed K of the regrouped conv
     assert kd * kh * view.C == (16 * 32 * c if pre.s2d == 2 else 28 * 4 * pre.ld)
+
+
+@pytest.mark.parametrize("mt,shape", [("I3D", (16, 64, 64, 3)), ("R3D_18", (16, 56, 56, 3)), ("TWOSTREAM_I3D", (16, 64, 64, 0))])
+def test_stem_roles_share_buffers(mt, shape):
+    """Stem fusion across two members (DeviceEnsemble(fuse_stems=True)): the leader's, the follower's and the stand-alone
+    lowering of one ensemble must place the pre-processed clips at the same workspace offsets, leader and follower must
+    agree on the peer buffer, the leader's stem is one N = 128 op with a column split, the follower has no stem op and
+    its first consumers read the peer buffer."""
+    from cse_b200 import runtime as rt
+    from cse_b200.lowering import Lowerer, lower
+    g = G.build_model_graph(mt, shape, 11)
+    assert Lowerer.stem_fusable(g) and not Lowerer.stem_fusable(g, "fp32")
+    w0, w1 = synthetic_weights(g, seed=1), synthetic_weights(g, seed=2)
+    solo = lower(g, w0, "bf16", 4, persist_input=True)
+    lead = lower(g, w0, "bf16", 4, persist_input=True, stem_role="lead", stem_peer=w1)
+    fol = lower(g, w1, "bf16", 4, persist_input=True, stem_role="follow")
+
+    def pre(p):
+        return [(o.name, o.out0.buf.offset, o.out0.buf.nbytes) for o in p.ops if o.kind == rt.OP_PREPROCESS]
+
+    def peer(p):
+        return sorted((b.name, b.offset, b.nbytes) for b in p.buffers if b.name.endswith(":peer"))
+
+    assert pre(solo) == pre(lead) == pre(fol)
+    assert peer(lead) == peer(fol) and len(peer(lead)) == len(g.inputs) and not peer(solo)
+    top_pre = max(o + n for _, o, n in pre(lead))
+    assert min(o for _, o, _ in peer(lead)) == top_pre                 # right behind the clips, before any plan-local buffer
+    stems = [o for o in lead.ops if o.name.endswith("+peer")]
+    assert len(stems) == len(g.inputs)
+    for o in stems:
+        assert (o.bn, o.out_split, o.halo, o.kc) == (128, 64, 3, 64) and o.out1.buf.name.endswith(":peer")
+        ref = [s for s in solo.ops if s.name == o.name[:-5]][0]
+        assert o.flops == 2 * ref.flops and o.k == ref.k and o.s == ref.s and o.pad == ref.pad and o.brick == ref.brick
+    assert len(fol.ops) == len(solo.ops) - len(g.inputs) and len(lead.ops) == len(solo.ops)
+    readers = [o for o in fol.ops if o.in0 is not None and o.in0.buf.name.endswith(":peer")]
+    assert len(readers) >= len(g.inputs)
+    assert lead.workspace_bytes >= max(fol.workspace_bytes, solo.workspace_bytes)
+    with pytest.raises(ValueError):
+        lower(g, w0, "bf16", 4, stem_role="lead")                      # a leader needs its peer's weights
+    cg = G.build_model_graph("C3D", (16, 56, 56, 3), 11)
+    assert not Lowerer.stem_fusable(cg)
