@@ -107,7 +107,9 @@ typedef struct cse_op {
                                 [out_split, out_split2 or Cout) -> the tensor at out1_off / out1_ld (branch 1a), starting at
                                 its channel 0; columns [out_split2, Cout) -> the tensor at out2_off / out2_ld (branch 2a)
                                 when out_split2 > 0.  One epilogue (scale0 / shift0 / relu0) for all columns; out1 is
-                                then NOT a second epilogue output */
+                                then NOT a second epilogue output.  With tc_halo = 3 and out_split = Cout / 2 = 64 the same
+                                fields carry the 7x7x7 stems of TWO ensemble members that read the same clips (train.py:1026,
+                                1481): columns [0, 64) -> this member's tensor, [64, 128) -> the peer member's */
   int32_t pre_s2d;           /* PREPROCESS: 1 = 2x2 space-to-depth over (H,W) for the stride-2 7x7x7 stems: out_dims =
                                 T, ceil(H/2), ceil(W/2); cell channel (ph*2+pw)*C + c, zero-padded to out_ld = 8/16 */
   int64_t in0_off, in1_off;  /* workspace byte offsets (-1 = none); in1 = residual for CONV3D, 2nd addend for ADD */
