@@ -23,6 +23,7 @@ def main():
     import json
     kw = json.loads(os.environ.get("CSE_LOWER_KW", "{}"))       # lowering experiments, as in bench.py
     ens = DeviceEnsemble(g, [synthetic_weights(g, seed=1 + j) for j in range(members)], max_batch=n, micro_batch=n, **kw)
+    torch.manual_seed(0)
     x = [torch.randint(0, 256, (n,) + tuple(g.shape(i)), dtype=torch.uint8, device="cuda") for i in g.inputs]
     ens.forward_members(x)
     torch.cuda.synchronize()
