@@ -77,3 +77,19 @@ def test_fused_stems_float_flow_and_profile():
     assert set(pa) == set(pf)
     for k in pa:
         assert pa[k]["flops"] == pytest.approx(pf[k]["flops"]) and pa[k]["bytes"] == pytest.approx(pf[k]["bytes"]), k
+
+
+@pytest.mark.parametrize("mt,shape", [("I3D", (64, 224, 224, 3)), ("TWOSTREAM_I3D", (20, 224, 224, 0)), ("R3D_34", (16, 112, 112, 3))])
+def test_fused_stems_bit_identical_baseline_shapes(mt, shape):
+    """BASELINE.json's own clip geometries (configs[2], the reference-true T = 20 TwoStream, the R3D-34 of configs[4])."""
+    g = G.build_model_graph(mt, shape, 11)
+    ws = [synthetic_weights(g, seed=30 + j) for j in range(2)]
+    x = clips_for(g, 3, 5)
+    plain = DeviceEnsemble(g, ws, max_batch=4, micro_batch=2, fuse_stems=False)
+    fused = DeviceEnsemble(g, ws, max_batch=4, micro_batch=2)
+    assert fused.roles == ["lead", "follow"]
+    plain.forward_members(x)
+    fused.forward_members(x)
+    torch.cuda.synchronize()
+    assert torch.equal(plain.logits[:, :3], fused.logits[:, :3]) and torch.equal(plain.probs[:, :3], fused.probs[:, :3])
+    assert torch.isfinite(fused.logits[:, :3]).all() and float(fused.logits[:, :3].abs().max()) > 0
