@@ -85,6 +85,20 @@ def test_flow_batch_equals_pairs_and_other_parameters():
         assert np.abs(got - ref).max() <= 1e-4
 
 
+def test_flow_long_video_matches_cv2():
+    """One call over a 33-frame 224 x 224 video (the I3D working size: three pyramid levels, 32 pairs on blockIdx.y):
+    spot-checked pairs against cv2 itself and against single-pair calls."""
+    rng = np.random.default_rng(7)
+    base = cv2.GaussianBlur(rng.integers(0, 256, (224 + 80, 224 + 80)).astype(np.float32), (9, 9), 2.5)
+    gray = np.stack([np.clip(base[i:i + 224, 2 * i:2 * i + 224], 0, 255).astype(np.uint8) for i in range(33)])
+    flow = rt.farneback(dev(gray)).cpu().numpy()
+    assert flow.shape == (32, 224, 224, 2)
+    for i in (0, 13, 31):
+        ref = cv2.calcOpticalFlowFarneback(gray[i], gray[i + 1], None, 0.5, 5, 11, 5, 5, 1.1, 0)
+        assert np.abs(ref).max() > 1.0 and np.abs(flow[i] - ref).max() <= 1e-4, (i, np.abs(flow[i] - ref).max())
+        assert np.array_equal(flow[i], rt.farneback(dev(gray[i:i + 2])).cpu().numpy()[0])
+
+
 def test_flow_argument_errors():
     lib = rt.load_library()
     g = dev(np.zeros((2, 64, 64), np.uint8))
