@@ -12,8 +12,12 @@ from cse_b200.weights import synthetic_weights                  # noqa: E402
 
 
 def main():
-    for mt, shape, n, pick in (("I3D", (64, 224, 224, 3), 16, lambda o: "+" in o.name and "Conv3d_3b_0a" in o.name),
-                               ("R3D_34", (16, 112, 112, 3), 128, lambda o: o.name == "conv3d_2")):
+    cases = [("I3D", (64, 224, 224, 3), 16, lambda o: "+" in o.name and "Conv3d_3b_0a" in o.name),
+             ("R3D_34", (16, 112, 112, 3), 128, lambda o: o.name == "conv3d_2")]
+    if len(sys.argv) > 1 and sys.argv[1] == "small":        # the small-Cin 3x3x3 convs of Inception branch 2b
+        cases = [("I3D", (64, 224, 224, 3), 16, lambda o: o.name.startswith("Conv3d_3c_2b_3x3")),
+                 ("I3D", (64, 224, 224, 3), 16, lambda o: o.name.startswith("Conv3d_3b_2b_3x3"))]
+    for mt, shape, n, pick in cases:
         g = G.build_model_graph(mt, shape, 11)
         m = Member(g, synthetic_weights(g, seed=1), precision="bf16", max_batch=n)
         x = [torch.randint(0, 256, (n,) + shape, dtype=torch.uint8, device="cuda")]
