@@ -16,9 +16,14 @@ namespace mdl {
 
 class Lowerer {
  public:
+  // stem_role: 0 = stand-alone, 1 = "lead" (the 7x7x7 stems carry the peer member's stem weights `peer_w` as columns 64..127
+  // and store them into a persistent peer buffer), 2 = "follow" (no stem op, the first consumers read that buffer) - the
+  // twin of lowering.Lowerer(stem_role=, stem_peer=)
   Lowerer(const Graph& g, const std::map<std::string, std::vector<Tensor>>& w, bool bf16, int max_batch, bool persist_input,
-          const std::vector<int>& input_f32)
-      : g_(g), w_(w), nb_(max_batch), persist_input_(persist_input), input_f32_(input_f32) {
+          const std::vector<int>& input_f32, int stem_role = 0, const std::map<std::string, std::vector<Tensor>>* peer_w = nullptr)
+      : g_(g), w_(w), nb_(max_batch), persist_input_(persist_input), input_f32_(input_f32), stem_role_(stem_role), peer_w_(peer_w) {
+    if (stem_role < 0 || stem_role > 2 || (stem_role == 1) != (peer_w != nullptr))
+      throw std::runtime_error("stem_role is 0, 1 = lead (with the peer's weights) or 2 = follow");
     act_ = bf16 ? CSE_BF16 : CSE_F32;
     use_tc_ = bf16;
     fuse_pool_ = bf16;
@@ -54,7 +59,10 @@ class Lowerer {
     if (probs_.valid()) bufs_[probs_.buf].last = (int)ops_.size() + 1;
     if (persist_input_)
       for (auto& op : ops_)
-        if (op.kind == CSE_OP_PREPROCESS) { bufs_[op.out0.buf].last = (int)ops_.size() + 1; bufs_[op.out0.buf].first = 0; }
+        if (op.kind == CSE_OP_PREPROCESS) { bufs_[op.out0.buf].last = (int)ops_.size() + 1; bufs_[op.out0.buf].first = stem_role_ ? -2 : 0; }
+    // peer stem buffers: right behind the pre-processed clips, before any plan-local buffer - the same offset in the
+    // leader's and the follower's plan
+    for (int b : persistent_) { bufs_[b].first = -1; bufs_[b].last = (int)ops_.size() + 1; }
     Plan plan;
     plan.workspace_bytes = assign_offsets();
     // weight arena: blobs at 256-byte aligned offsets, in creation order
@@ -76,6 +84,9 @@ class Lowerer {
   int nb_, act_;
   bool use_tc_, fuse_pool_, persist_input_;
   std::vector<int> input_f32_;
+  int stem_role_ = 0;
+  const std::map<std::string, std::vector<Tensor>>* peer_w_ = nullptr;
+  std::vector<int> persistent_;
   std::vector<DevOp> ops_;
   std::vector<Buf> bufs_;
   std::vector<Blob> blobs_;
@@ -553,31 +564,87 @@ class Lowerer {
     int off[3];
     for (int i = 0; i < 3; ++i) off[i] = pb[i] - 2 * ((pb[i] + 1) / 2);
     const bool depth = x.s2d == 2;
-    Kernel5 k2(depth ? 4 : 7, 4, 1, 4 * cell, co);
-    for (int fd = 0; fd < k2.kd; ++fd)
-      for (int pd = 0; pd < (depth ? 2 : 1); ++pd) {
-        const int td = depth ? 2 * fd + pd + off[0] : fd;
-        if (td < 0 || td >= 7) continue;
-        for (int fh = 0; fh < 4; ++fh)
-          for (int ph = 0; ph < 2; ++ph) {
-            const int th = 2 * fh + ph + off[1];
-            if (th < 0 || th >= 7) continue;
-            for (int fw = 0; fw < 4; ++fw)
-              for (int pw = 0; pw < 2; ++pw) {
-                const int tw = 2 * fw + pw + off[2];
-                if (tw < 0 || tw >= 7) continue;
-                const int c0 = fw * cell + ((pd * 2 + ph) * 2 + pw) * ci;
-                for (int c = 0; c < ci; ++c)
-                  for (int o = 0; o < co; ++o) k2.at(fd, fh, 0, c0 + c, o) = kernel.at(td, th, tw, c, o);
-              }
-          }
-      }
+    auto regroup = [&](const Kernel5& kern) {
+      Kernel5 k2(depth ? 4 : 7, 4, 1, 4 * cell, co);
+      for (int fd = 0; fd < k2.kd; ++fd)
+        for (int pd = 0; pd < (depth ? 2 : 1); ++pd) {
+          const int td = depth ? 2 * fd + pd + off[0] : fd;
+          if (td < 0 || td >= 7) continue;
+          for (int fh = 0; fh < 4; ++fh)
+            for (int ph = 0; ph < 2; ++ph) {
+              const int th = 2 * fh + ph + off[1];
+              if (th < 0 || th >= 7) continue;
+              for (int fw = 0; fw < 4; ++fw)
+                for (int pw = 0; pw < 2; ++pw) {
+                  const int tw = 2 * fw + pw + off[2];
+                  if (tw < 0 || tw >= 7) continue;
+                  const int c0 = fw * cell + ((pd * 2 + ph) * 2 + pw) * ci;
+                  for (int c = 0; c < ci; ++c)
+                    for (int o = 0; o < co; ++o) k2.at(fd, fh, 0, c0 + c, o) = kern.at(td, th, tw, c, o);
+                }
+            }
+        }
+      return k2;
+    };
     TRef view = make_ref(x.buf, 0, 4 * cell, cell, x.dims, x.dtype);
     view.wpitch = x.wpitch; view.wpad = x.wpad;
     int k[3], s[3], pads[3];
     if (depth) { k[0] = 4; k[1] = 4; k[2] = 1; s[0] = s[1] = s[2] = 1; pads[0] = (pb[0] + 1) / 2; pads[1] = (pb[1] + 1) / 2; pads[2] = 0; }
     else { k[0] = 7; k[1] = 4; k[2] = 1; s[0] = 2; s[1] = 1; s[2] = 1; pads[0] = pb[0]; pads[1] = (pb[1] + 1) / 2; pads[2] = 0; }
-    DevOp& op = conv_like(node.name, view, k2, bias, k, s, pads, out_dims, ch.bn, ch.bn_gamma, ch.relu, ch.final, act_, nullptr, nullptr, 2, nullptr);
+    if (stem_role_ != 0) {
+      if (!use_tc_ || co != 64) throw std::runtime_error("stem_role needs the bf16 tcgen05 path and a 64-filter 7x7x7 stem");
+      const int pbuf = new_buf(ch.final + ":peer", out_dims, co, act_);
+      persistent_.push_back(pbuf);
+      const TRef peer = make_ref(pbuf, 0, co, co, out_dims, act_);
+      if (stem_role_ == 2) { set_val(ch.layers, peer); return; }
+      auto pit = peer_w_->find(node.name);
+      if (pit == peer_w_->end()) throw std::runtime_error("peer weights for layer " + node.name + " missing");
+      const Tensor& pt = pit->second[0];
+      Kernel5 pkernel(pt.shape[0], pt.shape[1], pt.shape[2], pt.shape[3], pt.shape[4]);
+      pkernel.v = pt.data;
+      const std::vector<float>* pbias = node.use_bias ? &pit->second[1].data : nullptr;
+      const std::vector<Tensor>* pbn = nullptr;
+      if (ch.bn) {
+        auto bit = peer_w_->find(ch.layers[1]);
+        if (bit == peer_w_->end()) throw std::runtime_error("peer weights for layer " + ch.layers[1] + " missing");
+        pbn = &bit->second;
+      }
+      std::vector<float> scale, shift;
+      for (int who = 0; who < 2; ++who) {
+        std::vector<float> sc, sh;
+        bool hs, hsh;
+        fold_bn(who ? pbias : bias, who ? pbn : ch.bn, ch.bn_gamma, &sc, &sh, &hs, &hsh);
+        if (!hs) sc.assign(co, 1.f);
+        if (!hsh) sh.assign(co, 0.f);
+        scale.insert(scale.end(), sc.begin(), sc.end());
+        shift.insert(shift.end(), sh.begin(), sh.end());
+      }
+      const Kernel5 ka = regroup(kernel), kb = regroup(pkernel);
+      Kernel5 kcat(ka.kd, ka.kh, ka.kw, ka.ci, 2 * co);
+      for (int a = 0; a < ka.kd; ++a)
+        for (int b = 0; b < ka.kh; ++b)
+          for (int c = 0; c < ka.ci; ++c)
+            for (int o = 0; o < co; ++o) {
+              kcat.at(a, b, 0, c, o) = ka.at(a, b, 0, c, o);
+              kcat.at(a, b, 0, c, co + o) = kb.at(a, b, 0, c, o);
+            }
+      const TRef o0 = out_ref(ch.final, out_dims, co, act_);
+      DevOp op; op.kind = CSE_OP_CONV3D; op.name = node.name + "+peer"; op.in0 = view;
+      op.out0 = make_ref(o0.buf, o0.coff, 2 * co, o0.ld, out_dims, act_);
+      op.out1 = peer;
+      for (int i = 0; i < 3; ++i) { op.k[i] = k[i]; op.s[i] = s[i]; op.pad[i] = pads[i]; }
+      op.relu0 = ch.relu ? 1 : 0;
+      op.scale0 = blob(blob_f32(scale));
+      op.shift0 = blob(blob_f32(shift));
+      op.out_split = co;
+      op.engine = CSE_ENGINE_TCGEN05; op.w_dtype = CSE_BF16; op.kc = choose_kc(view.C); op.bn = 2 * co; op.halo = 3;
+      choose_brick_hhalo(out_dims[1], out_dims[2], 4, op.brick);
+      op.w_blob = blob(pack_tc_weights_hhalo(kcat, op.kc, op.bn, 1));
+      ops_.push_back(op);
+      set_val(ch.layers, o0);
+      return;
+    }
+    DevOp& op = conv_like(node.name, view, regroup(kernel), bias, k, s, pads, out_dims, ch.bn, ch.bn_gamma, ch.relu, ch.final, act_, nullptr, nullptr, 2, nullptr);
     if (op.engine != CSE_ENGINE_TCGEN05) throw std::runtime_error("s2d stem must lower to the tcgen05 engine");
     set_val(ch.layers, op.out0);
   }
@@ -802,6 +869,10 @@ struct cse_model {
   std::vector<std::string> layers;                                   // weighted layers, Keras model.layers order
   std::map<std::string, std::vector<cse::mdl::Tensor>> weights;
   bool bf16 = true, persist_input = false, lowered = false, finalized = false;
+  int stem_role = 0;                                                  // 0 stand-alone, 1 lead, 2 follow (cse_model_pair_stems)
+  std::map<std::string, std::vector<cse::mdl::Tensor>> peer_weights;  // lead: the follower's Keras-layout tensors
+  std::string model_type;
+  int T = 0, H = 0, W = 0;
   int max_batch = 0, nb_classes = 0;
   std::vector<int> input_f32;
   cse::mdl::Plan plan;
@@ -843,6 +914,7 @@ int cse_model_create(cse_model** out, const char* model_type, int T, int H, int 
       m->weights[l] = std::move(ts);
     }
     m->bf16 = dtype == CSE_BF16;
+    m->model_type = mt; m->T = T; m->H = H; m->W = W;
     m->max_batch = max_batch;
     m->nb_classes = nb_classes;
     m->input_f32.assign(m->graph.inputs.size(), 0);
@@ -904,6 +976,35 @@ int cse_model_set_weight(cse_model* m, int layer, int tensor, const float* host,
   return CSE_OK;
 }
 
+int cse_model_pair_stems(cse_model* lead, cse_model* follow) {
+  CSE_REQUIRE(lead && follow && lead != follow, "model_pair_stems: two distinct models");
+  CSE_REQUIRE(!lead->lowered && !follow->lowered, "model_pair_stems: pair the members before lowering them");
+  CSE_REQUIRE(lead->stem_role == 0 && follow->stem_role == 0, "model_pair_stems: a member is already paired");
+  CSE_REQUIRE(lead->model_type == follow->model_type && lead->T == follow->T && lead->H == follow->H && lead->W == follow->W &&
+                  lead->max_batch == follow->max_batch && lead->nb_classes == follow->nb_classes && lead->bf16 && follow->bf16 &&
+                  lead->input_f32 == follow->input_f32,
+              "model_pair_stems: both members must be the same bf16 architecture, clip shape, batch and input types");
+  // every clip input must feed a 64-filter 7x7x7 / stride-2 conv (I3D, TwoStream-I3D, R3D), cf. Lowerer.stem_fusable
+  for (auto& in : lead->graph.inputs) {
+    const mdl::Node* conv = nullptr;
+    int n_cons = 0;
+    for (auto& n : lead->graph.nodes)
+      for (auto& i : n.inputs)
+        if (i == in) { conv = &n; ++n_cons; }
+    CSE_REQUIRE(n_cons == 1 && conv->op == "conv3d" && conv->k[0] == 7 && conv->k[1] == 7 && conv->k[2] == 7 && conv->s[0] == 2 &&
+                    conv->s[1] == 2 && conv->s[2] == 2 && conv->filters == 64,
+                "model_pair_stems: %s has no 64-filter 7x7x7 / stride-2 stem", lead->model_type.c_str());
+  }
+  for (auto& l : follow->layers)
+    for (size_t i = 0; i < follow->weights[l].size(); ++i)
+      CSE_REQUIRE(follow->weights[l][i].set, "model_pair_stems: set the follower's weights first (tensor %zu of layer %s)", i, l.c_str());
+  lead->peer_weights = follow->weights;
+  lead->stem_role = 1;
+  follow->stem_role = 2;
+  lead->persist_input = follow->persist_input = true;
+  return CSE_OK;
+}
+
 int cse_model_lower(cse_model* m) {
   CSE_REQUIRE(m, "model_lower: NULL model");
   if (m->lowered) return CSE_OK;
@@ -911,10 +1012,12 @@ int cse_model_lower(cse_model* m) {
     for (size_t i = 0; i < m->weights[l].size(); ++i)
       CSE_REQUIRE(m->weights[l][i].set, "model_lower: tensor %zu of layer %s was never set", i, l.c_str());
   return guarded([&]() {
-    mdl::Lowerer low(m->graph, m->weights, m->bf16, m->max_batch, m->persist_input, m->input_f32);
+    mdl::Lowerer low(m->graph, m->weights, m->bf16, m->max_batch, m->persist_input, m->input_f32, m->stem_role,
+                     m->stem_role == 1 ? &m->peer_weights : nullptr);
     m->plan = low.lower();
     m->lowered = true;
     m->weights.clear();             // the packed arena replaces the Keras-layout copies
+    m->peer_weights.clear();
     return (int)CSE_OK;
   });
 }

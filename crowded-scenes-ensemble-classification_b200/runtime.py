@@ -27,7 +27,7 @@ EXPORTS = ["cse_abi_version", "cse_last_error", "cse_device_info", "cse_tune",
            "cse_assemble_clip", "cse_resize_u8", "cse_bgr2gray", "cse_farneback_workspace_bytes", "cse_farneback",
            "cse_resize_linear_f32",
            "cse_model_create", "cse_model_set_option", "cse_model_num_layers", "cse_model_layer_info", "cse_model_tensor_info",
-           "cse_model_set_weight", "cse_model_lower", "cse_model_num_ops", "cse_model_get_op", "cse_model_workspace_bytes",
+           "cse_model_set_weight", "cse_model_pair_stems", "cse_model_lower", "cse_model_num_ops", "cse_model_get_op", "cse_model_workspace_bytes",
            "cse_model_weight_bytes", "cse_model_copy_weight_arena", "cse_model_logits_offset", "cse_model_probs_offset",
            "cse_model_finalize", "cse_model_forward", "cse_model_forward_shared_input", "cse_model_destroy"]
 
@@ -108,6 +108,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cse_model_tensor_info.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(C.c_int), C.c_char_p, i32]
     lib.cse_model_set_weight.argtypes = [vp, i32, i32, vp, C.POINTER(i64), i32]
     lib.cse_model_lower.argtypes = [vp]
+    lib.cse_model_pair_stems.argtypes = [vp, vp]
     lib.cse_model_num_ops.argtypes = [vp]
     lib.cse_model_get_op.argtypes = [vp, i32, C.POINTER(CseOp)]
     lib.cse_model_workspace_bytes.argtypes = [vp]
@@ -343,6 +344,12 @@ class NativeModel:
                 a = np.ascontiguousarray(a, dtype=np.float32)
                 dims = (C.c_int64 * a.ndim)(*a.shape)
                 check(self.lib.cse_model_set_weight(self.handle, i, j, a.ctypes.data, dims, a.ndim))
+
+    def pair_stems(self, follow: "NativeModel"):
+        """This member leads, `follow` follows: one N = 128 stem GEMM for both (cse_model_pair_stems).  Weights of both are
+        set, neither is lowered; finalize both on one shared workspace, forward the leader first, the follower with
+        shared_input=True."""
+        check(self.lib.cse_model_pair_stems(self.handle, follow.handle))
 
     def lower(self):
         check(self.lib.cse_model_lower(self.handle))

@@ -194,6 +194,13 @@ int  cse_model_num_layers(const cse_model* m);
 int  cse_model_layer_info(const cse_model* m, int layer, char* name, int name_cap, int* n_tensors);
 int  cse_model_tensor_info(const cse_model* m, int layer, int tensor, int64_t* dims /*[5]*/, int* ndim, char* name, int name_cap);
 int  cse_model_set_weight(cse_model* m, int layer, int tensor, const float* host, const int64_t* dims, int ndim);
+/* Stem fusion across two members of one ensemble (I3D / TwoStream-I3D / R3D: 64-filter 7x7x7 stride-2 stems, train.py:1026,
+ * 999-1009, 1481).  Members of a fold read the same clips, so `lead` runs the stems of BOTH as one N = 128 GEMM and stores the
+ * follower's activations into a persistent buffer that `follow` reads instead of running its own stem (bit-identical results).
+ * Call after both members' weights are set and before either is lowered; it turns "persist_input" on for both.  Finalize both
+ * on ONE shared workspace of max(workspace_bytes) bytes, and per batch run cse_model_forward(lead, ...) first, then
+ * cse_model_forward_shared_input(follow, ...). */
+int  cse_model_pair_stems(cse_model* lead, cse_model* follow);
 /* Host-only lowering (no device needed): after it the plan can be inspected. */
 int  cse_model_lower(cse_model* m);
 int  cse_model_num_ops(const cse_model* m);

@@ -72,6 +72,72 @@ def test_native_options_and_errors():
     assert m2.lib.cse_model_set_weight(m2.handle, 0, 0, bad.ctypes.data, dims, 5) != 0      # conv1 has 64 filters
 
 
+@pytest.mark.parametrize("mt,shape,nb,f32flow", [("I3D", (64, 224, 224, 3), 4, False), ("R3D_34", (16, 112, 112, 3), 32, False),
+                                                 ("TWOSTREAM_I3D", (20, 224, 224, 0), 8, False), ("TWOSTREAM_I3D", (20, 96, 96, 0), 2, True)])
+def test_native_stem_pair_equals_python_roles(mt, shape, nb, f32flow):
+    """cse_model_pair_stems: the leader's and the follower's native plans equal lowering.lower(stem_role='lead' / 'follow')
+    field by field and byte by byte (the N = 128 stem op with the peer's columns, the persistent peer buffer's offset)."""
+    g = G.build_model_graph(mt, shape, 11)
+    w0, w1 = synthetic_weights(g, seed=5, nontrivial=True), synthetic_weights(g, seed=6, nontrivial=True)
+    kw = dict(flow_input_f32=True) if f32flow else {}
+    lead, fol = rt.NativeModel(mt, shape, 11, "bf16", nb, **kw), rt.NativeModel(mt, shape, 11, "bf16", nb, **kw)
+    lead.set_weights(w0)
+    fol.set_weights(w1)
+    lead.pair_stems(fol)
+    lead.lower()
+    fol.lower()
+    pkw = dict(persist_input=True, **(dict(input_dtypes=("u8", "f32")) if f32flow else {}))
+    for m, plan in ((lead, L.lower(g, w0, "bf16", nb, stem_role="lead", stem_peer=w1, **pkw)),
+                    (fol, L.lower(g, w1, "bf16", nb, stem_role="follow", **pkw))):
+        ref_ops, ops = plan.to_structs(), m.ops()
+        assert len(ops) == len(ref_ops)
+        for i, (a, b) in enumerate(zip(ops, ref_ops)):
+            fa, fb = _fields(a), _fields(b)
+            diff = {k: (fa[k], fb[k]) for k in fa if fa[k] != fb[k]}
+            assert not diff, "op %d (%s): native vs python %r" % (i, plan.ops[i].name, diff)
+        assert m.workspace_bytes() == plan.workspace_bytes
+        assert np.array_equal(m.weight_arena(), plan.weight_arena)
+    # pairing rules
+    c1, c2 = rt.NativeModel("C3D", (16, 48, 48, 3), 11, "bf16", 2), rt.NativeModel("C3D", (16, 48, 48, 3), 11, "bf16", 2)
+    cg = G.build_model_graph("C3D", (16, 48, 48, 3), 11)
+    c1.set_weights(synthetic_weights(cg, seed=1))
+    c2.set_weights(synthetic_weights(cg, seed=2))
+    with pytest.raises(rt.CseError):
+        c1.pair_stems(c2)                                # C3D has no 7x7x7 stem
+    a, b = rt.NativeModel(mt, shape, 11, "bf16", nb), rt.NativeModel(mt, shape, 11, "bf16", nb)
+    a.set_weights(w0)
+    with pytest.raises(rt.CseError):
+        a.pair_stems(b)                                  # the follower's weights are not set yet
+    with pytest.raises(rt.CseError):
+        lead.pair_stems(fol)                             # already lowered
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mt,shape,n", [("I3D", (20, 96, 96, 3), 2), ("R3D_18", (16, 64, 64, 3), 3)])
+def test_native_stem_pair_forward(mt, shape, n):
+    """A paired leader / follower on one shared workspace: bit-identical logits to the stand-alone Python members."""
+    import torch
+    from cse_b200.model import Member
+    g = G.build_model_graph(mt, shape, 11)
+    ws = [synthetic_weights(g, seed=31 + j, nontrivial=True) for j in range(2)]
+    x = torch.from_numpy(np.random.default_rng(2).integers(0, 256, (n,) + shape, dtype=np.uint8)).cuda()
+    refs = [Member(g, w, precision="bf16", max_batch=n).forward_device([x])[0] for w in ws]
+    lead, fol = rt.NativeModel(mt, shape, 11, "bf16", n), rt.NativeModel(mt, shape, 11, "bf16", n)
+    lead.set_weights(ws[0])
+    fol.set_weights(ws[1])
+    lead.pair_stems(fol)
+    lead.lower()
+    fol.lower()
+    shared = torch.empty(max(lead.workspace_bytes(), fol.workspace_bytes()) + 1024, dtype=torch.uint8, device="cuda")
+    lead.finalize(shared)
+    fol.finalize(shared)
+    for _ in range(2):                                   # twice: the peer buffer is rewritten by every leader pass
+        l0, _ = lead.forward(x)
+        l1, _ = fol.forward(x, shared_input=True)
+        torch.cuda.synchronize()
+        assert torch.equal(l0, refs[0]) and torch.equal(l1, refs[1])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mt,shape,n", [("C3D", (16, 112, 112, 3), 3), ("I3D", (20, 96, 96, 3), 2), ("R3D_18", (16, 64, 64, 3), 3)])
 def test_native_model_forward_matches_member(mt, shape, n):
