@@ -17,8 +17,8 @@
 // of several pixels (cv2's IPP / AVX2 blur sums in another order, its box filter is a sliding window of float-rounded
 // differences) - tests/test_oracle_farneback.py, tests/test_gpu_flow.py.  One call handles all the frames of a video:
 // blur / resize / polynomial expansion once per FRAME and level, matrices and solves per consecutive PAIR (blockIdx.y).
-// The loader-side cv2 path stays the default (bit-exact with the reference's golden, tests/test_clips_farneback.py);
-// this is its GPU alternative (clips.ClipSequence(..., device=cuda) computes the flow on that device).
+// clips.ClipSequence(..., device=cuda) - the evaluation path's default - computes the flow here; CSE_CPU_FLOW=1 keeps the
+// loader-side cv2 calls of the reference (bit-exact with its golden, tests/test_clips_farneback.py).
 #include <math.h>
 
 #include <vector>
