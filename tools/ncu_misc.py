@@ -17,6 +17,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "small":        # the small-Cin 3x3x3 convs of Inception branch 2b
         cases = [("I3D", (64, 224, 224, 3), 16, lambda o: o.name.startswith("Conv3d_3c_2b_3x3")),
                  ("I3D", (64, 224, 224, 3), 16, lambda o: o.name.startswith("Conv3d_3b_2b_3x3"))]
+    if len(sys.argv) > 1 and sys.argv[1] == "pool":         # the 3x3x3 / stride-1 'same' pools of the Inception branches
+        cases = [("I3D", (64, 224, 224, 3), 32, lambda o: o.name.startswith("MaxPool2d_3c_3a")),
+                 ("I3D", (64, 224, 224, 3), 32, lambda o: o.name.startswith("MaxPool2d_4c_3a"))]
     for mt, shape, n, pick in cases:
         g = G.build_model_graph(mt, shape, 11)
         m = Member(g, synthetic_weights(g, seed=1), precision="bf16", max_batch=n)
